@@ -1,0 +1,312 @@
+"""ctypes binding of libbirp_b200.so (include/birp_b200.h).
+
+This is the same C ABI the reference's C++ code would link against;
+Python is only used here to drive it from the tests and from bench.py.  There is no
+fallback: if the shared library is missing or no CUDA device is usable, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libbirp_b200.so"
+HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
+
+BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
+NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
+
+FRAME_DTYPE = np.dtype(
+    [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
+     ("aspect", "<f4"), ("sun_angle", "<f4")]
+)
+assert FRAME_DTYPE.itemsize == 64
+
+CMEM_FIELDS = [
+    "p0", "p1", "p2", "p3", "bs", "A1", "A2", "B", "alpha", "beta", "ay_bs", "az_bs", "r0_lin", "charlie",
+    "dn", "ds", "theta_n", "theta_s", "a5", "a21", "beta_c0", "beta_c1", "beta_c2", "beta_c3",
+    "pressure_dynamic", "pressure_magnetic", "density",
+]
+CMEM_DTYPE = np.dtype([(n, "<f4") for n in CMEM_FIELDS])
+assert CMEM_DTYPE.itemsize == 27 * 4
+
+
+class BirpError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"birp_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/birp_b200.h declares
+SIGNATURES = {
+    "birp_version": (C.c_char_p, []),
+    "birp_last_error": (C.c_char_p, []),
+    "birp_device_count": (C.c_int, [_i32p]),
+    "birp_set_device": (C.c_int, [C.c_int]),
+    "birp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "birp_host_free": (C.c_int, [_vp]),
+    "birp_frame_setup": (C.c_int, [_f32p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
+    "birp_ray_table": (C.c_int, [C.c_int, C.c_int, _f32p, _f32p]),
+    "birp_cmem_init": (C.c_int, [C.c_int, _i32p, C.c_int, _i32p, C.c_float, C.c_float, C.c_int, C.c_int,
+                                 C.c_int] + [C.c_float] * 9 + [_vp]),
+    "birp_cube_upload": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.POINTER(_vp)]),
+    "birp_cube_upload_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _vp, C.POINTER(_vp)]),
+    "birp_cube_free": (None, [_vp]),
+    "birp_render_cube": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
+    "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
+    "birp_accumulate": (C.c_int, [_vp, C.c_long, C.c_int, C.c_float, C.c_int, _vp]),
+    "birp_sample_cube": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
+    "birp_sample_cmem": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
+    "birp_render_cube_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
+    "birp_render_cmem_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
+    "birp_check_device_status": (C.c_int, [_vp]),
+    "birp_launch_count": (C.c_ulonglong, []),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libbirp_b200.so (built in-tree by `make -C birp_cpp_b200/csrc` / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C {_HERE / 'csrc'}` "
+                "(birp_cpp_b200 has no CPU or pure-Python path)"
+            )
+        handle = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != BIRP_OK:
+        raise BirpError(rc, lib().birp_last_error().decode(errors="replace"))
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+# ------------------------------------------------------------------ host-side setup
+def frame_setup(pos, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int) -> np.ndarray:
+    """One birp_frame record (FRAME_DTYPE scalar array of shape (1,))."""
+    out = np.zeros(1, dtype=FRAME_DTYPE)
+    p = _f32(pos, (3,))
+    _check(lib().birp_frame_setup(p.ctypes.data_as(_f32p), aim_x, fov_x_deg, fov_y_deg, W, H, _ptr(out)))
+    return out
+
+
+def frames_for_poses(poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int) -> np.ndarray:
+    poses = _f32(poses).reshape(-1, 3)
+    out = np.zeros(len(poses), dtype=FRAME_DTYPE)
+    fn = lib().birp_frame_setup
+    base = out.ctypes.data
+    for n in range(len(poses)):
+        _check(fn(poses[n].ctypes.data_as(_f32p), aim_x, fov_x_deg, fov_y_deg, W, H,
+                  C.c_void_p(base + n * FRAME_DTYPE.itemsize)))
+    return out
+
+
+def ray_table(nsamples: int, maxdist: int):
+    dist = np.zeros(nsamples, dtype=np.float32)
+    w = C.c_float(0)
+    _check(lib().birp_ray_table(nsamples, maxdist, dist.ctypes.data_as(_f32p), C.byref(w)))
+    return dist, np.float32(w.value)
+
+
+def cmem_init(v=None, b=None, dipole=0.0, p0=0.786300004, p1=1, p2=3, p3=4, B=2.0, alpha=2.5, beta=-1.6,
+              bs=12.6400003, A1=7.2e-06, A2=3.5000000000000004e-06, ay_bs=0.0, az_bs=0.0, density=0.0) -> np.ndarray:
+    """CMEM::Init(true, ...) with the reference's default arguments (include/Cmem.h:21-39)."""
+    out = np.zeros(1, dtype=CMEM_DTYPE)
+    va = (C.c_int * 3)(*(v if v is not None else (0, 0, 0)))
+    ba = (C.c_int * 3)(*(b if b is not None else (0, 0, 0)))
+    _check(lib().birp_cmem_init(int(v is not None), va, int(b is not None), ba, dipole, p0, int(p1), int(p2),
+                                int(p3), B, alpha, beta, bs, A1, A2, ay_bs, az_bs, density, _ptr(out)))
+    return out
+
+
+def cmem_init_cli() -> np.ndarray:
+    """The parameters `birp -c` ends up with (reference src/main.cpp:66-78,294): every CMEM flag
+    left at NULL/0 and p = {1,1,3,4}."""
+    return cmem_init(v=None, b=None, dipole=0.0, p0=1.0, p1=1, p2=3, p3=4, B=0.0, alpha=0.0, beta=0.0, bs=0.0,
+                     A1=0.0, A2=0.0, ay_bs=0.0, az_bs=0.0, density=0.0)
+
+
+# ------------------------------------------------------------------ pinned host memory
+class PinnedArray:
+    """float32 / structured numpy array backed by cudaHostAlloc memory."""
+
+    def __init__(self, shape, dtype=np.float32):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        self._p = _vp()
+        _check(lib().birp_host_alloc(max(n, 1), C.byref(self._p)))
+        buf = (C.c_char * max(n, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().birp_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ cube
+class Cube:
+    """Device-resident DataCube grid."""
+
+    def __init__(self, zyx: np.ndarray, origin, spacing):
+        zyx = _f32(zyx)
+        assert zyx.ndim == 3, "cube must be [nz][ny][nx]"
+        self.nz, self.ny, self.nx = zyx.shape
+        self.origin = _f32(origin, (3,))
+        self.spacing = _f32(spacing, (3,))
+        self._h = _vp()
+        _check(lib().birp_cube_upload(_ptr(zyx), self.nx, self.ny, self.nz, self.origin.ctypes.data_as(_f32p),
+                                      self.spacing.ctypes.data_as(_f32p), C.byref(self._h)))
+
+    @classmethod
+    def from_device(cls, d_ptr: int, nx: int, ny: int, nz: int, origin, spacing, stream: int = 0) -> "Cube":
+        self = cls.__new__(cls)
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.origin = _f32(origin, (3,))
+        self.spacing = _f32(spacing, (3,))
+        self._h = _vp()
+        _check(lib().birp_cube_upload_device(_vp(d_ptr), nx, ny, nz, self.origin.ctypes.data_as(_f32p),
+                                             self.spacing.ctypes.data_as(_f32p), _vp(stream), C.byref(self._h)))
+        return self
+
+    @property
+    def handle(self):
+        return self._h
+
+    def free(self):
+        if self._h:
+            lib().birp_cube_free(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def sample(self, xyz, trilinear: bool) -> np.ndarray:
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.empty(len(xyz), dtype=np.float32)
+        _check(lib().birp_sample_cube(self._h, _ptr(xyz), len(xyz), TRILINEAR if trilinear else NEAREST, _ptr(out)))
+        return out
+
+    def render(self, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
+               trilinear: bool = True, rows=(0, 0), images: np.ndarray | None = None) -> np.ndarray:
+        """Host-buffer render; `images` given => accumulated into (BIRP_ACCUMULATE)."""
+        frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+        flags = TRILINEAR if trilinear else NEAREST
+        if images is None:
+            images = np.zeros((len(frames), H, W), dtype=np.float32)
+        else:
+            assert images.dtype == np.float32 and images.flags.c_contiguous
+            assert images.size == len(frames) * H * W
+            flags |= ACCUMULATE
+        _check(lib().birp_render_cube(self._h, _ptr(frames), len(frames), W, H, rows[0], rows[1], nsamples, maxdist,
+                                      flags, _ptr(images)))
+        return images
+
+
+def render_cmem(params: np.ndarray, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
+                fast: bool = False, rows=(0, 0), images: np.ndarray | None = None) -> np.ndarray:
+    frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+    params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
+    flags = CMEM_FAST if fast else 0
+    if images is None:
+        images = np.zeros((len(frames), H, W), dtype=np.float32)
+    else:
+        assert images.dtype == np.float32 and images.flags.c_contiguous
+        flags |= ACCUMULATE
+    _check(lib().birp_render_cmem(_ptr(params), _ptr(frames), len(frames), W, H, rows[0], rows[1], nsamples,
+                                  maxdist, flags, _ptr(images)))
+    return images
+
+
+def sample_cmem(params: np.ndarray, xyz, fast: bool = False) -> np.ndarray:
+    params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = np.empty(len(xyz), dtype=np.float32)
+    _check(lib().birp_sample_cmem(_ptr(params), _ptr(xyz), len(xyz), CMEM_FAST if fast else 0, _ptr(out)))
+    return out
+
+
+def accumulate(samples, ray_width: float, image: np.ndarray | None = None) -> np.ndarray:
+    samples = _f32(samples)
+    assert samples.ndim == 2
+    nrays, nsamples = samples.shape
+    flags = 0
+    if image is None:
+        image = np.zeros(nrays, dtype=np.float32)
+    else:
+        assert image.dtype == np.float32 and image.flags.c_contiguous and image.size == nrays
+        flags = ACCUMULATE
+    _check(lib().birp_accumulate(_ptr(samples), nrays, nsamples, float(ray_width), flags, _ptr(image)))
+    return image
+
+
+# ------------------------------------------------------------------ device-buffer entry points
+def render_cube_device(cube: Cube, d_frames: int, nframes: int, W: int, H: int, d_images: int, *, nsamples=200,
+                       maxdist=44, trilinear=True, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
+                       stream: int = 0) -> None:
+    flags = (TRILINEAR if trilinear else NEAREST) | (ACCUMULATE if accumulate_into else 0)
+    _check(lib().birp_render_cube_device(cube.handle, _vp(d_frames), nframes, W, H, rows[0], rows[1], nsamples,
+                                         maxdist, flags, _vp(d_images), _vp(d_valid), _vp(stream)))
+
+
+def render_cmem_device(params: np.ndarray, d_frames: int, nframes: int, W: int, H: int, d_images: int, *,
+                       nsamples=200, maxdist=44, fast=False, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
+                       stream: int = 0) -> None:
+    params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
+    flags = (CMEM_FAST if fast else 0) | (ACCUMULATE if accumulate_into else 0)
+    _check(lib().birp_render_cmem_device(_ptr(params), _vp(d_frames), nframes, W, H, rows[0], rows[1], nsamples,
+                                         maxdist, flags, _vp(d_images), _vp(d_valid), _vp(stream)))
+
+
+def check_device_status(stream: int = 0) -> None:
+    _check(lib().birp_check_device_status(_vp(stream)))
+
+
+def launch_count() -> int:
+    return int(lib().birp_launch_count())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().birp_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(ordinal: int) -> None:
+    _check(lib().birp_set_device(ordinal))

@@ -1,0 +1,498 @@
+// C ABI of libbirp_b200.so (declared in include/birp_b200.h): device contexts, cube
+// residency, pinned staging, chunked host<->device pipelines around the kernels.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "birp_host.h"
+#include "birp_internal.h"
+
+struct birp_cube {
+    birp::CubeView view;
+    float* d_data;
+    int device;
+    size_t voxels;
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define BIRP_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return set_error(BIRP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct RayTable {
+    float* d_dist = nullptr;
+    float ray_width = 0.f;
+};
+
+// Per-device state.  Created lazily on first use from the thread that owns the device.
+struct DeviceCtx {
+    int device = -1;
+    cudaStream_t compute = nullptr;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t rendered[2] = {nullptr, nullptr};
+    cudaEvent_t drained[2] = {nullptr, nullptr};
+    std::map<std::pair<int, int>, RayTable> tables;
+    birp_frame* d_frames = nullptr;
+    size_t frames_cap = 0;
+    float* d_images[2] = {nullptr, nullptr};
+    size_t images_cap = 0;  // floats per buffer
+    float* d_scratch = nullptr;
+    size_t scratch_cap = 0;  // floats
+    int* d_status = nullptr;
+    int* h_status = nullptr;  // pinned
+    std::mutex mu;
+};
+
+std::mutex g_ctx_mu;
+std::map<int, DeviceCtx*> g_ctx;
+
+int get_ctx(DeviceCtx** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return set_error(BIRP_ERR_CUDA, "no usable CUDA device: %s (this library has no CPU path)",
+                         cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto it = g_ctx.find(dev);
+    if (it != g_ctx.end()) {
+        *out = it->second;
+        return BIRP_OK;
+    }
+    DeviceCtx* c = new DeviceCtx();
+    c->device = dev;
+    BIRP_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    BIRP_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        BIRP_CUDA(cudaEventCreateWithFlags(&c->rendered[i], cudaEventDisableTiming));
+        BIRP_CUDA(cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming));
+    }
+    BIRP_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
+    BIRP_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
+    BIRP_CUDA(cudaHostAlloc(&c->h_status, sizeof(int), cudaHostAllocDefault));
+    g_ctx[dev] = c;
+    *out = c;
+    return BIRP_OK;
+}
+
+int get_ray_table(DeviceCtx* c, int nsamples, int maxdist, cudaStream_t stream, RayTable* out) {
+    auto key = std::make_pair(nsamples, maxdist);
+    auto it = c->tables.find(key);
+    if (it != c->tables.end()) {
+        *out = it->second;
+        return BIRP_OK;
+    }
+    std::vector<float> h(nsamples);
+    RayTable t;
+    birp::host_ray_table(nsamples, maxdist, h.data(), &t.ray_width);
+    BIRP_CUDA(cudaMalloc(&t.d_dist, sizeof(float) * nsamples));
+    // synchronous copy from pageable memory: the table is ready for any stream afterwards
+    BIRP_CUDA(cudaMemcpy(t.d_dist, h.data(), sizeof(float) * nsamples, cudaMemcpyHostToDevice));
+    (void)stream;
+    c->tables[key] = t;
+    *out = t;
+    return BIRP_OK;
+}
+
+template <class T>
+int ensure(T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return BIRP_OK;
+    if (*p) BIRP_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    BIRP_CUDA(cudaMalloc(p, need * sizeof(T)));
+    *cap = need;
+    return BIRP_OK;
+}
+
+int check_geom(const void* frames, int nframes, int W, int H, int* row_begin, int* row_end, int nsamples,
+               const void* images) {
+    if (!frames || !images) return set_error(BIRP_ERR_ARG, "null frames/images pointer");
+    if (nframes < 0 || W <= 0 || H <= 0 || nsamples <= 0)
+        return set_error(BIRP_ERR_ARG, "bad sizes: nframes=%d W=%d H=%d nsamples=%d", nframes, W, H, nsamples);
+    if (*row_end <= 0 || *row_end > H) *row_end = H;
+    if (*row_begin < 0) *row_begin = 0;
+    if (*row_begin > *row_end) return set_error(BIRP_ERR_ARG, "row_begin > row_end");
+    return BIRP_OK;
+}
+
+int read_status(DeviceCtx* c, cudaStream_t stream) {
+    BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BIRP_CUDA(cudaStreamSynchronize(stream));
+    const int st = *c->h_status;
+    if (st) {
+        BIRP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), stream));
+        BIRP_CUDA(cudaStreamSynchronize(stream));
+        if (st & birp::kStatusNanIndex)
+            return set_error(BIRP_ERR_RANGE,
+                             "NaN sample coordinate inside the cube bounds test "
+                             "(the reference throws std::out_of_range here)");
+    }
+    return BIRP_OK;
+}
+
+// Shared host-buffer pipeline: frames are rendered in chunks of up to ~64 MiB of pixels,
+// chunk c rendering on the compute stream while chunk c-1 drains to the host on the copy
+// stream (two device image buffers).
+template <class Launch>
+int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int H, int row_begin, int row_end,
+                int nsamples, int maxdist, int flags, float* images, Launch&& launch) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    RayTable table;
+    int rc = get_ray_table(c, nsamples, maxdist, c->compute, &table);
+    if (rc) return rc;
+    if (nframes == 0 || row_begin == row_end) return BIRP_OK;
+
+    const size_t frame_px = (size_t)W * H;
+    const size_t band_px = (size_t)W * (row_end - row_begin);
+    const size_t band_off = (size_t)W * row_begin;
+    size_t chunk = (size_t(16) << 20) / frame_px;  // 16 Mi pixels = 64 MiB per buffer
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)nframes) chunk = nframes;
+    rc = ensure(&c->d_frames, &c->frames_cap, (size_t)nframes);
+    if (rc) return rc;
+    {
+        size_t cap = c->images_cap;
+        rc = ensure(&c->d_images[0], &cap, chunk * frame_px);
+        if (rc) return rc;
+        cap = c->images_cap;
+        rc = ensure(&c->d_images[1], &cap, chunk * frame_px);
+        if (rc) return rc;
+        c->images_cap = cap;
+    }
+    BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
+                              c->compute));
+    const bool full_rows = (row_begin == 0 && row_end == H);
+    int nchunks = 0;
+    for (size_t f0 = 0; f0 < (size_t)nframes; f0 += chunk, ++nchunks) {
+        const int b = nchunks & 1;
+        const int nf = (int)((f0 + chunk <= (size_t)nframes) ? chunk : (size_t)nframes - f0);
+        float* d_img = c->d_images[b];
+        if (nchunks >= 2) BIRP_CUDA(cudaStreamWaitEvent(c->compute, c->drained[b], 0));
+        if (flags & BIRP_ACCUMULATE) {
+            if (full_rows) {
+                BIRP_CUDA(cudaMemcpyAsync(d_img, images + f0 * frame_px, sizeof(float) * nf * frame_px,
+                                          cudaMemcpyHostToDevice, c->compute));
+            } else {
+                for (int f = 0; f < nf; ++f)
+                    BIRP_CUDA(cudaMemcpyAsync(d_img + f * frame_px + band_off,
+                                              images + (f0 + f) * frame_px + band_off, sizeof(float) * band_px,
+                                              cudaMemcpyHostToDevice, c->compute));
+            }
+        }
+        birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
+        cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
+        if (e != cudaSuccess)
+            return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        BIRP_CUDA(cudaEventRecord(c->rendered[b], c->compute));
+        BIRP_CUDA(cudaStreamWaitEvent(c->copy, c->rendered[b], 0));
+        if (full_rows) {
+            BIRP_CUDA(cudaMemcpyAsync(images + f0 * frame_px, d_img, sizeof(float) * nf * frame_px,
+                                      cudaMemcpyDeviceToHost, c->copy));
+        } else {
+            for (int f = 0; f < nf; ++f)
+                BIRP_CUDA(cudaMemcpyAsync(images + (f0 + f) * frame_px + band_off,
+                                          d_img + f * frame_px + band_off, sizeof(float) * band_px,
+                                          cudaMemcpyDeviceToHost, c->copy));
+        }
+        BIRP_CUDA(cudaEventRecord(c->drained[b], c->copy));
+    }
+    BIRP_CUDA(cudaStreamSynchronize(c->copy));
+    return read_status(c, c->compute);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* birp_version(void) { return "birp_b200 0.1 (sm_100a)"; }
+const char* birp_last_error(void) { return g_error.c_str(); }
+
+int birp_device_count(int* count) {
+    if (!count) return set_error(BIRP_ERR_ARG, "null count");
+    *count = 0;
+    BIRP_CUDA(cudaGetDeviceCount(count));
+    return BIRP_OK;
+}
+
+int birp_set_device(int ordinal) {
+    BIRP_CUDA(cudaSetDevice(ordinal));
+    return BIRP_OK;
+}
+
+int birp_host_alloc(size_t bytes, void** out) {
+    if (!out) return set_error(BIRP_ERR_ARG, "null out");
+    BIRP_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BIRP_OK;
+}
+
+int birp_host_free(void* p) {
+    if (p) BIRP_CUDA(cudaFreeHost(p));
+    return BIRP_OK;
+}
+
+int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                     birp_frame* out) {
+    if (!pos || !out || W <= 0 || H <= 0) return set_error(BIRP_ERR_ARG, "bad frame_setup arguments");
+    int rc = birp::host_frame_setup(pos, aim_x, fov_x_deg, fov_y_deg, W, H, out);
+    if (rc == BIRP_ERR_SINGULAR) return set_error(rc, "Determinant is 0");
+    return rc;
+}
+
+int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out) {
+    if (nsamples <= 0) return set_error(BIRP_ERR_ARG, "nsamples must be positive");
+    birp::host_ray_table(nsamples, maxdist, dist_out, ray_width_out);
+    return BIRP_OK;
+}
+
+int birp_cmem_init(int has_v, const int v[3], int has_b, const int b[3], float dipole, float p0, int p1,
+                   int p2, int p3, float B, float alpha, float beta, float bs, float A1, float A2,
+                   float ay_bs, float az_bs, float density, birp_cmem_params* out) {
+    if (!out) return set_error(BIRP_ERR_ARG, "null out");
+    if ((has_v && !v) || (has_b && !b)) return set_error(BIRP_ERR_ARG, "null v/b");
+    birp::host_cmem_init(has_v, v, has_b, b, dipole, p0, p1, p2, p3, B, alpha, beta, bs, A1, A2, ay_bs, az_bs,
+                         density, out);
+    return BIRP_OK;
+}
+
+static int make_cube(const float* src, bool src_on_device, int nx, int ny, int nz, const float origin[3],
+                     const float spacing[3], cudaStream_t stream, birp_cube** out) {
+    if (!src || !origin || !spacing || !out) return set_error(BIRP_ERR_ARG, "null pointer");
+    if (nx <= 0 || ny <= 0 || nz <= 0) return set_error(BIRP_ERR_ARG, "bad cube size %dx%dx%d", nx, ny, nz);
+    const size_t voxels = (size_t)nx * ny * nz;
+    if (voxels >= (size_t(1) << 31)) return set_error(BIRP_ERR_ARG, "cube has >= 2^31 voxels");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    birp_cube* cube = new birp_cube();
+    cube->device = c->device;
+    cube->voxels = voxels;
+    cudaError_t e = cudaMalloc(&cube->d_data, voxels * sizeof(float));
+    if (e != cudaSuccess) {
+        delete cube;
+        return set_error(e == cudaErrorMemoryAllocation ? BIRP_ERR_NOMEM : BIRP_ERR_CUDA,
+                         "cudaMalloc of %zu-voxel cube failed: %s", voxels, cudaGetErrorString(e));
+    }
+    if (src_on_device) {
+        e = cudaMemcpyAsync(cube->d_data, src, voxels * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    } else {
+        e = cudaMemcpy(cube->d_data, src, voxels * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(cube->d_data);
+        delete cube;
+        return set_error(BIRP_ERR_CUDA, "cube copy failed: %s", cudaGetErrorString(e));
+    }
+    birp::CubeView& v = cube->view;
+    v.v = cube->d_data;
+    v.nx = nx;
+    v.ny = ny;
+    v.nz = nz;
+    v.fnx = (float)nx;
+    v.fny = (float)ny;
+    v.fnz = (float)nz;
+    v.ox = origin[0];
+    v.oy = origin[1];
+    v.oz = origin[2];
+    v.sx = spacing[0];
+    v.sy = spacing[1];
+    v.sz = spacing[2];
+    *out = cube;
+    return BIRP_OK;
+}
+
+int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origin[3], const float spacing[3],
+                     birp_cube** out) {
+    return make_cube(zyx, false, nx, ny, nz, origin, spacing, nullptr, out);
+}
+
+int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const float origin[3],
+                            const float spacing[3], void* stream, birp_cube** out) {
+    return make_cube(d_zyx, true, nx, ny, nz, origin, spacing, (cudaStream_t)stream, out);
+}
+
+void birp_cube_free(birp_cube* cube) {
+    if (!cube) return;
+    cudaFree(cube->d_data);
+    delete cube;
+}
+
+int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframes, int W, int H, int row_begin,
+                     int row_end, int nsamples, int maxdist, int flags, float* images) {
+    if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
+    int rc = check_geom(frames, nframes, W, H, &row_begin, &row_end, nsamples, images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    const birp::CubeView view = cube->view;
+    int* d_status = c->d_status;
+    return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
+                       [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
+                           cudaStream_t s) {
+                           return birp::launch_render_cube(view, d_fr, g, d_dist, flags, d_img, nullptr,
+                                                           d_status, s);
+                       });
+}
+
+int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, int nframes, int W, int H,
+                     int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images) {
+    if (!params) return set_error(BIRP_ERR_ARG, "null params");
+    int rc = check_geom(frames, nframes, W, H, &row_begin, &row_end, nsamples, images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    const birp_cmem_params P = *params;
+    return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
+                       [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
+                           cudaStream_t s) {
+                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
+                       });
+}
+
+int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags, float* image) {
+    if (!samples || !image) return set_error(BIRP_ERR_ARG, "null pointer");
+    if (nrays < 0 || nsamples <= 0) return set_error(BIRP_ERR_ARG, "bad sizes");
+    if (nrays == 0) return BIRP_OK;
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t ns = (size_t)nrays * nsamples;
+    rc = ensure(&c->d_scratch, &c->scratch_cap, ns + (size_t)nrays);
+    if (rc) return rc;
+    float* d_samples = c->d_scratch;
+    float* d_image = c->d_scratch + ns;
+    BIRP_CUDA(cudaMemcpyAsync(d_samples, samples, ns * sizeof(float), cudaMemcpyHostToDevice, c->compute));
+    if (flags & BIRP_ACCUMULATE)
+        BIRP_CUDA(cudaMemcpyAsync(d_image, image, nrays * sizeof(float), cudaMemcpyHostToDevice, c->compute));
+    cudaError_t e = birp::launch_accumulate(d_samples, nrays, nsamples, ray_width, flags, d_image, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(image, d_image, nrays * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    return BIRP_OK;
+}
+
+int birp_sample_cube(const birp_cube* cube, const float* xyz, long n, int flags, float* out) {
+    if (!cube || !xyz || !out) return set_error(BIRP_ERR_ARG, "null pointer");
+    if (n < 0) return set_error(BIRP_ERR_ARG, "negative count");
+    if (n == 0) return BIRP_OK;
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)n * 4);
+    if (rc) return rc;
+    float* d_xyz = c->d_scratch;
+    float* d_out = c->d_scratch + (size_t)n * 3;
+    BIRP_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->compute));
+    cudaError_t e = birp::launch_sample_cube(cube->view, d_xyz, n, flags, d_out, c->d_status, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    return read_status(c, c->compute);
+}
+
+int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, int flags, float* out) {
+    if (!params || !xyz || !out) return set_error(BIRP_ERR_ARG, "null pointer");
+    if (n < 0) return set_error(BIRP_ERR_ARG, "negative count");
+    if (n == 0) return BIRP_OK;
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)n * 4);
+    if (rc) return rc;
+    float* d_xyz = c->d_scratch;
+    float* d_out = c->d_scratch + (size_t)n * 3;
+    BIRP_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->compute));
+    cudaError_t e = birp::launch_sample_cmem(*params, d_xyz, n, flags, d_out, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    return BIRP_OK;
+}
+
+int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                            int row_begin, int row_end, int nsamples, int maxdist, int flags, float* d_images,
+                            unsigned long long* d_valid_samples, void* stream) {
+    if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
+    int rc = check_geom(d_frames, nframes, W, H, &row_begin, &row_end, nsamples, d_images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    RayTable table;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        rc = get_ray_table(c, nsamples, maxdist, (cudaStream_t)stream, &table);
+        if (rc) return rc;
+    }
+    birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    cudaError_t e = birp::launch_render_cube(cube->view, d_frames, g, table.d_dist, flags, d_images,
+                                             d_valid_samples, c->d_status, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_frames, int nframes, int W,
+                            int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                            float* d_images, unsigned long long* d_valid_samples, void* stream) {
+    if (!params) return set_error(BIRP_ERR_ARG, "null params");
+    int rc = check_geom(d_frames, nframes, W, H, &row_begin, &row_end, nsamples, d_images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    RayTable table;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        rc = get_ray_table(c, nsamples, maxdist, (cudaStream_t)stream, &table);
+        if (rc) return rc;
+    }
+    birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    cudaError_t e = birp::launch_render_cmem(*params, d_frames, g, table.d_dist, flags, d_images,
+                                             d_valid_samples, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+int birp_check_device_status(void* stream) {
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return read_status(c, (cudaStream_t)stream);
+}
+
+unsigned long long birp_launch_count(void) { return birp::launch_count(); }
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// Device-side building blocks of the line-of-sight integrator (sm_100a).
+//
+// Everything that decides WHICH voxel a sample reads, WHEN a ray terminates and in what
+// order a pixel accumulates is written with explicitly rounded IEEE intrinsics
+// (__fmul_rn / __fadd_rn / __fdiv_rn / __fsqrt_rn: never contracted into FMA), in the
+// operation order of the reference, so the DataCube path is bit-identical to the
+// reference CPU render (which contains no FMA instructions: x86-64 baseline build,
+// reference CMakeLists.txt:18-22).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/birp_b200.h"
+
+namespace birp {
+
+// ---------------------------------------------------------------------------------
+// Device view of a resident cube (x fastest, like slices[z][y][x]).
+// ---------------------------------------------------------------------------------
+struct CubeView {
+    const float* __restrict__ v;
+    int nx, ny, nz;
+    float fnx, fny, fnz;  // (float)size.{x,y,z}: right-hand side of the reference's bounds test
+    float ox, oy, oz;     // coords_{x,y,z}[0]
+    float sx, sy, sz;     // spacing[0..2]
+};
+
+// The fp32 -> fp64 -> fp32 scale of reference src/Camera.cpp:201,
+//   sample = (sample * ray_width * (1000 * 100 * 6378.1) / (4 / M_PI)) / 10000;
+// i.e. fl32( ((double)fl32(sample*ray_width) * 637810000.0 / (4/pi)) / 10000 ).
+#define BIRP_SCALE_C1 (1000 * 100 * 6378.1)
+#define BIRP_SCALE_C2 (4 / 3.14159265358979323846)
+#define BIRP_SCALE_C3 10000.0
+
+__device__ __forceinline__ float scale_sample_chain(float p) {
+    double d = (double)p;
+    d = __dmul_rn(d, BIRP_SCALE_C1);
+    d = __ddiv_rn(d, BIRP_SCALE_C2);
+    d = __ddiv_rn(d, BIRP_SCALE_C3);
+    return __double2float_rn(d);
+}
+
+// Same result as scale_sample_chain for every input, cheaper on average.
+// One fp64 multiply by K = C1/C2/C3 lands within a few fp64 ulps of the three-step
+// chain (each step of either route is correctly rounded, so both stay within 4 ulp64
+// of the real product).  The two can only round to different fp32 values when that
+// fp64 result sits within a few ulp64 of an fp32 rounding boundary -- either a midpoint
+// between consecutive fp32 values (low 29 mantissa bits ~ 0x10000000) or, because the
+// chain's fp32 result may be subnormal/overflow, outside the normal fp32 range.  Those
+// cases (about 1 in 2^24) take the exact chain.
+__device__ __forceinline__ float scale_sample(float s, float ray_width) {
+    const float p = __fmul_rn(s, ray_width);
+    constexpr double K = BIRP_SCALE_C1 / BIRP_SCALE_C2 / BIRP_SCALE_C3;
+    const double d = __dmul_rn((double)p, K);
+    const unsigned lo = (unsigned)__double2loint(d);
+    const unsigned hi = (unsigned)__double2hiint(d) & 0x7fffffffu;
+    // distance of the 29 dropped mantissa bits from the midpoint pattern, window +-32 ulp64
+    const unsigned frac = lo & 0x1fffffffu;
+    const bool near_mid = (frac - (0x10000000u - 32u)) < 64u;
+    // fp64 exponent range in which the fp32 result is a normal number with margin:
+    // 2^-120 .. 2^120  ->  biased 903 .. 1143
+    const unsigned e = hi >> 20;
+    const bool normal = (e - 903u) < 240u;
+    const bool zero = (hi | lo) == 0u;
+    if (__builtin_expect(!near_mid && (normal || zero), 1)) return __double2float_rn(d);
+    return scale_sample_chain(p);
+}
+
+// libstdc++ 13 std::lerp (<cmath> __lerp), the interpolation the reference calls
+// (src/DataCube.cpp:260-270, src/Cmem.cpp:149,170).
+__device__ __forceinline__ float lerp_ref(float a, float b, float t) {
+    if ((a <= 0.f && b >= 0.f) || (a >= 0.f && b <= 0.f))
+        return __fadd_rn(__fmul_rn(t, b), __fmul_rn(__fsub_rn(1.f, t), a));
+    if (t == 1.f) return b;
+    const float x = __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+    return ((t > 1.f) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+}
+
+// Helper::VectorDistance, src/Helper.cpp:591-594
+__device__ __forceinline__ float vec_len3(float x, float y, float z) {
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// World-space unit direction of pixel (i, j): src/Camera.cpp:148-168 with
+// Helper::ApplyRotation (src/Helper.cpp:136-148).
+__device__ __forceinline__ void pixel_direction(const birp_frame& fr, int i, int j, float fW, float fH,
+                                                float& dx, float& dy, float& dz) {
+    const float device_x = __fdiv_rn(__fadd_rn((float)i, 0.5f), fW);
+    const float device_y = __fdiv_rn(__fadd_rn((float)j, 0.5f), fH);
+    const float screen_x =
+        __fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(2.f, device_x), 1.f), fr.tan_half_x), fr.aspect);
+    const float screen_y = __fmul_rn(__fsub_rn(1.f, __fmul_rn(2.f, device_y)), fr.tan_half_y);
+    const float nd = vec_len3(screen_x, screen_y, -1.f);
+    const float ux = __fdiv_rn(screen_x, nd), uy = __fdiv_rn(screen_y, nd), uz = __fdiv_rn(-1.f, nd);
+    const float* r = fr.rinv;
+    const float wx = __fadd_rn(__fadd_rn(__fmul_rn(r[0], ux), __fmul_rn(r[1], uy)), __fmul_rn(r[2], uz));
+    const float wy = __fadd_rn(__fadd_rn(__fmul_rn(r[3], ux), __fmul_rn(r[4], uy)), __fmul_rn(r[5], uz));
+    const float wz = __fadd_rn(__fadd_rn(__fmul_rn(r[6], ux), __fmul_rn(r[7], uy)), __fmul_rn(r[8], uz));
+    const float wd = vec_len3(wx, wy, wz);
+    dx = __fdiv_rn(wx, wd);
+    dy = __fdiv_rn(wy, wd);
+    dz = __fdiv_rn(wz, wd);
+}
+
+// ---------------------------------------------------------------------------------
+// DataCube::GetSample, src/DataCube.cpp:203-277.
+// Returns -1 for the reference's out-of-bounds result.  *nan_index is set when an index
+// is NaN after passing the bounds test (where the reference's .at() throws).
+// ---------------------------------------------------------------------------------
+template <bool TRILINEAR>
+__device__ __forceinline__ float cube_sample(const CubeView& c, float x, float y, float z, bool& nan_index) {
+    const float xi = __fsub_rn(x, c.ox);
+    const float fx = __fdiv_rn(xi, c.sx);
+    const float yi = __fsub_rn(y, c.oy);
+    const float fy = __fdiv_rn(yi, c.sy);
+    const float zi = __fsub_rn(z, c.oz);
+    const float fz = __fdiv_rn(zi, c.sz);
+    if ((0.f > xi || __fadd_rn(fx, 1.f) >= c.fnx) || (0.f > yi || __fadd_rn(fy, 1.f) >= c.fny) ||
+        (0.f > zi || __fadd_rn(fz, 1.f) >= c.fnz))
+        return -1.f;
+    if (!(fx == fx) || !(fy == fy) || !(fz == fz)) {
+        nan_index = true;
+        return 0.f;
+    }
+    // indices are in [0, n-1): truncation == floor
+    // (the cube has < 2^31 voxels, checked at upload: 32-bit index arithmetic)
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const int row = c.nx;
+    const int base = (z0 * c.ny + y0) * row + x0;
+    if (!TRILINEAR) return __ldg(c.v + base);
+
+    const float tx = __fsub_rn(fx, (float)x0);
+    const float ty = __fsub_rn(fy, (float)y0);
+    const float tz = __fsub_rn(fz, (float)z0);
+    // ceil == floor on an exact integer index: the "max" corner is then the same voxel
+    const int ddx = (tx > 0.f) ? 1 : 0;
+    const int ddy = (ty > 0.f) ? row : 0;
+    const int ddz = (tz > 0.f) ? row * c.ny : 0;
+    const float* p = c.v + base;
+    const float s000 = __ldg(p);
+    const float s001 = __ldg(p + ddx);
+    const float s010 = __ldg(p + ddy);
+    const float s011 = __ldg(p + ddy + ddx);
+    const float s100 = __ldg(p + ddz);
+    const float s101 = __ldg(p + ddz + ddx);
+    const float s110 = __ldg(p + ddz + ddy);
+    const float s111 = __ldg(p + ddz + ddy + ddx);
+    const float low_x1 = lerp_ref(s000, s001, tx);
+    const float low_x2 = lerp_ref(s010, s011, tx);
+    const float high_x1 = lerp_ref(s100, s101, tx);
+    const float high_x2 = lerp_ref(s110, s111, tx);
+    const float low_y = lerp_ref(low_x1, low_x2, ty);
+    const float high_y = lerp_ref(high_x1, high_x2, ty);
+    return lerp_ref(low_y, high_y, tz);
+}
+
+// ---------------------------------------------------------------------------------
+// CMEM::GetSample, src/Cmem.cpp:117-186, with ShueCoords :224-246, LinScaled :188-222
+// and ShueModel :280-288.
+//
+// The reference evaluates fp32 glibc functions (correctly rounded in the vast majority
+// of cases).  PRECISE = true evaluates every transcendental in fp64 and rounds once to
+// fp32, which reproduces a correctly rounded fp32 result except within ~1e-8 of a
+// rounding boundary; PRECISE = false calls CUDA's fp32 libdevice functions (1-4 ulp).
+// The algebra between the calls keeps the reference's types and operation order.
+// ---------------------------------------------------------------------------------
+template <bool PRECISE>
+struct M {
+    static __device__ __forceinline__ float sin_(float x) { return PRECISE ? (float)sin((double)x) : sinf(x); }
+    static __device__ __forceinline__ float cos_(float x) { return PRECISE ? (float)cos((double)x) : cosf(x); }
+    static __device__ __forceinline__ float acos_(float x) { return PRECISE ? (float)acos((double)x) : acosf(x); }
+    static __device__ __forceinline__ float exp_(float x) { return PRECISE ? (float)exp((double)x) : expf(x); }
+    static __device__ __forceinline__ float pow_(float x, float y) {
+        return PRECISE ? (float)pow((double)x, (double)y) : powf(x, y);
+    }
+};
+
+template <bool PRECISE>
+__device__ __forceinline__ float cmem_sample(const birp_cmem_params& P, float x, float y, float z) {
+    typedef M<PRECISE> m;
+    // ShueCoords
+    const float r = vec_len3(x, y, z);
+    const float theta = (x != 0.f) ? m::acos_(__fdiv_rn(x, r)) : 0.f;
+    const float phi =
+        (y != 0.f) ? m::acos_(__fdiv_rn(y, __fsqrt_rn(__fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))))) : 0.f;
+
+    const float sin_t = m::sin_(theta), cos_t = m::cos_(theta);
+    const float sin_p = m::sin_(phi), cos_p = m::cos_(phi);
+
+    // LinScaled: the cos(phi - pi/2) factors and the outer acos are fp64 in the reference
+    const double c_n = cos((double)phi - CUDART_PI / 2);
+    const double c_s = cos((double)phi - (3 * CUDART_PI / 2));
+    const float cos_tn = m::cos_(P.theta_n), sin_tn = m::sin_(P.theta_n);
+    const float cos_ts = m::cos_(P.theta_s), sin_ts = m::sin_(P.theta_s);
+    const float phi_n = (float)acos(
+        __dadd_rn((double)__fmul_rn(cos_t, cos_tn), __dmul_rn((double)__fmul_rn(sin_t, sin_tn), c_n)));
+    const float phi_s = (float)acos(
+        __dadd_rn((double)__fmul_rn(cos_t, cos_ts), __dmul_rn((double)__fmul_rn(sin_t, sin_ts), c_s)));
+
+    const float fbase = __fadd_rn(
+        m::cos_(__fdiv_rn(theta, 2.f)),
+        __fmul_rn(__fmul_rn(P.a5, m::sin_(__fmul_rn(2.f, theta))), __fsub_rn(1.f, m::exp_(-theta))));
+    const float fexp = __fmul_rn(
+        P.p1, __fadd_rn(__fadd_rn(P.beta_c[0], __fmul_rn(P.beta_c[1], cos_p)),
+                        __fmul_rn(P.beta_c[3], __fmul_rn(sin_p, sin_p))));
+    const float f = m::pow_(fbase, fexp);
+    const float p2c = __fmul_rn(P.p2, P.charlie);
+    const float q = __fadd_rn(
+        __fmul_rn(p2c, m::exp_(__fmul_rn(__fmul_rn(P.p3, P.dn), m::pow_(phi_n, P.a21)))),
+        __fmul_rn(p2c, m::exp_(__fmul_rn(__fmul_rn(P.p3, P.ds), m::pow_(phi_s, P.a21)))));
+    const float radius_mp = __fadd_rn(__fmul_rn(__fmul_rn(P.p0, P.r0_lin), f), q);
+
+    // ShueModel(theta, phi, bs, ay_bs, az_bs)
+    const float sbase = __fdiv_rn(2.f, __fadd_rn(1.f, cos_t));
+    const float ry = __fmul_rn(P.bs, m::pow_(sbase, P.ay_bs));
+    const float rz = __fmul_rn(P.bs, m::pow_(sbase, P.az_bs));
+    const float rzc = __fmul_rn(rz, cos_p);
+    const float rys = __fmul_rn(ry, sin_p);
+    const float radius_bs =
+        __fdiv_rn(__fmul_rn(ry, rz), __fsqrt_rn(__fadd_rn(__fmul_rn(rzc, rzc), __fmul_rn(rys, rys))));
+
+    const float half_thickness = 0.025f;  // 0.05f / 2
+    const float mp_lo = __fsub_rn(radius_mp, half_thickness), mp_hi = __fadd_rn(radius_mp, half_thickness);
+    const float bs_lo = __fsub_rn(radius_bs, half_thickness), bs_hi = __fadd_rn(radius_bs, half_thickness);
+
+    if (r < mp_lo) return 0.f;
+
+    const bool in_mp_layer = (r >= mp_lo && r <= mp_hi);
+    const bool in_sheath = (r > mp_hi && r < bs_lo);
+    const bool in_bs_layer = (r >= bs_lo && r <= bs_hi);
+
+    float b1 = 0.f;
+    if (in_mp_layer || in_sheath || in_bs_layer) {
+        const float h = __fdiv_rn(theta, 2.f);
+        const float h4 = __fmul_rn(__fmul_rn(__fmul_rn(h, h), h), h);
+        const float e = m::exp_(__fmul_rn(-P.B, h4));
+        const float pw = m::pow_(__fdiv_rn(r, 10.f),
+                                 __fsub_rn(-P.alpha, __fmul_rn(P.beta, __fmul_rn(sin_t, sin_t))));
+        b1 = __fmul_rn(__fmul_rn(P.A1, e), pw);
+    }
+    if (in_mp_layer) {
+        const float shue_norm = __fdiv_rn(__fsub_rn(r, mp_lo), mp_hi);
+        return lerp_ref(0.f, b1, shue_norm);
+    }
+    if (in_sheath) return b1;
+
+    // beyond the magnetosheath: b2 is computed in double from the fp32 quotient r/10
+    const double sd = (double)__fdiv_rn(r, 10.f);
+    const double cube = __dmul_rn(__dmul_rn(sd, sd), sd);
+    const float b2 = __double2float_rn(__dmul_rn((double)P.A2, __ddiv_rn(1.0, cube)));
+    if (in_bs_layer) {
+        const float shue_norm = __fdiv_rn(__fsub_rn(r, bs_lo), bs_hi);
+        return lerp_ref(b1, b2, shue_norm);
+    }
+    return b2;
+}
+
+}  // namespace birp

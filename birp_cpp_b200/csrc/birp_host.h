@@ -1,0 +1,13 @@
+// Host-side setup routines (birp_hostmath.cpp), wrapped by the C ABI in birp_capi.cu.
+#pragma once
+#include "../../include/birp_b200.h"
+
+namespace birp {
+int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                     birp_frame* out);
+void host_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);
+void host_cmem_init(int has_v, const int v_in[3], int has_b, const int b_in[3], float dipole, float p0_passed,
+                    int p1_passed, int p2_passed, int p3_passed, float B_passed, float alpha, float beta,
+                    float bs_passed, float A1_passed, float A2_passed, float ay_bs_passed, float az_bs_passed,
+                    float density_passed, birp_cmem_params* out);
+}  // namespace birp

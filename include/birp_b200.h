@@ -1,0 +1,158 @@
+/*
+ * birp_b200.h -- C ABI of the B200-native line-of-sight integrator.
+ *
+ * This is the drop-in boundary for the one hot path of Zach-Clare/birp_cpp: the
+ * per-pixel integration that the reference runs serially inside
+ *     Camera::Render() -> Camera::Integrate()          (reference src/Camera.cpp:63-233)
+ * calling Space::GetSample 200x per pixel              (reference include/Space.h:21-22)
+ * on a DataCube                                        (reference src/DataCube.cpp:203-277)
+ * or on the analytic CMEM field                        (reference src/Cmem.cpp:117-288).
+ *
+ * Plain pointers and sizes only.  Every entry point returns 0 on success and a
+ * BIRP_ERR_* code otherwise; nothing throws across this boundary.  The C++ classes in
+ * birp_cpp_b200/include (same names and signatures as the reference's include/ *.h)
+ * sit on top of it and turn error codes back into the reference's exceptions.
+ *
+ * Calls are synchronous on return unless the name ends in _device (those enqueue on
+ * the stream given and return).  One host thread per GPU; the library keeps one
+ * context (streams, staging buffers, ray tables) per device.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails
+ * with BIRP_ERR_CUDA.  The host-math entry points (frame setup, ray table, CMEM
+ * constants) are per-frame / per-run setup that the reference also does once outside
+ * its pixel loop; they run on the host with glibc so their outputs are bit-identical
+ * to the reference's.
+ */
+#ifndef BIRP_B200_H
+#define BIRP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    BIRP_OK = 0,
+    BIRP_ERR_CUDA = 1,     /* CUDA runtime error, or no device / extension unusable */
+    BIRP_ERR_ARG = 2,      /* bad argument (null pointer, non-positive size, ...) */
+    BIRP_ERR_SINGULAR = 3, /* rotation matrix has determinant 0: reference throws
+                              std::runtime_error("Determinant is 0") (src/Helper.cpp:242-244) */
+    BIRP_ERR_RANGE = 4,    /* a sample coordinate was NaN inside the cube bounds test: the
+                              reference throws std::out_of_range from .at()
+                              (src/DataCube.cpp:245-252,273) */
+    BIRP_ERR_NOMEM = 5
+};
+
+/* flags for the render entry points */
+enum {
+    BIRP_NEAREST = 0,        /* DataCube::SetTrilinear(false), the reference default (src/main.cpp:56) */
+    BIRP_TRILINEAR = 1,      /* DataCube::SetTrilinear(true) */
+    BIRP_ACCUMULATE = 2,     /* start each pixel from the value already in `images`
+                                (the reference never clears Camera::image, src/Camera.cpp:223);
+                                without it pixels start from 0 and `images` is overwritten */
+    BIRP_CMEM_FAST = 4       /* CMEM only: evaluate the transcendental calls in fp32 libdevice
+                                instead of fp64-then-round */
+};
+
+/* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */
+typedef struct birp_cube birp_cube;
+
+/*
+ * Per-frame camera state, computed once per frame on the host exactly as the reference
+ * does before its pixel loop (src/Camera.cpp:85-137 with Orient :309-417 and
+ * PointToPlane :419-508).  64 bytes.
+ */
+typedef struct birp_frame {
+    float pos[3];     /* Camera::position */
+    float rinv[9];    /* rotation_inverse, row-major (src/Camera.cpp:135) */
+    float tan_half_x; /* tanf(to_rad * (fov_x / 2))   (src/Camera.cpp:150) */
+    float tan_half_y; /* tanf(to_rad * (fov_y / 2))   (src/Camera.cpp:151) */
+    float aspect;     /* (float)W / (float)H          (src/Camera.cpp:137) */
+    float sun_angle;  /* Camera::Orient() result, diagnostic only */
+} birp_frame;
+
+/*
+ * CMEM state after CMEM::Init (private members of include/Cmem.h:43-75 that GetSample
+ * reads, src/Cmem.cpp:117-288).  27 floats.
+ */
+typedef struct birp_cmem_params {
+    float p0, p1, p2, p3;
+    float bs, A1, A2, B, alpha, beta;
+    float ay_bs, az_bs;
+    float r0_lin, charlie, dn, ds, theta_n, theta_s;
+    float a5, a21;       /* a[5], a[21] of DefineLinearCoeffs (src/Cmem.cpp:253) */
+    float beta_c[4];
+    float pressure_dynamic, pressure_magnetic, density;
+} birp_cmem_params;
+
+/* ------------------------------------------------------------------ library / device */
+const char* birp_version(void);
+const char* birp_last_error(void);          /* thread-local message of the last failure */
+int birp_device_count(int* count);
+int birp_set_device(int ordinal);           /* cudaSetDevice for the calling thread */
+int birp_host_alloc(size_t bytes, void** out); /* pinned host memory for images / frames */
+int birp_host_free(void* p);
+
+/* ------------------------------------------------------------------ host-side setup */
+/* replaces Camera::Integrate's per-frame prologue + Camera::Orient (src/Camera.cpp:85-137,309-508) */
+int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                     birp_frame* out);
+/* replaces Camera::GenerateRayDistWidth (src/Camera.cpp:69-81); dist_out may be NULL */
+int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);
+/* replaces CMEM::Init(bool, ...) (src/Cmem.cpp:38-115); has_v/has_b = 0 mean "empty vector" */
+int birp_cmem_init(int has_v, const int v[3], int has_b, const int b[3], float dipole, float p0, int p1,
+                   int p2, int p3, float B, float alpha, float beta, float bs, float A1, float A2,
+                   float ay_bs, float az_bs, float density, birp_cmem_params* out);
+
+/* ------------------------------------------------------------------ cube residency */
+/* zyx: nz*ny*nx floats, x fastest (slices[z][y][x], include/DataCube.h:42).
+   origin = coords_{x,y,z}[0], spacing = DataCube::spacing (src/DataCube.cpp:140-191). */
+int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origin[3],
+                     const float spacing[3], birp_cube** out);
+/* same, the grid already in device memory (e.g. after an NCCL broadcast); copied */
+int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const float origin[3],
+                            const float spacing[3], void* stream, birp_cube** out);
+void birp_cube_free(birp_cube* cube);
+
+/* ------------------------------------------------------------------ the hot path, host buffers
+ * frames: nframes records (host).  images: nframes*H*W floats (host), row j = image y, top row
+ * first, like Camera::image[j][i].  Only rows [row_begin,row_end) are rendered and written
+ * (row_end <= 0 means H): the unit of multi-GPU image sharding.
+ * nsamples/maxdist = 200/44 reproduce Camera::Render() (src/Camera.cpp:31,65).
+ */
+int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframes, int W, int H,
+                     int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
+int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, int nframes, int W, int H,
+                     int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
+/* src/Camera.cpp:201-223 on samples[nrays][nsamples] taken on the host from a user-defined Space
+   subclass (e.g. the reference tests' CubeFake, tests/Camera_test.cpp:25-29). image: nrays floats. */
+int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags,
+                    float* image);
+/* Space::GetSample on n points, xyz interleaved (host in, host out) */
+int birp_sample_cube(const birp_cube* cube, const float* xyz, long n, int flags, float* out);
+int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, int flags, float* out);
+
+/* ------------------------------------------------------------------ the hot path, device buffers
+ * d_frames / d_images are device pointers; the work is enqueued on `stream` (a cudaStream_t,
+ * NULL = default stream) and the call returns without synchronising.
+ * d_valid_samples (optional, may be NULL): incremented by the number of samples that were
+ * evaluated and accumulated (the live prefix of every ray), for roofline accounting.
+ */
+int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                            int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                            float* d_images, unsigned long long* d_valid_samples, void* stream);
+int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_frames, int nframes,
+                            int W, int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                            float* d_images, unsigned long long* d_valid_samples, void* stream);
+/* device error word of the calling thread's device (BIRP_ERR_RANGE conditions raised by
+   *_device launches); synchronises `stream`, returns BIRP_OK / BIRP_ERR_RANGE and clears it */
+int birp_check_device_status(void* stream);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long birp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIRP_B200_H */
