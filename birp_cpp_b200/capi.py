@@ -224,31 +224,39 @@ class Cube:
         return out
 
     def render(self, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
-               trilinear: bool = True, rows=(0, 0), images: np.ndarray | None = None) -> np.ndarray:
-        """Host-buffer render; `images` given => accumulated into (BIRP_ACCUMULATE)."""
+               trilinear: bool = True, rows=(0, 0), images: np.ndarray | None = None,
+               out: np.ndarray | None = None) -> np.ndarray:
+        """Host-buffer render.  `images` given => accumulated into (BIRP_ACCUMULATE);
+        `out` given => overwritten (rows outside the band untouched); neither => new zeros."""
         frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
         flags = TRILINEAR if trilinear else NEAREST
-        if images is None:
-            images = np.zeros((len(frames), H, W), dtype=np.float32)
-        else:
-            assert images.dtype == np.float32 and images.flags.c_contiguous
-            assert images.size == len(frames) * H * W
+        if images is not None:
             flags |= ACCUMULATE
+        elif out is not None:
+            images = out
+        else:
+            images = np.zeros((len(frames), H, W), dtype=np.float32)
+        assert images.dtype == np.float32 and images.flags.c_contiguous
+        assert images.size == len(frames) * H * W
         _check(lib().birp_render_cube(self._h, _ptr(frames), len(frames), W, H, rows[0], rows[1], nsamples, maxdist,
                                       flags, _ptr(images)))
         return images
 
 
 def render_cmem(params: np.ndarray, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
-                fast: bool = False, rows=(0, 0), images: np.ndarray | None = None) -> np.ndarray:
+                fast: bool = False, rows=(0, 0), images: np.ndarray | None = None,
+                out: np.ndarray | None = None) -> np.ndarray:
     frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
     params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
     flags = CMEM_FAST if fast else 0
-    if images is None:
-        images = np.zeros((len(frames), H, W), dtype=np.float32)
-    else:
-        assert images.dtype == np.float32 and images.flags.c_contiguous
+    if images is not None:
         flags |= ACCUMULATE
+    elif out is not None:
+        images = out
+    else:
+        images = np.zeros((len(frames), H, W), dtype=np.float32)
+    assert images.dtype == np.float32 and images.flags.c_contiguous
+    assert images.size == len(frames) * H * W
     _check(lib().birp_render_cmem(_ptr(params), _ptr(frames), len(frames), W, H, rows[0], rows[1], nsamples,
                                   maxdist, flags, _ptr(images)))
     return images

@@ -1,0 +1,336 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, on a B200.
+
+DataCube path: bit-exact (index selection, termination and accumulation order are all
+reproduced).  CMEM path: SURVEY.md 8(d) tolerance -- 1e-5 per pixel, 1e-4 integrated flux,
+at least 95 % of pixels (device transcendentals are not glibc's)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from birp_cpp_b200 import capi, synthetic as S
+from conftest import assert_bit_exact, assert_image_parity, pixel_fraction_within
+
+pytestmark = pytest.mark.gpu
+
+W, H = S.SXI_W, S.SXI_H
+AIM = S.DEFAULT_AIM_X
+POSES = np.array([S.DEFAULT_POS, (30.0, -25.0, 28.0), (-14.0, 3.0, 5.0), (2.0, 9.5, -7.25), (1.5, -3.0, 2.0),
+                  (38.0, 38.0, 38.0), (-9.9, -39.9, 39.4)], np.float32)
+
+
+def frames_pair(poses, fov_x, fov_y, w, h):
+    """product frames (structured) and oracle frames (float rows); must agree bitwise"""
+    fp = capi.frames_for_poses(poses, AIM, fov_x, fov_y, w, h)
+    fo = O.orc_frames(poses, AIM, fov_x, fov_y, w, h)
+    assert_bit_exact(fp.view(np.float32).reshape(-1, 16), fo)
+    return fp, fo
+
+
+@pytest.fixture(scope="module")
+def dev_cube1(gpu, cube1):
+    c = capi.Cube(*cube1)
+    yield c
+    c.free()
+
+
+@pytest.fixture(scope="module")
+def dev_cube1_neg(gpu, cube1_neg):
+    c = capi.Cube(*cube1_neg)
+    yield c
+    c.free()
+
+
+# ------------------------------------------------------------------ DataCube sampler
+@pytest.mark.parametrize("tri", [False, True])
+def test_sampler_bit_exact(dev_cube1, cube1, tri):
+    zyx, org, sp = cube1
+    rng = np.random.default_rng(5)
+    pts = rng.uniform([-12, -42, -42], [42, 42, 42], size=(200000, 3)).astype(np.float32)
+    nodes = org + sp * rng.integers(0, 100, size=(5000, 3)).astype(np.float32)
+    edge = np.array([[-10.0, -40.0, -40.0], [39.5, 39.5, 39.5], [40.0, 0, 0], [39.499996, 0, 0], [-10.000001, 0, 0],
+                     [np.inf, 0, 0], [-np.inf, 0, 0], [0, 1e30, 0]], np.float32)
+    pts = np.concatenate([pts, nodes, edge])
+    assert_bit_exact(dev_cube1.sample(pts, tri), O.orc_cube_sample(zyx, org, sp, tri, pts), f"tri={tri}")
+
+
+def test_sampler_golden(dev_cube1, golden, cube1_matches_golden):
+    if not cube1_matches_golden:
+        pytest.skip("synthetic cube differs by an ulp on this CPU")
+    for tri in (0, 1):
+        assert_bit_exact(dev_cube1.sample(golden["sample_points"], bool(tri)), golden[f"samples_tri{tri}"])
+
+
+def test_sampler_empty_and_nan(dev_cube1):
+    assert dev_cube1.sample(np.zeros((0, 3), np.float32), True).shape == (0,)
+    with pytest.raises(capi.BirpError) as e:  # the reference throws std::out_of_range here
+        dev_cube1.sample([[np.nan, 0.0, 0.0]], True)
+    assert e.value.code == capi.BIRP_ERR_RANGE
+    # NaN in one axis but another axis out of bounds: the reference returns -1 without throwing
+    assert dev_cube1.sample([[np.nan, 100.0, 0.0]], True)[0] == -1.0
+    assert dev_cube1.sample([[0.0, 0.0, 0.0]], True)[0] > 0  # status word was cleared
+
+
+# ------------------------------------------------------------------ DataCube renders
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("neg", [False, True])
+def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tri, neg):
+    zyx, org, sp = cube1_neg if neg else cube1
+    dev = dev_cube1_neg if neg else dev_cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    got = dev.render(fp, W, H, trilinear=tri)
+    want = O.orc_render_cube(zyx, org, sp, tri, fo, W, H)
+    assert_bit_exact(got, want, f"tri={tri} neg={neg}")
+    assert want[0].min() > 0 and want[2].max() == 0  # inside / outside the cube
+
+
+@pytest.mark.parametrize("name", ["cube", "cubeneg"])
+@pytest.mark.parametrize("tri", [0, 1])
+def test_render_golden_reference_images(dev_cube1, dev_cube1_neg, golden, cube1_matches_golden, name, tri):
+    dev = dev_cube1 if name == "cube" else dev_cube1_neg
+    fp = capi.frames_for_poses(golden["poses"], float(golden["aim_x"]), S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    got = dev.render(fp, W, H, trilinear=bool(tri))
+    want = golden[f"{name}_tri{tri}"]
+    if cube1_matches_golden:
+        assert_bit_exact(got, want, "vs images rendered by the unmodified reference")
+    else:
+        for g, w in zip(got, want):
+            assert_image_parity(g, w)
+
+
+@pytest.mark.parametrize("w,h,n,maxdist", [(37, 21, 517, 44), (1, 1, 200, 44), (8, 4, 1, 44), (9, 5, 2, 10),
+                                             (131, 3, 64, 60), (3, 131, 33, 44)])
+def test_render_ragged_shapes(dev_cube1, cube1, w, h, n, maxdist):
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES[:3], 37.0, 21.0, w, h)
+    for tri in (False, True):
+        got = dev_cube1.render(fp, w, h, nsamples=n, maxdist=maxdist, trilinear=tri)
+        want = O.orc_render_cube(zyx, org, sp, tri, fo, w, h, nsamples=n, maxdist=maxdist)
+        assert_bit_exact(got, want, f"{w}x{h} n={n}")
+
+
+def test_render_golden_nondefault_march(dev_cube1, golden, cube1_matches_golden):
+    if not cube1_matches_golden:
+        pytest.skip("synthetic cube differs by an ulp on this CPU")
+    fp = capi.frames_for_poses(golden["poses"][:1], float(golden["aim_x"]), 37.0, 21.0, 37, 21)
+    assert_bit_exact(dev_cube1.render(fp, 37, 21, nsamples=517)[0], golden["cube_tri1_n517_w37_h21"])
+
+
+def test_render_twice_accumulates_like_reference(dev_cube1, golden, cube1_matches_golden, cube1):
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES[:1], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    once = dev_cube1.render(fp, W, H)
+    twice = dev_cube1.render(fp, W, H, images=once.copy())
+    want = O.orc_render_cube(zyx, org, sp, True, fo, W, H, images=O.orc_render_cube(zyx, org, sp, True, fo, W, H))
+    assert_bit_exact(twice, want)
+    if cube1_matches_golden:
+        assert_bit_exact(twice[0], golden["cube_tri1_twice"])
+
+
+def test_render_row_bands_tile_the_image(dev_cube1):
+    """row bands are the unit of multi-GPU image sharding: they tile the full image exactly"""
+    fp, _ = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    full = dev_cube1.render(fp, W, H)
+    tiled = np.zeros_like(full)
+    for r0, r1 in ((0, 9), (9, 10), (10, 41), (41, 64)):
+        band = dev_cube1.render(fp, W, H, rows=(r0, r1))
+        assert band[:, :r0].max(initial=0) == 0 and band[:, r1:].max(initial=0) == 0
+        tiled[:, r0:r1] = band[:, r0:r1]
+    assert_bit_exact(tiled, full)
+    # with BIRP_ACCUMULATE only the band's rows are read and written back
+    canvas = np.full_like(full, 3.0)
+    dev_cube1.render(fp, W, H, rows=(9, 10), images=canvas)
+    assert (canvas[:, :9] == 3.0).all() and (canvas[:, 10:] == 3.0).all() and (canvas[:, 9] > 3.0).all()
+
+
+def test_render_many_frames_chunked_pipeline(dev_cube1, cube1):
+    """more frames than one staging chunk of a larger image, odd count"""
+    zyx, org, sp = cube1
+    poses = S.orbit_poses(37)
+    fp, fo = frames_pair(poses, 36.0, 36.0, 512, 512)  # 1 MiB frames -> 16 per chunk -> 3 chunks
+    got = dev_cube1.render(fp, 512, 512, nsamples=40, trilinear=True)
+    want = O.orc_render_cube(zyx, org, sp, True, fo, 512, 512, nsamples=40)
+    assert_bit_exact(got, want)
+
+
+def test_render_nan_pose_reports_range_error(dev_cube1):
+    fr = capi.frame_setup((10.0, 0.0, 0.0), AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    assert np.isnan(fr["rinv"]).any()
+    with pytest.raises(capi.BirpError) as e:
+        dev_cube1.render(fr, W, H)
+    assert e.value.code == capi.BIRP_ERR_RANGE
+    ok = dev_cube1.render(capi.frame_setup(S.DEFAULT_POS, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H), W, H)
+    assert ok.min() > 0
+
+
+def test_render_zero_frames(dev_cube1):
+    out = dev_cube1.render(np.zeros(0, capi.FRAME_DTYPE), W, H)
+    assert out.shape == (0, H, W)
+
+
+def test_render_linearity_in_the_cube(gpu, cube1):
+    """scaling the emissivity by a power of two scales every pixel exactly"""
+    zyx, org, sp = cube1
+    fp, _ = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    a = capi.Cube(zyx, org, sp)
+    b = capi.Cube(zyx * np.float32(4.0), org, sp)
+    try:
+        assert_bit_exact(b.render(fp, W, H), a.render(fp, W, H) * np.float32(4.0))
+    finally:
+        a.free()
+        b.free()
+
+
+def test_render_constant_cube_counts_samples(gpu):
+    """a constant field integrates to (live samples) x constant: checks the termination prefix"""
+    zyx = np.full((33, 33, 33), 2.0 ** -10, np.float32)
+    org, sp = np.array([-8, -8, -8], np.float32), np.array([0.5, 0.5, 0.5], np.float32)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        fp, fo = frames_pair(np.array([(1.0, 2.0, 3.0)], np.float32), 36.0, 36.0, 64, 64)
+        for tri in (False, True):
+            got = c.render(fp, 64, 64, trilinear=tri)
+            want, valid = O.orc_render_cube(zyx, org, sp, tri, fo, 64, 64, return_valid=True)
+            assert_bit_exact(got, want)
+            assert 0 < valid < 64 * 64 * 200  # every ray leaves this small cube
+    finally:
+        c.free()
+
+
+# ------------------------------------------------------------------ full-size configs (BASELINE.json configs[2], [3])
+@pytest.mark.parametrize("n", [256])
+def test_config3_256cube_1024_image(gpu, n):
+    zyx, org, sp = S.make_cube(n, n, n)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        fp, fo = frames_pair(np.array([S.DEFAULT_POS], np.float32), 36.0, 36.0, 1024, 1024)
+        got = c.render(fp, 1024, 1024, nsamples=200, trilinear=True)
+        want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=200, nthreads=16)
+        assert_bit_exact(got, want, "256^3, 1024x1024, 200 samples")
+        # fine step: a row band against the oracle, the whole image through band-tiling consistency
+        fine = c.render(fp, 1024, 1024, nsamples=2048, trilinear=True)
+        want_band = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=2048, rows=(500, 532), nthreads=16)
+        assert_bit_exact(fine[:, 500:532], want_band[:, 500:532], "fine step band")
+        band = c.render(fp, 1024, 1024, nsamples=2048, trilinear=True, rows=(100, 228))
+        assert_bit_exact(band[:, 100:228], fine[:, 100:228])
+        # the fine march converges to the coarse one (same integral, step-size independent scale)
+        rel = abs(fine.sum(dtype=np.float64) - got.sum(dtype=np.float64)) / got.sum(dtype=np.float64)
+        assert rel < 5e-3
+    finally:
+        c.free()
+
+
+# ------------------------------------------------------------------ CMEM
+KA_DEFAULT = [((8, 4, 4), 0.0), ((4, 12, 10), 4.46853346e-06), ((3, 1.5, 1.2), 0.0), ((8, 10, 10), 8.15947317e-07),
+              ((8, -10, -10), 8.15947317e-07), ((8, 10, -10), 8.15947317e-07)]
+KA_TEST2 = [((8, 4, 4), 0.0), ((12, 12, 10), 4.57952495e-07), ((3, 1.5, 1.2), 0.0), ((12, 10, 10), 5.48567925e-07),
+            ((12, -10, -10), 5.48567925e-07), ((12, 10, -10), 5.48567925e-07)]
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("kw,answers", [({}, KA_DEFAULT), (O.CMEM_TEST2, KA_TEST2)])
+def test_cmem_known_answers_on_device(gpu, kw, answers, fast):
+    """the reference's own CMEM tests (tests/CMEM_test.cpp), evaluated by the device sampler"""
+    P = capi.cmem_init(**kw)
+    got = capi.sample_cmem(P, [p for p, _ in answers], fast=fast)
+    want = np.array([v for _, v in answers], np.float32)
+    np.testing.assert_allclose(got, want, rtol=(2e-6 if fast else 3e-7), atol=0)
+    assert got[3] == got[4] == got[5]  # mirror symmetry in y and z
+    if not fast:
+        assert_bit_exact(got, want, "precise mode reproduces the known answers bitwise")
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("kw", [{}, O.CMEM_CLI, O.CMEM_TEST2, dict(dipole=0.2, b=(1, -2, -6), v=(450, 10, -20))])
+def test_cmem_samples_vs_oracle(gpu, kw, fast):
+    P = capi.cmem_init(**kw)
+    Po = O.orc_cmem_init(**kw)
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([rng.uniform(-30, 30, size=(200000, 3)), [[0, 5, 5], [5, 0, 5], [0, 0, 9], [7, 0, 0]]])
+    got = capi.sample_cmem(P, pts, fast=fast)
+    want = O.orc_cmem_sample(Po, pts)
+    rel = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
+    rel[(got == 0) & (want == 0)] = 0
+    # region flips at the layer boundaries change a sample discontinuously; they must be rare
+    assert np.mean(rel <= 1e-5) > 0.9995, np.mean(rel <= 1e-5)
+    if not fast:
+        assert np.mean(got.view(np.uint32) == want.view(np.uint32)) > 0.90
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("name,kw", [("default", {}), ("cli", O.CMEM_CLI), ("test2", O.CMEM_TEST2)])
+def test_cmem_render_vs_oracle_and_golden(gpu, golden, name, kw, fast):
+    P = capi.cmem_init(**kw)
+    fp, fo = frames_pair(golden["poses"], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    got = capi.render_cmem(P, fp, W, H, fast=fast)
+    want = O.orc_render_cmem(O.orc_cmem_init(**kw), fo, W, H)
+    for g, w in zip(got, want):
+        assert assert_image_parity(g, w, f"cmem {name}") >= 0.99
+    for g, w in zip(got[:2], golden[f"cmem_{name}_images"]):
+        assert assert_image_parity(g, w, f"cmem {name} vs reference-rendered fixture") >= 0.99
+
+
+def test_cmem_row_bands_and_accumulate(gpu):
+    P = capi.cmem_init()
+    fp, _ = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    full = capi.render_cmem(P, fp, W, H)
+    band = capi.render_cmem(P, fp, W, H, rows=(17, 40))
+    assert_bit_exact(band[:, 17:40], full[:, 17:40])
+    assert band[:, :17].max() == 0 and band[:, 40:].max() == 0
+    twice = capi.render_cmem(P, fp, W, H, images=full.copy())
+    np.testing.assert_allclose(twice, 2 * full, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ K4: user-defined Space subclasses
+def test_accumulate_matches_oracle(gpu):
+    rng = np.random.default_rng(2)
+    s = rng.uniform(0, 1e-5, size=(6912, 200)).astype(np.float32)
+    s[::7, 50] = -1.0     # rays that die early
+    s[3, 0] = -1.0        # dies at the first sample
+    s[5, 10] = np.nan     # NaN is not < 0: it accumulates
+    _, w = capi.ray_table(200, 44)
+    got = capi.accumulate(s, w)
+    want = O.orc_accumulate(s, w)
+    assert_bit_exact(got, want)
+    assert got[3] == 0 and np.isnan(got[5])
+    # CubeFake of the reference tests (tests/Camera_test.cpp:25-29): constant 1.f
+    ones = np.ones((144 * 144, 200), np.float32)
+    assert_bit_exact(capi.accumulate(ones, w), O.orc_accumulate(ones, w))
+    img0 = rng.uniform(0, 1, size=6912).astype(np.float32)
+    assert_bit_exact(capi.accumulate(s, w, image=img0.copy()), O.orc_accumulate(s, w, image=img0.copy()))
+
+
+def test_scale_chain_exhaustive_slice(gpu):
+    """the fp64 scale (src/Camera.cpp:201): fast path + exact fallback must equal the plain chain
+    for every fp32 input; checked on a dense slice of bit patterns incl. subnormals, inf, NaN"""
+    _, w = capi.ray_table(200, 44)
+    pats = np.concatenate([
+        np.arange(0, 1 << 32, 4099, dtype=np.uint64),
+        np.arange(0x00000000, 0x00002000, dtype=np.uint64),  # subnormals
+        np.arange(0x7F7FF000, 0x7F802000, dtype=np.uint64),  # around +inf
+        np.arange(0x3A000000, 0x3A100000, dtype=np.uint64),  # a dense run of ordinary values
+    ]).astype(np.uint32)
+    s = pats.view(np.float32).reshape(-1, 1)
+    got = capi.accumulate(s, w)
+    want = O.orc_accumulate(s, w)
+    assert_bit_exact(got, want)
+
+
+# ------------------------------------------------------------------ device-buffer entry points (what bench.py times)
+def test_device_entry_points_match_host_entry_points(dev_cube1):
+    torch = pytest.importorskip("torch")
+    fp, _ = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    want = dev_cube1.render(fp, W, H)
+    d_frames = torch.from_numpy(fp.view(np.float32).reshape(-1, 16).copy()).cuda()
+    d_images = torch.full((len(fp), H, W), -1.0, device="cuda")
+    d_valid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    capi.render_cube_device(dev_cube1, d_frames.data_ptr(), len(fp), W, H, d_images.data_ptr(),
+                            d_valid=d_valid.data_ptr(), stream=stream)
+    capi.check_device_status(stream)
+    assert_bit_exact(d_images.cpu().numpy(), want)
+    assert 0 < int(d_valid.item()) <= len(fp) * W * H * 200
+    P = capi.cmem_init()
+    capi.render_cmem_device(P, d_frames.data_ptr(), len(fp), W, H, d_images.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    assert_bit_exact(d_images.cpu().numpy(), capi.render_cmem(P, fp, W, H))
+    assert capi.launch_count() > 0
