@@ -31,8 +31,10 @@ def assert_bit_exact(got, want, what=""):
     want = np.asarray(want, dtype=np.float32)
     assert got.shape == want.shape, f"{what}: shape {got.shape} vs {want.shape}"
     bad = bits(got) != bits(want)
-    # +0 and -0 compare equal as pixels; NaNs must match as NaNs
+    # +0 and -0 compare equal as pixels; a NaN must be matched by a NaN (payload bits are not
+    # preserved by the GPU's arithmetic and carry no meaning here)
     bad &= ~((got == 0) & (want == 0))
+    bad &= ~(np.isnan(got) & np.isnan(want))
     n = int(bad.sum())
     if n:
         idx = np.argwhere(bad)[:5]
