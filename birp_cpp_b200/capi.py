@@ -18,6 +18,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
+DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP = 8, 16, 32
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "birp_cube_upload": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.POINTER(_vp)]),
     "birp_cube_upload_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _vp, C.POINTER(_vp)]),
     "birp_cube_free": (None, [_vp]),
+    "birp_cube_info": (C.c_int, [_vp, _i32p]),
     "birp_render_cube": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_accumulate": (C.c_int, [_vp, C.c_long, C.c_int, C.c_float, C.c_int, _vp]),
@@ -217,6 +219,11 @@ class Cube:
         except Exception:
             pass
 
+    def info(self) -> dict:
+        out = (C.c_int * 2)()
+        _check(lib().birp_cube_info(self._h, out))
+        return {"divmode": int(out[0]), "positive": bool(out[1])}
+
     def sample(self, xyz, trilinear: bool) -> np.ndarray:
         xyz = _f32(xyz).reshape(-1, 3)
         out = np.empty(len(xyz), dtype=np.float32)
@@ -225,11 +232,11 @@ class Cube:
 
     def render(self, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
                trilinear: bool = True, rows=(0, 0), images: np.ndarray | None = None,
-               out: np.ndarray | None = None) -> np.ndarray:
+               out: np.ndarray | None = None, extra_flags: int = 0) -> np.ndarray:
         """Host-buffer render.  `images` given => accumulated into (BIRP_ACCUMULATE);
         `out` given => overwritten (rows outside the band untouched); neither => new zeros."""
         frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
-        flags = TRILINEAR if trilinear else NEAREST
+        flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
         if images is not None:
             flags |= ACCUMULATE
         elif out is not None:

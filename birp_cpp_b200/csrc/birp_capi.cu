@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -21,6 +22,29 @@ struct birp_cube {
     int device;
     size_t voxels;
 };
+
+// smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
+// index = ingress / spacing in fp32 (src/DataCube.cpp:205-218).  The test is monotone in the
+// ingress, so a bisection over the fp32 bit patterns finds the exact threshold.
+static float bounds_limit(float spacing, int n) {
+    auto rejected = [&](unsigned bits) {
+        float xi;
+        std::memcpy(&xi, &bits, sizeof(xi));
+        const volatile float index = xi / spacing;
+        const volatile float plus1 = index + 1;
+        return plus1 >= (float)n;
+    };
+    unsigned lo = 0, hi = 0x7f800000u;  // +0 .. +inf (always rejected)
+    if (rejected(lo)) return 0.f;
+    while (hi - lo > 1) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (rejected(mid)) hi = mid;
+        else lo = mid;
+    }
+    float out;
+    std::memcpy(&out, &hi, sizeof(out));
+    return out;
+}
 
 namespace {
 
@@ -65,6 +89,10 @@ struct DeviceCtx {
     size_t scratch_cap = 0;  // floats
     int* d_status = nullptr;
     int* h_status = nullptr;  // pinned
+    int* d_flags = nullptr;   // 4 ints of scratch for the upload-time analysis kernels
+    // spacing bits + limit bits -> cheapest exact div_spacing mode (0, 1, 2), proven on this device
+    std::map<std::pair<unsigned, unsigned>, int> divmode_cache;
+    int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
     std::mutex mu;
 };
 
@@ -93,7 +121,9 @@ int get_ctx(DeviceCtx** out) {
     }
     BIRP_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
     BIRP_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
-    BIRP_CUDA(cudaHostAlloc(&c->h_status, sizeof(int), cudaHostAllocDefault));
+    BIRP_CUDA(cudaHostAlloc(&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
+    BIRP_CUDA(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
+    if (const char* t = getenv("BIRP_TILE_W_LOG2")) c->tile_w_log2 = atoi(t);
     g_ctx[dev] = c;
     *out = c;
     return BIRP_OK;
@@ -205,6 +235,7 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             }
         }
         birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
+        g.tile_w_log2 = c->tile_w_log2;
         cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
         if (e != cudaSuccess)
             return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -279,10 +310,63 @@ int birp_cmem_init(int has_v, const int v[3], int has_b, const int b[3], float d
     return BIRP_OK;
 }
 
+// Upload-time analysis of a resident cube: reciprocal spacings, bounds limits, the cheapest
+// division variant that is EXACT for this cube (exhaustive device check, cached per spacing),
+// and whether all voxels are finite and positive.
+static int finish_cube(DeviceCtx* c, birp_cube* cube) {
+    birp::CubeView& v = cube->view;
+    const float sp[3] = {v.sx, v.sy, v.sz};
+    const int n[3] = {v.nx, v.ny, v.nz};
+    float rcp[3], lim[3];
+    int mode = 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (int a = 0; a < 3; ++a) {
+        const volatile float r = 1.0f / sp[a];
+        rcp[a] = r;
+        lim[a] = bounds_limit(sp[a], n[a]);
+        unsigned sbits, lbits;
+        std::memcpy(&sbits, &sp[a], 4);
+        std::memcpy(&lbits, &lim[a], 4);
+        auto key = std::make_pair(sbits, lbits);
+        auto it = c->divmode_cache.find(key);
+        int m;
+        if (it != c->divmode_cache.end()) {
+            m = it->second;
+        } else {
+            BIRP_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute));
+            cudaError_t e = birp::launch_verify_div(sp[a], rcp[a], lbits, c->d_flags, c->compute);
+            if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "verify_div launch: %s", cudaGetErrorString(e));
+            BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+            BIRP_CUDA(cudaStreamSynchronize(c->compute));
+            m = (c->h_status[0] == 0) ? 0 : (c->h_status[1] == 0) ? 1 : 2;
+            c->divmode_cache[key] = m;
+        }
+        if (m > mode) mode = m;
+    }
+    BIRP_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute));
+    cudaError_t e = birp::launch_scan_positive(cube->d_data, cube->voxels, c->d_flags, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "scan_positive launch: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    v.positive = (c->h_status[0] == 0) ? 1 : 0;
+    *c->h_status = 0;
+    v.rx = rcp[0];
+    v.ry = rcp[1];
+    v.rz = rcp[2];
+    v.lx = lim[0];
+    v.ly = lim[1];
+    v.lz = lim[2];
+    v.divmode = mode;
+    return BIRP_OK;
+}
+
 static int make_cube(const float* src, bool src_on_device, int nx, int ny, int nz, const float origin[3],
                      const float spacing[3], cudaStream_t stream, birp_cube** out) {
     if (!src || !origin || !spacing || !out) return set_error(BIRP_ERR_ARG, "null pointer");
     if (nx <= 0 || ny <= 0 || nz <= 0) return set_error(BIRP_ERR_ARG, "bad cube size %dx%dx%d", nx, ny, nz);
+    for (int a = 0; a < 3; ++a)
+        if (!(spacing[a] > 0.f) || std::isinf(spacing[a]) || std::isnan(origin[a]) || std::isinf(origin[a]))
+            return set_error(BIRP_ERR_ARG, "cube spacing must be positive and finite, origin finite");
     const size_t voxels = (size_t)nx * ny * nz;
     if (voxels >= (size_t(1) << 31)) return set_error(BIRP_ERR_ARG, "cube has >= 2^31 voxels");
     DeviceCtx* c;
@@ -322,6 +406,12 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.sx = spacing[0];
     v.sy = spacing[1];
     v.sz = spacing[2];
+    rc = finish_cube(c, cube);
+    if (rc) {
+        cudaFree(cube->d_data);
+        delete cube;
+        return rc;
+    }
     *out = cube;
     return BIRP_OK;
 }
@@ -334,6 +424,13 @@ int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origi
 int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const float origin[3],
                             const float spacing[3], void* stream, birp_cube** out) {
     return make_cube(d_zyx, true, nx, ny, nz, origin, spacing, (cudaStream_t)stream, out);
+}
+
+int birp_cube_info(const birp_cube* cube, int info[2]) {
+    if (!cube || !info) return set_error(BIRP_ERR_ARG, "null pointer");
+    info[0] = cube->view.divmode;
+    info[1] = cube->view.positive;
+    return BIRP_OK;
 }
 
 void birp_cube_free(birp_cube* cube) {
@@ -457,6 +554,7 @@ int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, i
         if (rc) return rc;
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    g.tile_w_log2 = c->tile_w_log2;
     cudaError_t e = birp::launch_render_cube(cube->view, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, c->d_status, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -479,6 +577,7 @@ int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_
         if (rc) return rc;
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    g.tile_w_log2 = c->tile_w_log2;
     cudaError_t e = birp::launch_render_cmem(*params, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));

@@ -23,7 +23,32 @@ struct CubeView {
     float fnx, fny, fnz;  // (float)size.{x,y,z}: right-hand side of the reference's bounds test
     float ox, oy, oz;     // coords_{x,y,z}[0]
     float sx, sy, sz;     // spacing[0..2]
+    // ---- derived once at upload (birp_capi.cu: finish_cube) ----
+    float rx, ry, rz;     // RN(1 / spacing), for div_spacing
+    float lx, ly, lz;     // smallest ingress >= 0 that the reference's bounds test rejects
+    int divmode;          // cheapest div_spacing variant proven exact for all three axes (0,1) or 2
+    int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch)
 };
+
+// ingress / spacing, correctly rounded.
+//   MODE 2: IEEE division.
+//   MODE 0/1: multiply by the correctly rounded reciprocal, then one / two residual corrections.
+// MODE 0 and 1 are only selected for a cube after an EXHAUSTIVE device-side comparison with
+// __fdiv_rn over every fp32 ingress the bounds test can let through (0 <= a < limit), for each
+// axis spacing (verify_div_kernel), so the quotient -- and with it the voxel index and the
+// interpolation weight -- is bit-identical to the reference's `x_ingress / spacing[0]`.
+template <int MODE>
+__device__ __forceinline__ float div_spacing(float a, float s, float r) {
+    if (MODE == 2) return __fdiv_rn(a, s);
+    float q = __fmul_rn(a, r);
+    float e = __fmaf_rn(-q, s, a);
+    q = __fmaf_rn(e, r, q);
+    if (MODE == 1) {
+        e = __fmaf_rn(-q, s, a);
+        q = __fmaf_rn(e, r, q);
+    }
+    return q;
+}
 
 // The fp32 -> fp64 -> fp32 scale of reference src/Camera.cpp:201,
 //   sample = (sample * ray_width * (1000 * 100 * 6378.1) / (4 / M_PI)) / 10000;
@@ -152,6 +177,83 @@ __device__ __forceinline__ float cube_sample(const CubeView& c, float x, float y
     const float low_y = lerp_ref(low_x1, low_x2, ty);
     const float high_y = lerp_ref(high_x1, high_x2, ty);
     return lerp_ref(low_y, high_y, tz);
+}
+
+// std::lerp restricted to what a strictly positive, finite cube can feed it: a, b > 0 and
+// t in [0,1).  The sign branch of __lerp is never taken, t == 1 and t > 1 cannot happen, and
+// no NaN can appear, so   (t>1)==(b>a) ? (b<x?x:b) : (b>x?x:b)   is min(x,b) when b > a and
+// max(x,b) otherwise.
+__device__ __forceinline__ float lerp_pos(float a, float b, float t) {
+    const float x = __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+    return (b > a) ? fminf(x, b) : fmaxf(x, b);
+}
+
+// Hot-path form of DataCube::GetSample for the march kernel.  Same results as cube_sample();
+// what changes is the cost:
+//  * the bounds test `0 > ingress || index + 1 >= size` is monotone in the ingress, so it is
+//    a comparison against a precomputed limit (c.l?) -- no division for dead samples;
+//  * the division by the spacing is div_spacing<DIVMODE>;
+//  * the eight corners are read at fixed offsets from one base address (x0+1, y0+1, z0+1 are
+//    always inside the grid for an in-bounds sample); on an exact integer index the reference
+//    reads the same voxel twice (ceil == floor) -- with weight 0 that gives the same result
+//    for finite data (POSITIVE), otherwise the duplicate is selected explicitly.
+// Returns false when the sample is not inside the bounds window (dead ray or NaN coordinate:
+// the caller takes the slow path), true with the sample in `out` otherwise.
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE>
+__device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, float y, float z, float& out) {
+    const float xi = __fsub_rn(x, c.ox);
+    const float yi = __fsub_rn(y, c.oy);
+    const float zi = __fsub_rn(z, c.oz);
+    const bool inb = (xi >= 0.f) && (xi < c.lx) && (yi >= 0.f) && (yi < c.ly) && (zi >= 0.f) && (zi < c.lz);
+    if (!inb) return false;
+    const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
+    const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);
+    const float fz = div_spacing<DIVMODE>(zi, c.sz, c.rz);
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const int row = c.nx;
+    const int slab = c.nx * c.ny;
+    const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
+    if (!TRILINEAR) {
+        out = __ldg(p);
+        return true;
+    }
+    const float tx = __fsub_rn(fx, (float)x0);
+    const float ty = __fsub_rn(fy, (float)y0);
+    const float tz = __fsub_rn(fz, (float)z0);
+    const float s000 = __ldg(p);
+    const float l001 = __ldg(p + 1);
+    const float l010 = __ldg(p + row);
+    const float l011 = __ldg(p + row + 1);
+    const float l100 = __ldg(p + slab);
+    const float l101 = __ldg(p + slab + 1);
+    const float l110 = __ldg(p + slab + row);
+    const float l111 = __ldg(p + slab + row + 1);
+    if (POSITIVE) {
+        const float low_x1 = lerp_pos(s000, l001, tx);
+        const float low_x2 = lerp_pos(l010, l011, tx);
+        const float high_x1 = lerp_pos(l100, l101, tx);
+        const float high_x2 = lerp_pos(l110, l111, tx);
+        const float low_y = lerp_pos(low_x1, low_x2, ty);
+        const float high_y = lerp_pos(high_x1, high_x2, ty);
+        out = lerp_pos(low_y, high_y, tz);
+        return true;
+    }
+    const bool ux = tx > 0.f, uy = ty > 0.f, uz = tz > 0.f;
+    const float s010 = uy ? l010 : s000;
+    const float s100 = uz ? l100 : s000;
+    const float s110 = uz ? (uy ? l110 : l100) : s010;
+    const float s001 = ux ? l001 : s000;
+    const float s011 = ux ? (uy ? l011 : l001) : s010;
+    const float s101 = ux ? (uz ? l101 : l001) : s100;
+    const float s111 = ux ? (uz ? (uy ? l111 : l101) : s011) : s110;
+    const float low_x1 = lerp_ref(s000, s001, tx);
+    const float low_x2 = lerp_ref(s010, s011, tx);
+    const float high_x1 = lerp_ref(s100, s101, tx);
+    const float high_x2 = lerp_ref(s110, s111, tx);
+    const float low_y = lerp_ref(low_x1, low_x2, ty);
+    const float high_y = lerp_ref(high_x1, high_x2, ty);
+    out = lerp_ref(low_y, high_y, tz);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------

@@ -12,6 +12,10 @@ struct RenderGeom {
     int row_begin, row_end;  // rows [row_begin,row_end) of every frame are rendered
     int nsamples;
     float ray_width;
+    // angular size of one pixel step in x / y (any common unit) and an optional forced tile
+    // width (log2, -1 = choose from the angles); only used to shape the per-warp pixel tile
+    float pixel_angle_x = 0.f, pixel_angle_y = 0.f;
+    int tile_w_log2 = -1;
 };
 
 // bit in the device status word
@@ -29,6 +33,10 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
                                int* d_status, cudaStream_t stream);
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
                                float* d_out, cudaStream_t stream);
+
+// upload-time analysis of a resident cube (see CubeView)
+cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream);
+cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 
 unsigned long long launch_count();
 

@@ -21,8 +21,6 @@ namespace {
 
 std::atomic<unsigned long long> g_launches{0};
 
-constexpr int kTileW = 8;
-constexpr int kTileH = 4;
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
@@ -35,6 +33,7 @@ struct MarchArgs {
     int W, H;
     int row_begin, rows;
     int nsamples;
+    int tile_w_log2;  // a warp's 32 rays form a (1 << tile_w_log2) x (32 >> tile_w_log2) pixel tile
     int tiles_x, tiles_per_frame;
     long long total_tiles;
     float ray_width;
@@ -57,20 +56,26 @@ struct CmemField {
     }
 };
 
-template <class Field>
-__global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a, const Field field) {
+// Which ray this lane owns; false when the lane falls outside the image / row band.
+__device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int& j) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (tile >= a.total_tiles) return;
-    const int f = (int)(tile / a.tiles_per_frame);
+    if (tile >= a.total_tiles) return false;
+    f = (int)(tile / a.tiles_per_frame);
     const int t = (int)(tile - (long long)f * a.tiles_per_frame);
     const int ty = t / a.tiles_x;
     const int tx = t - ty * a.tiles_x;
-    const int i = tx * kTileW + (lane & (kTileW - 1));
-    const int jr = ty * kTileH + (lane / kTileW);
-    if (i >= a.W || jr >= a.rows) return;
-    const int j = a.row_begin + jr;
+    i = (tx << a.tile_w_log2) + (lane & ((1 << a.tile_w_log2) - 1));
+    const int jr = ty * (32 >> a.tile_w_log2) + (lane >> a.tile_w_log2);
+    j = a.row_begin + jr;
+    return i < a.W && jr < a.rows;
+}
 
+// Generic march: any Field functor (used for CMEM; the DataCube path has its own kernel below).
+template <class Field>
+__global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a, const Field field) {
+    int f, i, j;
+    if (!lane_ray(a, f, i, j)) return;
     const birp_frame fr = a.frames[f];
     float dx, dy, dz;
     pixel_direction(fr, i, j, (float)a.W, (float)a.H, dx, dy, dz);
@@ -93,15 +98,79 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
         ++nvalid;
     }
     *pix = acc;
-    if (nan_index) atomicOr(a.status, kStatusNanIndex);
+    if (nan_index && a.status) atomicOr(a.status, kStatusNanIndex);
     if (a.valid) atomicAdd(a.valid, (unsigned long long)nvalid);
 }
 
-template <class Field>
-cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const RenderGeom& g,
-                         const float* d_dist, int flags, float* d_images, unsigned long long* d_valid,
-                         int* d_status, cudaStream_t stream) {
-    MarchArgs a;
+// DataCube march (K1/K3).  One lane per ray; per step: position (6 flops), bounds window
+// (6 compares), 3 exact divisions by the spacing, 8 corner loads at fixed offsets from one
+// base address, 7 lerps, the fp64 scale, the fp32 accumulate.  Everything a sample outside
+// the window needs (dead ray, NaN coordinate) is on the cold side of one branch.
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE>
+__global__ void __launch_bounds__(kBlockThreads) march_cube_kernel(const MarchArgs a, const CubeView c) {
+    int f, i, j;
+    if (!lane_ray(a, f, i, j)) return;
+    const birp_frame* __restrict__ frp = a.frames + f;
+    float dx, dy, dz;
+    pixel_direction(*frp, i, j, (float)a.W, (float)a.H, dx, dy, dz);
+    const float px = frp->pos[0], py = frp->pos[1], pz = frp->pos[2];
+
+    float* pix = a.images + ((size_t)f * a.H + j) * a.W + i;
+    float acc = a.accumulate ? *pix : 0.f;
+    bool nan_index = false;
+    const float ray_width = a.ray_width;
+    const float* __restrict__ dist = a.dist;
+    int k = 0;
+    for (; k < a.nsamples; ++k) {
+        const float tk = __ldg(dist + k);
+        const float x = __fadd_rn(__fmul_rn(dx, tk), px);
+        const float y = __fadd_rn(__fmul_rn(dy, tk), py);
+        const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
+        float s;
+        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE>(c, x, y, z, s)) {
+            // outside the window: the reference returns -1 (which ends the ray unless the
+            // scaled value is not negative, e.g. a zero ray width), or, for a NaN coordinate
+            // that passes its comparisons, throws from .at()
+            const float xi = __fsub_rn(x, c.ox), yi = __fsub_rn(y, c.oy), zi = __fsub_rn(z, c.oz);
+            const bool oob = (0.f > xi || xi >= c.lx) || (0.f > yi || yi >= c.ly) || (0.f > zi || zi >= c.lz);
+            if (!oob) nan_index = true;
+            s = oob ? -1.f : 0.f;
+        }
+        s = scale_sample(s, ray_width);
+        if (s < 0.f) break;
+        acc = __fadd_rn(acc, s);
+    }
+    *pix = acc;
+    if (nan_index) atomicOr(a.status, kStatusNanIndex);
+    if (a.valid) atomicAdd(a.valid, (unsigned long long)k);
+}
+
+// Tile shape: split the warp's 32 rays so that the tile is as square as possible in ANGLE
+// (the SXI pixel is 1.7x wider than tall once the reference's extra aspect factor is applied):
+// compact ray bundles touch fewer cache lines per corner load.
+int pick_tile_w_log2(const RenderGeom& g) {
+    if (g.tile_w_log2 >= 0 && g.tile_w_log2 <= 5) return g.tile_w_log2;
+    // default: the reference ties the image size to the field of view (W ~ fov_w / px,
+    // H ~ fov_h / px) and then stretches x by W/H once more, so a pixel step in x spans about
+    // W/H times the angle of a step in y
+    const double ax = g.pixel_angle_x > 0 ? g.pixel_angle_x : (double)g.W;
+    const double ay = g.pixel_angle_y > 0 ? g.pixel_angle_y : (double)g.H;
+    int best = 3;
+    double best_cost = 1e300;
+    for (int l = 0; l <= 5; ++l) {
+        const int tw = 1 << l, th = 32 >> l;
+        if (tw > 2 * g.W && l > 0) continue;
+        const double cost = tw * ax + th * ay;  // half-perimeter of the tile's angular footprint
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = l;
+        }
+    }
+    return best;
+}
+
+bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, const float* d_dist, int flags,
+               float* d_images, unsigned long long* d_valid, int* d_status, unsigned* blocks) {
     a.frames = d_frames;
     a.dist = d_dist;
     a.images = d_images;
@@ -112,17 +181,63 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     a.row_begin = g.row_begin;
     a.rows = g.row_end - g.row_begin;
     a.nsamples = g.nsamples;
-    a.tiles_x = (g.W + kTileW - 1) / kTileW;
-    a.tiles_per_frame = a.tiles_x * ((a.rows + kTileH - 1) / kTileH);
+    a.tile_w_log2 = pick_tile_w_log2(g);
+    const int tw = 1 << a.tile_w_log2, th = 32 >> a.tile_w_log2;
+    a.tiles_x = (g.W + tw - 1) / tw;
+    a.tiles_per_frame = a.tiles_x * ((a.rows + th - 1) / th);
     a.total_tiles = (long long)a.tiles_per_frame * g.nframes;
     a.ray_width = g.ray_width;
     a.accumulate = (flags & BIRP_ACCUMULATE) ? 1 : 0;
+    const long long nb = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    *blocks = (unsigned)nb;
+    return nb <= 0x7fffffffLL;
+}
+
+template <class Field>
+cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const RenderGeom& g,
+                         const float* d_dist, int flags, float* d_images, unsigned long long* d_valid,
+                         int* d_status, cudaStream_t stream) {
+    MarchArgs a;
+    unsigned blocks;
+    if (!fill_args(a, d_frames, g, d_dist, flags, d_images, d_valid, d_status, &blocks))
+        return cudaErrorInvalidConfiguration;
     if (a.total_tiles <= 0) return cudaSuccess;
-    const long long blocks = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    march_kernel<Field><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(a, field);
+    march_kernel<Field><<<blocks, kBlockThreads, 0, stream>>>(a, field);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
+}
+
+template <bool TRI, int DIV, bool POS>
+cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
+    march_cube_kernel<TRI, DIV, POS><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    return cudaGetLastError();
+}
+
+// ---- upload-time analysis kernels -------------------------------------------------------
+// flag |= 1 unless every voxel is finite and > 0
+__global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restrict__ v, size_t n, int* flag) {
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = __ldg(v + i);
+        bad |= !(x > 0.f && x < CUDART_INF_F);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// Exhaustive proof for one spacing: for EVERY fp32 ingress a with 0 <= a < limit (all bit
+// patterns below limit_bits), do the cheap quotients equal the IEEE one?  bad[0] / bad[1]
+// are set when div_spacing<0> / div_spacing<1> ever differs from __fdiv_rn.
+__global__ void __launch_bounds__(256) verify_div_kernel(float s, float r, unsigned limit_bits, int* bad) {
+    bool b0 = false, b1 = false;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < limit_bits;
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float a = __uint_as_float((unsigned)u);
+        const unsigned want = __float_as_uint(__fdiv_rn(a, s));
+        b0 |= __float_as_uint(div_spacing<0>(a, s, r)) != want;
+        b1 |= __float_as_uint(div_spacing<1>(a, s, r)) != want;
+    }
+    if (__any_sync(0xffffffffu, b0) && (threadIdx.x & 31) == 0) atomicOr(bad + 0, 1);
+    if (__any_sync(0xffffffffu, b1) && (threadIdx.x & 31) == 0) atomicOr(bad + 1, 1);
 }
 
 // K4: one thread per ray, samples[ray][k] (row-major, as the host sampled them)
@@ -169,12 +284,47 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames, const RenderGeom& g,
                                const float* d_dist, int flags, float* d_images,
                                unsigned long long* d_valid, int* d_status, cudaStream_t stream) {
-    if (flags & BIRP_TRILINEAR) {
-        CubeField<true> f{cube};
-        return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, d_status, stream);
+    MarchArgs a;
+    unsigned blocks;
+    if (!fill_args(a, d_frames, g, d_dist, flags, d_images, d_valid, d_status, &blocks))
+        return cudaErrorInvalidConfiguration;
+    if (a.total_tiles <= 0) return cudaSuccess;
+    const bool tri = (flags & BIRP_TRILINEAR) != 0;
+    const bool pos = cube.positive != 0 && !(flags & BIRP_GENERAL_LERP);
+    int divmode = cube.divmode;
+    if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
+    if (flags & BIRP_DIV_IEEE) divmode = 2;
+    cudaError_t e;
+#define BIRP_CUBE_CASE(T, D, P) e = launch_cube_variant<T, D, P>(a, cube, blocks, stream)
+    switch (divmode) {
+        case 0:
+            if (tri) { if (pos) BIRP_CUBE_CASE(true, 0, true); else BIRP_CUBE_CASE(true, 0, false); }
+            else BIRP_CUBE_CASE(false, 0, false);
+            break;
+        case 1:
+            if (tri) { if (pos) BIRP_CUBE_CASE(true, 1, true); else BIRP_CUBE_CASE(true, 1, false); }
+            else BIRP_CUBE_CASE(false, 1, false);
+            break;
+        default:
+            if (tri) { if (pos) BIRP_CUBE_CASE(true, 2, true); else BIRP_CUBE_CASE(true, 2, false); }
+            else BIRP_CUBE_CASE(false, 2, false);
+            break;
     }
-    CubeField<false> f{cube};
-    return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, d_status, stream);
+#undef BIRP_CUBE_CASE
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e;
+}
+
+cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream) {
+    scan_positive_kernel<<<148 * 8, 256, 0, stream>>>(d_v, n, d_flag);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream) {
+    verify_div_kernel<<<148 * 16, 256, 0, stream>>>(s, r, limit_bits, d_bad2);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame* d_frames,

@@ -51,8 +51,12 @@ enum {
     BIRP_ACCUMULATE = 2,     /* start each pixel from the value already in `images`
                                 (the reference never clears Camera::image, src/Camera.cpp:223);
                                 without it pixels start from 0 and `images` is overwritten */
-    BIRP_CMEM_FAST = 4       /* CMEM only: evaluate the transcendental calls in fp32 libdevice
+    BIRP_CMEM_FAST = 4,      /* CMEM only: evaluate the transcendental calls in fp32 libdevice
                                 instead of fp64-then-round */
+    /* diagnostics: force the slower, equally exact kernel variants (see DESIGN.md "variants") */
+    BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
+    BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
+    BIRP_GENERAL_LERP = 32   /* full std::lerp semantics even for an all-positive cube */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */
@@ -114,6 +118,9 @@ int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origi
 int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const float origin[3],
                             const float spacing[3], void* stream, birp_cube** out);
 void birp_cube_free(birp_cube* cube);
+/* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
+   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0 */
+int birp_cube_info(const birp_cube* cube, int info[2]);
 
 /* ------------------------------------------------------------------ the hot path, host buffers
  * frames: nframes records (host).  images: nframes*H*W floats (host), row j = image y, top row

@@ -83,6 +83,51 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
     assert want[0].min() > 0 and want[2].max() == 0  # inside / outside the cube
 
 
+@pytest.mark.parametrize("tri", [False, True])
+@pytest.mark.parametrize("neg", [False, True])
+@pytest.mark.parametrize("extra", [0, capi.DIV_TWO_STEP, capi.DIV_IEEE, capi.GENERAL_LERP,
+                                   capi.DIV_IEEE | capi.GENERAL_LERP, capi.DIV_TWO_STEP | capi.GENERAL_LERP])
+def test_every_kernel_variant_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tri, neg, extra):
+    """all template variants of the DataCube march kernel (division x lerp flavour) agree with the oracle"""
+    zyx, org, sp = cube1_neg if neg else cube1
+    dev = dev_cube1_neg if neg else dev_cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    got = dev.render(fp, W, H, trilinear=tri, extra_flags=extra)
+    assert_bit_exact(got, O.orc_render_cube(zyx, org, sp, tri, fo, W, H), f"flags={extra}")
+
+
+def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
+    a, b = dev_cube1.info(), dev_cube1_neg.info()
+    assert a["positive"] and not b["positive"]
+    assert a["divmode"] in (0, 1, 2) and a["divmode"] == b["divmode"]
+    print("division variant proven exact for spacing 0.5:", a["divmode"])
+    # awkward spacings: whatever variant is chosen, the renders must stay bit-exact
+    rng = np.random.default_rng(9)
+    for sp in (0.3137255, 1.0 / 3.0, 0.1, 0.7, 1.9999999):
+        zyx = rng.uniform(1e-7, 1e-5, size=(24, 20, 28)).astype(np.float32)
+        zyx[3, 4, 5] = 0.0  # one zero voxel: not "positive" any more
+        org = np.array([-3.3, -2.9, -3.1], np.float32)
+        spacing = np.array([sp, sp * 1.25, sp * 0.8], np.float32)
+        c = capi.Cube(zyx, org, spacing)
+        try:
+            assert not c.info()["positive"]
+            fp, fo = frames_pair(np.array([(0.5, 0.25, 1.0), (1.0, -1.0, 0.5)], np.float32), 36.0, 36.0, 48, 48)
+            for tri in (False, True):
+                got = c.render(fp, 48, 48, nsamples=300, maxdist=12, trilinear=tri)
+                want = O.orc_render_cube(zyx, org, spacing, tri, fo, 48, 48, nsamples=300, maxdist=12)
+                assert_bit_exact(got, want, f"spacing {sp} tri={tri} divmode={c.info()['divmode']}")
+        finally:
+            c.free()
+
+
+def test_bad_spacing_rejected(gpu):
+    zyx = np.ones((4, 4, 4), np.float32)
+    for sp in ((0.0, 1, 1), (1, -1.0, 1), (1, 1, np.nan), (np.inf, 1, 1)):
+        with pytest.raises(capi.BirpError) as e:
+            capi.Cube(zyx, (0, 0, 0), sp)
+        assert e.value.code == capi.BIRP_ERR_ARG
+
+
 @pytest.mark.parametrize("name", ["cube", "cubeneg"])
 @pytest.mark.parametrize("tri", [0, 1])
 def test_render_golden_reference_images(dev_cube1, dev_cube1_neg, golden, cube1_matches_golden, name, tri):
