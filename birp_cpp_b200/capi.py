@@ -66,6 +66,7 @@ SIGNATURES = {
     "birp_render_cube": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_accumulate": (C.c_int, [_vp, C.c_long, C.c_int, C.c_float, C.c_int, _vp]),
+    "birp_ray_directions": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "birp_sample_cube": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
     "birp_sample_cmem": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
     "birp_render_cube_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
@@ -274,6 +275,13 @@ def sample_cmem(params: np.ndarray, xyz, fast: bool = False) -> np.ndarray:
     xyz = _f32(xyz).reshape(-1, 3)
     out = np.empty(len(xyz), dtype=np.float32)
     _check(lib().birp_sample_cmem(_ptr(params), _ptr(xyz), len(xyz), CMEM_FAST if fast else 0, _ptr(out)))
+    return out
+
+
+def ray_directions(frame: np.ndarray, W: int, H: int) -> np.ndarray:
+    frame = np.ascontiguousarray(frame, dtype=FRAME_DTYPE).reshape(-1)[:1]
+    out = np.empty((H, W, 3), dtype=np.float32)
+    _check(lib().birp_ray_directions(_ptr(frame), W, H, _ptr(out)))
     return out
 
 

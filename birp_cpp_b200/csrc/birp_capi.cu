@@ -497,6 +497,26 @@ int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_wi
     return BIRP_OK;
 }
 
+int birp_ray_directions(const birp_frame* frame, int W, int H, float* dirs) {
+    if (!frame || !dirs) return set_error(BIRP_ERR_ARG, "null pointer");
+    if (W <= 0 || H <= 0 || (long)W * H > (1L << 30)) return set_error(BIRP_ERR_ARG, "bad image size");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = (size_t)W * H * 3;
+    rc = ensure(&c->d_scratch, &c->scratch_cap, n + 16);
+    if (rc) return rc;
+    birp_frame* d_frame = reinterpret_cast<birp_frame*>(c->d_scratch);
+    float* d_dirs = c->d_scratch + 16;
+    BIRP_CUDA(cudaMemcpyAsync(d_frame, frame, sizeof(birp_frame), cudaMemcpyHostToDevice, c->compute));
+    cudaError_t e = birp::launch_ray_directions(d_frame, W, H, d_dirs, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(dirs, d_dirs, n * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    return BIRP_OK;
+}
+
 int birp_sample_cube(const birp_cube* cube, const float* xyz, long n, int flags, float* out) {
     if (!cube || !xyz || !out) return set_error(BIRP_ERR_ARG, "null pointer");
     if (n < 0) return set_error(BIRP_ERR_ARG, "negative count");

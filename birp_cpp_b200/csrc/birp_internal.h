@@ -34,6 +34,8 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
                                float* d_out, cudaStream_t stream);
 
+cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream);
+
 // upload-time analysis of a resident cube (see CubeView)
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);

@@ -275,6 +275,17 @@ __global__ void __launch_bounds__(256) sample_cmem_kernel(const birp_cmem_params
     out[p] = cmem_sample<PRECISE>(P, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2]);
 }
 
+__global__ void __launch_bounds__(256) ray_directions_kernel(const birp_frame* __restrict__ frame, int W, int H,
+                                                             float* __restrict__ dirs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= W * H) return;
+    float dx, dy, dz;
+    pixel_direction(*frame, p % W, p / W, (float)W, (float)H, dx, dy, dz);
+    dirs[3 * p] = dx;
+    dirs[3 * p + 1] = dy;
+    dirs[3 * p + 2] = dz;
+}
+
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -343,6 +354,12 @@ cudaError_t launch_accumulate(const float* d_samples, long nrays, int nsamples, 
     if (nrays <= 0) return cudaSuccess;
     accumulate_kernel<<<blocks_for(nrays, 256), 256, 0, stream>>>(d_samples, nrays, nsamples, ray_width,
                                                                   (flags & BIRP_ACCUMULATE) ? 1 : 0, d_image);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream) {
+    ray_directions_kernel<<<blocks_for((long)W * H, 256), 256, 0, stream>>>(d_frame, W, H, d_dirs);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -136,6 +136,9 @@ int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, i
    subclass (e.g. the reference tests' CubeFake, tests/Camera_test.cpp:25-29). image: nrays floats. */
 int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags,
                     float* image);
+/* world-space unit ray direction of every pixel of one frame, dirs[H*W*3] (host out): the GPU ray
+   generator (src/Camera.cpp:148-168) on its own, for callers that must sample on the host */
+int birp_ray_directions(const birp_frame* frame, int W, int H, float* dirs);
 /* Space::GetSample on n points, xyz interleaved (host in, host out) */
 int birp_sample_cube(const birp_cube* cube, const float* xyz, long n, int flags, float* out);
 int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, int flags, float* out);
