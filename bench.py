@@ -234,7 +234,7 @@ def run_b200(args, wl, name):
     import torch
     import torch.distributed as dist
 
-    from birp_cpp_b200 import capi
+    from birp_cpp_b200 import capi, sharding
 
     desc, cube_n, W, H, fov_w, fov_h, nsamples, nframes, field = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -273,19 +273,19 @@ def run_b200(args, wl, name):
     if nframes > 1:
         poses = S.orbit_poses(nframes)
         frames_all = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
-        counts = [nframes // world + (1 if r < nframes % world else 0) for r in range(world)]
-        f0 = sum(counts[:rank])
-        my_frames = frames_all[f0:f0 + counts[rank]]
+        counts = sharding.block_counts(nframes, world)
+        f0, f1 = sharding.frame_block(nframes, world, rank)
+        my_frames = frames_all[f0:f1]
         rows = (0, H)
         my_rows = H
+        band = None
     else:
         poses = np.array([S.DEFAULT_POS], np.float32)
         frames_all = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
         my_frames = frames_all
-        band = [H // world + (1 if r < H % world else 0) for r in range(world)]
-        r0 = sum(band[:rank])
-        rows = (r0, r0 + band[rank])
-        my_rows = band[rank]
+        band = sharding.block_counts(H, world)
+        rows = sharding.row_band(H, world, rank)
+        my_rows = rows[1] - rows[0]
         counts = [1] * world
     nmine = len(my_frames)
 
@@ -293,12 +293,15 @@ def run_b200(args, wl, name):
     d_images = torch.zeros((nmine, H, W), dtype=torch.float32, device=dev)
     d_valid = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_list = None
-    if world > 1:
+    gathered = None
+    if world > 1 and rank == 0:
+        gathered = torch.empty((nframes, H, W) if nframes > 1 else (H, W), dtype=torch.float32, device=dev)
+
+    def gather():
         if nframes > 1:
-            gather_list = [torch.empty((c, H, W), dtype=torch.float32, device=dev) for c in counts] if rank == 0 else None
+            sharding.gather_frames(d_images, counts, 0, out=gathered)
         else:
-            gather_list = [torch.empty((1, b, W), dtype=torch.float32, device=dev) for b in band] if rank == 0 else None
+            sharding.gather_row_bands(d_images[0, rows[0]:rows[1], :], band, 0, out=gathered)
 
     def launch(valid_ptr=0):
         if field == "cube":
@@ -311,8 +314,7 @@ def run_b200(args, wl, name):
     def step():
         launch()
         if world > 1:
-            send = d_images if nframes > 1 else d_images[:, rows[0]:rows[1], :].contiguous()
-            dist.gather(send, gather_list, dst=0)
+            gather()
 
     def barrier():
         if world > 1:
@@ -344,8 +346,7 @@ def run_b200(args, wl, name):
             launch()
             b.record(stream)
             if world > 1:
-                send = d_images if nframes > 1 else d_images[:, rows[0]:rows[1], :].contiguous()
-                dist.gather(send, gather_list, dst=0)
+                gather()
             c.record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -449,7 +450,9 @@ def run_b200(args, wl, name):
             "config": {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples,
                        "maxdist_RE": MAXDIST, "interpolation": "trilinear" if field == "cube" else "analytic",
                        "frames": frames_total, "cube": cube_n, "parallelism": f"frames x{world}" if nframes > 1 else f"row bands x{world}",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed)"},
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "cube_analysis": cube.info() if cube is not None else None,
+                       "gather": "NCCL grouped send/recv to rank 0, inside the timed region" if world > 1 else "none (1 GPU)"},
             "rays_per_sec": value * W * H,
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
@@ -459,7 +462,8 @@ def run_b200(args, wl, name):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": None, "peak_source": hbm_src, "kernel": "march_kernel",
+                         "traffic": None, "peak_source": hbm_src,
+                         "kernel": "march_cube_kernel<trilinear>" if field == "cube" else "march_kernel<CmemField>",
                          "kernel_ms": float(kern_ms.mean()), "algorithmic_bytes_per_launch": int(alg_bytes),
                          "live_samples_per_launch": int(valid_mine)},
             "cpu_baseline": cpu,

@@ -1,0 +1,92 @@
+"""How the path shards over the GPUs of one box: every pixel and every frame is
+independent, the cube is replicated, and the only exchange is the gather of finished images to
+rank 0.  One process per GPU; torch.distributed is the plumbing (NCCL on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def block_counts(total: int, world: int) -> List[int]:
+    """contiguous blocks, the first `total % world` ranks take one extra unit"""
+    return [total // world + (1 if r < total % world else 0) for r in range(world)]
+
+
+def block_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    counts = block_counts(total, world)
+    start = sum(counts[:rank])
+    return start, start + counts[rank]
+
+
+def frame_block(nframes: int, world: int, rank: int) -> Tuple[int, int]:
+    """orbit sweep: frames [begin, end) rendered by `rank`"""
+    return block_range(nframes, world, rank)
+
+
+def row_band(height: int, world: int, rank: int) -> Tuple[int, int]:
+    """single large image: rows [begin, end) rendered by `rank` (birp_render_* row_begin/row_end)"""
+    return block_range(height, world, rank)
+
+
+def broadcast_cube(cube_tensor, geom_tensor, src: int = 0):
+    """replicate the grid and its origin/spacing from `src` to every rank (one-time)"""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(cube_tensor, src)
+        dist.broadcast(geom_tensor, src)
+    return cube_tensor, geom_tensor
+
+
+def _gather_uneven(local, recv_views, dst: int):
+    """rank r sends `local` to `dst`; `dst` receives straight into recv_views[r] (views of the output).
+    Grouped point-to-point ops: ncclSend/ncclRecv inside one ncclGroup under NCCL, no padding."""
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    ops = []
+    if rank == dst:
+        recv_views[dst].copy_(local)
+        for r, view in enumerate(recv_views):
+            if r != dst and view.numel():
+                ops.append(dist.P2POp(dist.irecv, view, r))
+    elif local.numel():
+        ops.append(dist.P2POp(dist.isend, local, dst))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def gather_frames(local_images, counts: Sequence[int], dst: int = 0, out=None):
+    """local_images: [counts[rank]][H][W] tensor.  Returns the [sum(counts)][H][W] tensor on `dst`
+    (None elsewhere).  Blocks may be uneven.  `out`: optional preallocated result on `dst`."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_images
+    rank = dist.get_rank()
+    shape = tuple(local_images.shape[1:])
+    views = None
+    if rank == dst:
+        if out is None:
+            out = torch.empty((sum(counts),) + shape, dtype=local_images.dtype, device=local_images.device)
+        offs = [sum(counts[:r]) for r in range(len(counts))]
+        views = [out[offs[r]:offs[r] + counts[r]] for r in range(len(counts))]
+    _gather_uneven(local_images.contiguous(), views, dst)
+    return out if rank == dst else None
+
+
+def gather_row_bands(local_band, bands: Sequence[int], dst: int = 0, out=None):
+    """local_band: [bands[rank]][W] rows of ONE image (contiguous).  Returns the [H][W] image on `dst`."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_band
+    rank = dist.get_rank()
+    W = local_band.shape[-1]
+    views = None
+    if rank == dst:
+        if out is None:
+            out = torch.empty((sum(bands), W), dtype=local_band.dtype, device=local_band.device)
+        offs = [sum(bands[:r]) for r in range(len(bands))]
+        views = [out[offs[r]:offs[r] + bands[r]] for r in range(len(bands))]
+    _gather_uneven(local_band.contiguous(), views, dst)
+    return out if rank == dst else None
