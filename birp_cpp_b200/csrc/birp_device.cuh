@@ -26,15 +26,20 @@ struct CubeView {
     // ---- derived once at upload (birp_capi.cu: finish_cube) ----
     float rx, ry, rz;     // RN(1 / spacing), for div_spacing
     float lx, ly, lz;     // smallest ingress >= 0 that the reference's bounds test rejects
+                          // (hot window: kTinyIngress <= ingress < l?; everything else is cold)
     int divmode;          // cheapest div_spacing variant proven exact for all three axes (0,1) or 2
     int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch)
 };
+
+// Ingresses below this (other than the cold-path cases) are so close to the first grid plane
+// that the residual of div_spacing would underflow; they take the generic sampler instead.
+#define BIRP_TINY_INGRESS 7.888609052210118e-31f /* 2^-100 */
 
 // ingress / spacing, correctly rounded.
 //   MODE 2: IEEE division.
 //   MODE 0/1: multiply by the correctly rounded reciprocal, then one / two residual corrections.
 // MODE 0 and 1 are only selected for a cube after an EXHAUSTIVE device-side comparison with
-// __fdiv_rn over every fp32 ingress the bounds test can let through (0 <= a < limit), for each
+// __fdiv_rn over every fp32 ingress of the hot window (2^-100 <= a < limit), for each
 // axis spacing (verify_div_kernel), so the quotient -- and with it the voxel index and the
 // interpolation weight -- is bit-identical to the reference's `x_ingress / spacing[0]`.
 template <int MODE>
@@ -197,14 +202,16 @@ __device__ __forceinline__ float lerp_pos(float a, float b, float t) {
 //    always inside the grid for an in-bounds sample); on an exact integer index the reference
 //    reads the same voxel twice (ceil == floor) -- with weight 0 that gives the same result
 //    for finite data (POSITIVE), otherwise the duplicate is selected explicitly.
-// Returns false when the sample is not inside the bounds window (dead ray or NaN coordinate:
-// the caller takes the slow path), true with the sample in `out` otherwise.
+// Returns false when the sample is not inside the hot window (dead ray, NaN coordinate, or an
+// ingress within 2^-100 of the first grid plane: the caller falls back to cube_sample()), true
+// with the sample in `out` otherwise.
 template <bool TRILINEAR, int DIVMODE, bool POSITIVE>
 __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, float y, float z, float& out) {
     const float xi = __fsub_rn(x, c.ox);
     const float yi = __fsub_rn(y, c.oy);
     const float zi = __fsub_rn(z, c.oz);
-    const bool inb = (xi >= 0.f) && (xi < c.lx) && (yi >= 0.f) && (yi < c.ly) && (zi >= 0.f) && (zi < c.lz);
+    const bool inb = (xi >= BIRP_TINY_INGRESS) && (xi < c.lx) && (yi >= BIRP_TINY_INGRESS) && (yi < c.ly) &&
+                     (zi >= BIRP_TINY_INGRESS) && (zi < c.lz);
     if (!inb) return false;
     const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
     const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);

@@ -128,13 +128,10 @@ __global__ void __launch_bounds__(kBlockThreads) march_cube_kernel(const MarchAr
         const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
         float s;
         if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE>(c, x, y, z, s)) {
-            // outside the window: the reference returns -1 (which ends the ray unless the
-            // scaled value is not negative, e.g. a zero ray width), or, for a NaN coordinate
-            // that passes its comparisons, throws from .at()
-            const float xi = __fsub_rn(x, c.ox), yi = __fsub_rn(y, c.oy), zi = __fsub_rn(z, c.oz);
-            const bool oob = (0.f > xi || xi >= c.lx) || (0.f > yi || yi >= c.ly) || (0.f > zi || zi >= c.lz);
-            if (!oob) nan_index = true;
-            s = oob ? -1.f : 0.f;
+            // outside the hot window: almost always a ray leaving the cube (the reference returns
+            // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
+            // generic transcription of DataCube::GetSample decides.
+            s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
         }
         s = scale_sample(s, ray_width);
         if (s < 0.f) break;
@@ -224,12 +221,14 @@ __global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restr
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
-// Exhaustive proof for one spacing: for EVERY fp32 ingress a with 0 <= a < limit (all bit
-// patterns below limit_bits), do the cheap quotients equal the IEEE one?  bad[0] / bad[1]
-// are set when div_spacing<0> / div_spacing<1> ever differs from __fdiv_rn.
+// Exhaustive proof for one spacing: for EVERY fp32 ingress a of the hot window,
+// 2^-100 <= a < limit (all bit patterns in [bits(2^-100), limit_bits)), do the cheap quotients
+// equal the IEEE one?  bad[0] / bad[1] are set when div_spacing<0> / div_spacing<1> ever differs
+// from __fdiv_rn.
 __global__ void __launch_bounds__(256) verify_div_kernel(float s, float r, unsigned limit_bits, int* bad) {
     bool b0 = false, b1 = false;
-    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < limit_bits;
+    const unsigned long long first = __float_as_uint(BIRP_TINY_INGRESS);
+    for (unsigned long long u = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < limit_bits;
          u += (unsigned long long)gridDim.x * blockDim.x) {
         const float a = __uint_as_float((unsigned)u);
         const unsigned want = __float_as_uint(__fdiv_rn(a, s));

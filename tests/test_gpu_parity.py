@@ -120,6 +120,33 @@ def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
             c.free()
 
 
+def test_rays_in_a_grid_plane_take_the_cold_path(gpu):
+    """hand-made frames whose rays run exactly inside the first grid plane (ingress 0) or within
+    1e-35 of it: below the 2^-100 window of the fast division, so the generic sampler must take
+    over -- and still match the oracle bit for bit"""
+    rng = np.random.default_rng(12)
+    zyx = rng.uniform(1e-7, 1e-5, size=(40, 30, 20)).astype(np.float32)
+    org = np.array([1.0, -2.0, 0.0], np.float32)
+    sp = np.array([0.3137255, 0.25, 0.5], np.float32)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        frames = np.zeros(3, capi.FRAME_DTYPE)
+        for n, px in enumerate((1.0, np.float32(1.0) + np.float32(1e-35), 1.0000001)):
+            frames[n]["pos"] = (px, -1.0, 0.125)
+            frames[n]["rinv"] = (1, 0, 0, 0, 1, 0, 0, 0, -1)  # camera -z maps to world +z
+            frames[n]["tan_half_x"] = 0.0  # every ray has direction x == 0 exactly
+            frames[n]["tan_half_y"] = 0.2
+            frames[n]["aspect"] = 1.0
+        fo = frames.view(np.float32).reshape(-1, 16)
+        for tri in (False, True):
+            got = c.render(frames, 8, 8, nsamples=64, maxdist=30, trilinear=tri)
+            want = O.orc_render_cube(zyx, org, sp, tri, fo, 8, 8, nsamples=64, maxdist=30)
+            assert_bit_exact(got, want, f"tri={tri}")
+            assert want.min() > 0
+    finally:
+        c.free()
+
+
 def test_bad_spacing_rejected(gpu):
     zyx = np.ones((4, 4, 4), np.float32)
     for sp in ((0.0, 1, 1), (1, -1.0, 1), (1, 1, np.nan), (np.inf, 1, 1)):
