@@ -39,6 +39,7 @@ if str(ROOT) not in sys.path:
 from birp_cpp_b200 import synthetic as S  # noqa: E402
 
 NSAMPLES, MAXDIST = 200, 44
+EXTRA_FLAGS = 0
 
 WORKLOADS = {
     # name: (description, cube n, W, H, fov_w, fov_h, nsamples, frames, field)
@@ -231,6 +232,8 @@ def run_reference(args, wl, name):
 
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args, wl, name):
+    global EXTRA_FLAGS
+    EXTRA_FLAGS = args.extra_flags
     import torch
     import torch.distributed as dist
 
@@ -306,7 +309,8 @@ def run_b200(args, wl, name):
     def launch(valid_ptr=0):
         if field == "cube":
             capi.render_cube_device(cube, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
-                                    maxdist=MAXDIST, trilinear=True, rows=rows, d_valid=valid_ptr, stream=sptr)
+                                    maxdist=MAXDIST, trilinear=True, rows=rows, d_valid=valid_ptr, stream=sptr,
+                                    extra_flags=EXTRA_FLAGS)
         else:
             capi.render_cmem_device(params, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
                                     maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr)
@@ -487,6 +491,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="orbit", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames of a sweep workload")
+    ap.add_argument("--extra-flags", type=int, default=0,
+                    help="BIRP_* diagnostic flags OR-ed into the device render call (A/B of kernel variants)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.frames and wl[7] > 1:

@@ -18,7 +18,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
-DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP = 8, 16, 32
+DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE = 8, 16, 32, 64
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -221,9 +221,9 @@ class Cube:
             pass
 
     def info(self) -> dict:
-        out = (C.c_int * 2)()
+        out = (C.c_int * 3)()
         _check(lib().birp_cube_info(self._h, out))
-        return {"divmode": int(out[0]), "positive": bool(out[1])}
+        return {"divmode": int(out[0]), "positive": bool(out[1]), "texture": bool(out[2])}
 
     def sample(self, xyz, trilinear: bool) -> np.ndarray:
         xyz = _f32(xyz).reshape(-1, 3)
@@ -302,8 +302,8 @@ def accumulate(samples, ray_width: float, image: np.ndarray | None = None) -> np
 # ------------------------------------------------------------------ device-buffer entry points
 def render_cube_device(cube: Cube, d_frames: int, nframes: int, W: int, H: int, d_images: int, *, nsamples=200,
                        maxdist=44, trilinear=True, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
-                       stream: int = 0) -> None:
-    flags = (TRILINEAR if trilinear else NEAREST) | (ACCUMULATE if accumulate_into else 0)
+                       stream: int = 0, extra_flags: int = 0) -> None:
+    flags = (TRILINEAR if trilinear else NEAREST) | (ACCUMULATE if accumulate_into else 0) | extra_flags
     _check(lib().birp_render_cube_device(cube.handle, _vp(d_frames), nframes, W, H, rows[0], rows[1], nsamples,
                                          maxdist, flags, _vp(d_images), _vp(d_valid), _vp(stream)))
 

@@ -21,6 +21,7 @@ struct birp_cube {
     float* d_data;
     int device;
     size_t voxels;
+    cudaArray_t tex_array = nullptr;  // layered copy for the gather path (optional)
 };
 
 // smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
@@ -310,6 +311,8 @@ int birp_cmem_init(int has_v, const int v[3], int has_b, const int b[3], float d
     return BIRP_OK;
 }
 
+static void destroy_cube(birp_cube* cube);
+
 // Upload-time analysis of a resident cube: reciprocal spacings, bounds limits, the cheapest
 // division variant that is EXACT for this cube (exhaustive device check, cached per spacing),
 // and whether all voxels are finite and positive.
@@ -350,6 +353,53 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
     v.positive = (c->h_status[0] == 0) ? 1 : 0;
     *c->h_status = 0;
+
+    // Layered-texture copy for the two-gather corner fetch (trilinear only).  Any failure here
+    // just leaves the global-load path in place.
+    v.tex = 0;
+    if (v.nx >= 2 && v.ny >= 2 && v.nz >= 2 && v.nx <= 32768 && v.ny <= 32768 && v.nz <= 2048 &&
+        !getenv("BIRP_DISABLE_TEXTURE")) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        cudaError_t te = cudaMalloc3DArray(&cube->tex_array, &desc, make_cudaExtent(v.nx, v.ny, v.nz), cudaArrayLayered);
+        if (te == cudaSuccess) {
+            cudaMemcpy3DParms cp = {};
+            cp.srcPtr = make_cudaPitchedPtr(cube->d_data, (size_t)v.nx * sizeof(float), v.nx, v.ny);
+            cp.dstArray = cube->tex_array;
+            cp.extent = make_cudaExtent(v.nx, v.ny, v.nz);
+            cp.kind = cudaMemcpyDeviceToDevice;
+            te = cudaMemcpy3DAsync(&cp, c->compute);
+        }
+        cudaTextureObject_t tex = 0;
+        if (te == cudaSuccess) {
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = cube->tex_array;
+            cudaTextureDesc td = {};
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            te = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        }
+        if (te == cudaSuccess) {
+            v.tex = tex;
+            cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute);
+            te = birp::launch_verify_gather(v, 65536, c->d_flags, c->compute);
+            if (te == cudaSuccess)
+                te = cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute);
+            if (te == cudaSuccess) te = cudaStreamSynchronize(c->compute);
+            if (te != cudaSuccess || c->h_status[0] != 0) {
+                cudaDestroyTextureObject(tex);
+                v.tex = 0;
+            }
+            *c->h_status = 0;
+        }
+        if (v.tex == 0) {
+            cudaGetLastError();  // clear a sticky-free error from the optional path
+            if (cube->tex_array) cudaFreeArray(cube->tex_array);
+            cube->tex_array = nullptr;
+        }
+    }
     v.rx = rcp[0];
     v.ry = rcp[1];
     v.rz = rcp[2];
@@ -408,8 +458,7 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.sz = spacing[2];
     rc = finish_cube(c, cube);
     if (rc) {
-        cudaFree(cube->d_data);
-        delete cube;
+        destroy_cube(cube);
         return rc;
     }
     *out = cube;
@@ -426,17 +475,23 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
     return make_cube(d_zyx, true, nx, ny, nz, origin, spacing, (cudaStream_t)stream, out);
 }
 
-int birp_cube_info(const birp_cube* cube, int info[2]) {
+int birp_cube_info(const birp_cube* cube, int info[3]) {
     if (!cube || !info) return set_error(BIRP_ERR_ARG, "null pointer");
     info[0] = cube->view.divmode;
     info[1] = cube->view.positive;
+    info[2] = cube->view.tex != 0;
     return BIRP_OK;
 }
 
-void birp_cube_free(birp_cube* cube) {
-    if (!cube) return;
+static void destroy_cube(birp_cube* cube) {
+    if (cube->view.tex) cudaDestroyTextureObject(cube->view.tex);
+    if (cube->tex_array) cudaFreeArray(cube->tex_array);
     cudaFree(cube->d_data);
     delete cube;
+}
+
+void birp_cube_free(birp_cube* cube) {
+    if (cube) destroy_cube(cube);
 }
 
 int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframes, int W, int H, int row_begin,

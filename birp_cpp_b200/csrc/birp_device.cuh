@@ -29,7 +29,24 @@ struct CubeView {
                           // (hot window: kTinyIngress <= ingress < l?; everything else is cold)
     int divmode;          // cheapest div_spacing variant proven exact for all three axes (0,1) or 2
     int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch)
+    // layered 2D texture over the same voxels (layer = z), point-sampled; 0 when the cube exceeds
+    // the layered-texture limits or the upload-time gather self-check failed
+    cudaTextureObject_t tex;
 };
+
+// The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
+// raw fp32 texels of the bilinear footprint, unfiltered (no 9-bit weights are involved -- the
+// interpolation itself stays in fp32 registers, below).  Passing the footprint CENTRE
+// (x0 + 1, y0 + 1 in unnormalised texel coordinates) keeps the footprint selection away from
+// any rounding edge of the sampler's fixed-point coordinate conversion.
+// Order: {T[y0+1][x0], T[y0+1][x0+1], T[y0][x0+1], T[y0][x0]}.
+__device__ __forceinline__ void gather4(cudaTextureObject_t tex, int layer, float u, float v, float& t01,
+                                        float& t11, float& t10, float& t00) {
+    asm("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %8}];"
+        : "=f"(t01), "=f"(t11), "=f"(t10), "=f"(t00)
+        : "l"(tex), "r"(layer), "f"(u), "f"(v), "f"(0.f));
+}
+
 
 // Ingresses below this (other than the cold-path cases) are so close to the first grid plane
 // that the residual of div_spacing would underflow; they take the generic sampler instead.
@@ -205,7 +222,7 @@ __device__ __forceinline__ float lerp_pos(float a, float b, float t) {
 // Returns false when the sample is not inside the hot window (dead ray, NaN coordinate, or an
 // ingress within 2^-100 of the first grid plane: the caller falls back to cube_sample()), true
 // with the sample in `out` otherwise.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE>
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, bool TEXGATHER>
 __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, float y, float z, float& out) {
     const float xi = __fsub_rn(x, c.ox);
     const float yi = __fsub_rn(y, c.oy);
@@ -219,22 +236,30 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
     const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
     const int row = c.nx;
     const int slab = c.nx * c.ny;
-    const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
     if (!TRILINEAR) {
-        out = __ldg(p);
+        out = __ldg(c.v + ((z0 * c.ny + y0) * row + x0));
         return true;
     }
-    const float tx = __fsub_rn(fx, (float)x0);
-    const float ty = __fsub_rn(fy, (float)y0);
+    const float gx = (float)x0, gy = (float)y0;
+    const float tx = __fsub_rn(fx, gx);
+    const float ty = __fsub_rn(fy, gy);
     const float tz = __fsub_rn(fz, (float)z0);
-    const float s000 = __ldg(p);
-    const float l001 = __ldg(p + 1);
-    const float l010 = __ldg(p + row);
-    const float l011 = __ldg(p + row + 1);
-    const float l100 = __ldg(p + slab);
-    const float l101 = __ldg(p + slab + 1);
-    const float l110 = __ldg(p + slab + row);
-    const float l111 = __ldg(p + slab + row + 1);
+    float s000, l001, l010, l011, l100, l101, l110, l111;
+    if (TEXGATHER) {
+        const float u = gx + 1.0f, v = gy + 1.0f;  // exact: small integers
+        gather4(c.tex, z0, u, v, l010, l011, l001, s000);
+        gather4(c.tex, z0 + 1, u, v, l110, l111, l101, l100);
+    } else {
+        const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
+        s000 = __ldg(p);
+        l001 = __ldg(p + 1);
+        l010 = __ldg(p + row);
+        l011 = __ldg(p + row + 1);
+        l100 = __ldg(p + slab);
+        l101 = __ldg(p + slab + 1);
+        l110 = __ldg(p + slab + row);
+        l111 = __ldg(p + slab + row + 1);
+    }
     if (POSITIVE) {
         const float low_x1 = lerp_pos(s000, l001, tx);
         const float low_x2 = lerp_pos(l010, l011, tx);

@@ -38,6 +38,7 @@ cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float
 
 // upload-time analysis of a resident cube (see CubeView)
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream);
+cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 
 unsigned long long launch_count();

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
 // (6 compares), 3 exact divisions by the spacing, 8 corner loads at fixed offsets from one
 // base address, 7 lerps, the fp64 scale, the fp32 accumulate.  Everything a sample outside
 // the window needs (dead ray, NaN coordinate) is on the cold side of one branch.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE>
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, bool TEXGATHER>
 __global__ void __launch_bounds__(kBlockThreads) march_cube_kernel(const MarchArgs a, const CubeView c) {
     int f, i, j;
     if (!lane_ray(a, f, i, j)) return;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kBlockThreads) march_cube_kernel(const MarchAr
         const float y = __fadd_rn(__fmul_rn(dy, tk), py);
         const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
         float s;
-        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE>(c, x, y, z, s)) {
+        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
             // outside the hot window: almost always a ray leaving the cube (the reference returns
             // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
             // generic transcription of DataCube::GetSample decides.
@@ -204,10 +204,52 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, bool POS>
+template <bool TRI, int DIV, bool POS, bool TEX>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
-    march_cube_kernel<TRI, DIV, POS><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    march_cube_kernel<TRI, DIV, POS, TEX><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
+}
+
+template <int DIV>
+cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, bool tex,
+                            cudaStream_t stream) {
+    if (!tri) return launch_cube_variant<false, DIV, false, false>(a, c, blocks, stream);
+    if (pos) {
+        if (tex) return launch_cube_variant<true, DIV, true, true>(a, c, blocks, stream);
+        return launch_cube_variant<true, DIV, true, false>(a, c, blocks, stream);
+    }
+    if (tex) return launch_cube_variant<true, DIV, false, true>(a, c, blocks, stream);
+    return launch_cube_variant<true, DIV, false, false>(a, c, blocks, stream);
+}
+
+// upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
+__global__ void __launch_bounds__(256) verify_gather_kernel(const CubeView c, int n, int* bad) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    unsigned h = (unsigned)t * 2654435761u + 17u;
+    h ^= h >> 15;
+    h *= 0x2c1b3c6du;
+    h ^= h >> 12;
+    // corners first (t < 8), then pseudo-random cells
+    int x0, y0, z0;
+    if (t < 8) {
+        x0 = (t & 1) ? c.nx - 2 : 0;
+        y0 = (t & 2) ? c.ny - 2 : 0;
+        z0 = (t & 4) ? c.nz - 2 : 0;
+    } else {
+        x0 = (int)(h % (unsigned)(c.nx - 1));
+        y0 = (int)((h >> 8) % (unsigned)(c.ny - 1));
+        z0 = (int)((h >> 16) % (unsigned)(c.nz - 1));
+    }
+    bool ok = true;
+    for (int dz = 0; dz < 2; ++dz) {
+        float t01, t11, t10, t00;
+        gather4(c.tex, z0 + dz, (float)x0 + 1.0f, (float)y0 + 1.0f, t01, t11, t10, t00);
+        const float* p = c.v + (((size_t)(z0 + dz) * c.ny + y0) * c.nx + x0);
+        ok &= __float_as_uint(t00) == __float_as_uint(p[0]) && __float_as_uint(t10) == __float_as_uint(p[1]) &&
+              __float_as_uint(t01) == __float_as_uint(p[c.nx]) && __float_as_uint(t11) == __float_as_uint(p[c.nx + 1]);
+    }
+    if (!ok) atomicOr(bad, 1);
 }
 
 // ---- upload-time analysis kernels -------------------------------------------------------
@@ -304,29 +346,25 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     int divmode = cube.divmode;
     if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
     if (flags & BIRP_DIV_IEEE) divmode = 2;
+    const bool tex = tri && cube.tex != 0 && !(flags & BIRP_NO_TEXTURE);
     cudaError_t e;
-#define BIRP_CUBE_CASE(T, D, P) e = launch_cube_variant<T, D, P>(a, cube, blocks, stream)
     switch (divmode) {
-        case 0:
-            if (tri) { if (pos) BIRP_CUBE_CASE(true, 0, true); else BIRP_CUBE_CASE(true, 0, false); }
-            else BIRP_CUBE_CASE(false, 0, false);
-            break;
-        case 1:
-            if (tri) { if (pos) BIRP_CUBE_CASE(true, 1, true); else BIRP_CUBE_CASE(true, 1, false); }
-            else BIRP_CUBE_CASE(false, 1, false);
-            break;
-        default:
-            if (tri) { if (pos) BIRP_CUBE_CASE(true, 2, true); else BIRP_CUBE_CASE(true, 2, false); }
-            else BIRP_CUBE_CASE(false, 2, false);
-            break;
+        case 0: e = launch_cube_div<0>(a, cube, blocks, tri, pos, tex, stream); break;
+        case 1: e = launch_cube_div<1>(a, cube, blocks, tri, pos, tex, stream); break;
+        default: e = launch_cube_div<2>(a, cube, blocks, tri, pos, tex, stream); break;
     }
-#undef BIRP_CUBE_CASE
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e;
 }
 
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream) {
     scan_positive_kernel<<<148 * 8, 256, 0, stream>>>(d_v, n, d_flag);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream) {
+    verify_gather_kernel<<<(ncells + 255) / 256, 256, 0, stream>>>(cube, ncells, d_bad);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

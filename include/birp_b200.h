@@ -56,7 +56,8 @@ enum {
     /* diagnostics: force the slower, equally exact kernel variants (see DESIGN.md "variants") */
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
-    BIRP_GENERAL_LERP = 32   /* full std::lerp semantics even for an all-positive cube */
+    BIRP_GENERAL_LERP = 32,  /* full std::lerp semantics even for an all-positive cube */
+    BIRP_NO_TEXTURE = 64     /* read the eight corners with global loads instead of two texture gathers */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */
@@ -119,8 +120,9 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
                             const float spacing[3], void* stream, birp_cube** out);
 void birp_cube_free(birp_cube* cube);
 /* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
-   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0 */
-int birp_cube_info(const birp_cube* cube, int info[2]);
+   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0,
+   info[2] = 1 when the layered-texture copy exists and passed its gather self-check */
+int birp_cube_info(const birp_cube* cube, int info[3]);
 
 /* ------------------------------------------------------------------ the hot path, host buffers
  * frames: nframes records (host).  images: nframes*H*W floats (host), row j = image y, top row

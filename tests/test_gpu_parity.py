@@ -86,7 +86,11 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
 @pytest.mark.parametrize("tri", [False, True])
 @pytest.mark.parametrize("neg", [False, True])
 @pytest.mark.parametrize("extra", [0, capi.DIV_TWO_STEP, capi.DIV_IEEE, capi.GENERAL_LERP,
-                                   capi.DIV_IEEE | capi.GENERAL_LERP, capi.DIV_TWO_STEP | capi.GENERAL_LERP])
+                                   capi.DIV_IEEE | capi.GENERAL_LERP, capi.DIV_TWO_STEP | capi.GENERAL_LERP,
+                                   capi.NO_TEXTURE, capi.NO_TEXTURE | capi.DIV_TWO_STEP, capi.NO_TEXTURE | capi.DIV_IEEE,
+                                   capi.NO_TEXTURE | capi.GENERAL_LERP,
+                                   capi.NO_TEXTURE | capi.DIV_IEEE | capi.GENERAL_LERP,
+                                   capi.NO_TEXTURE | capi.DIV_TWO_STEP | capi.GENERAL_LERP])
 def test_every_kernel_variant_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tri, neg, extra):
     """all template variants of the DataCube march kernel (division x lerp flavour) agree with the oracle"""
     zyx, org, sp = cube1_neg if neg else cube1
@@ -99,6 +103,7 @@ def test_every_kernel_variant_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_n
 def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
     a, b = dev_cube1.info(), dev_cube1_neg.info()
     assert a["positive"] and not b["positive"]
+    assert a["texture"] and b["texture"], "layered-texture copy missing or failed its gather self-check"
     assert a["divmode"] in (0, 1, 2) and a["divmode"] == b["divmode"]
     print("division variant proven exact for spacing 0.5:", a["divmode"])
     # awkward spacings: whatever variant is chosen, the renders must stay bit-exact
@@ -278,6 +283,9 @@ def test_config3_256cube_1024_image(gpu, n):
         got = c.render(fp, 1024, 1024, nsamples=200, trilinear=True)
         want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=200, nthreads=16)
         assert_bit_exact(got, want, "256^3, 1024x1024, 200 samples")
+        assert c.info()["texture"]
+        assert_bit_exact(c.render(fp, 1024, 1024, nsamples=200, trilinear=True, extra_flags=capi.NO_TEXTURE), want,
+                         "global-load variant")
         # fine step: a row band against the oracle, the whole image through band-tiling consistency
         fine = c.render(fp, 1024, 1024, nsamples=2048, trilinear=True)
         want_band = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=2048, rows=(500, 532), nthreads=16)
