@@ -233,23 +233,26 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
     const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
     const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);
     const float fz = div_spacing<DIVMODE>(zi, c.sz, c.rz);
-    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
     const int row = c.nx;
     const int slab = c.nx * c.ny;
     if (!TRILINEAR) {
+        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
         out = __ldg(c.v + ((z0 * c.ny + y0) * row + x0));
         return true;
     }
-    const float gx = (float)x0, gy = (float)y0;
+    // indices are in [0, n-1): floor == the reference's truncation; the fractions are exact
+    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
     const float tx = __fsub_rn(fx, gx);
     const float ty = __fsub_rn(fy, gy);
-    const float tz = __fsub_rn(fz, (float)z0);
+    const float tz = __fsub_rn(fz, gz);
     float s000, l001, l010, l011, l100, l101, l110, l111;
     if (TEXGATHER) {
         const float u = gx + 1.0f, v = gy + 1.0f;  // exact: small integers
+        const int z0 = (int)gz & 0xffff;           // layers are < 2048 (upload check)
         gather4(c.tex, z0, u, v, l010, l011, l001, s000);
         gather4(c.tex, z0 + 1, u, v, l110, l111, l101, l100);
     } else {
+        const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
         const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
         s000 = __ldg(p);
         l001 = __ldg(p + 1);
@@ -261,6 +264,21 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
         l111 = __ldg(p + slab + row + 1);
     }
     if (POSITIVE) {
+        // With a weight t <= 1 - 2^-20 the clamp of std::lerp provably never fires:
+        // RN(t * RN(b - a)) <= (1 - 2^-20)(1 + 2^-24)^2 |b - a| < |b - a| (or, for subnormal products,
+        // RN(t * d) <= d with d = b - a exact), so a + RN(t * RN(b - a)) stays on a's side of b and the
+        // final rounding, being monotone, cannot cross the representable value b.  Then
+        // lerp == a + t * (b - a), three instructions.  Weights within 2^-20 of 1 take the clamped form.
+        if (fmaxf(fmaxf(tx, ty), tz) <= 0.99999904632568359375f) {
+            const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
+            const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
+            const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));
+            const float high_x2 = __fadd_rn(l110, __fmul_rn(tx, __fsub_rn(l111, l110)));
+            const float low_y = __fadd_rn(low_x1, __fmul_rn(ty, __fsub_rn(low_x2, low_x1)));
+            const float high_y = __fadd_rn(high_x1, __fmul_rn(ty, __fsub_rn(high_x2, high_x1)));
+            out = __fadd_rn(low_y, __fmul_rn(tz, __fsub_rn(high_y, low_y)));
+            return true;
+        }
         const float low_x1 = lerp_pos(s000, l001, tx);
         const float low_x2 = lerp_pos(l010, l011, tx);
         const float high_x1 = lerp_pos(l100, l101, tx);
