@@ -327,9 +327,22 @@ struct M {
     }
 };
 
+// CMEM parameters plus everything that does not depend on the sample, evaluated once on the
+// host with glibc (make_cmem_dev in birp_kernels.cu) -- the reference recomputes these per sample
+// with the same glibc calls, so hoisting them is exact.
+struct CmemDev {
+    birp_cmem_params P;
+    float cos_tn, sin_tn, cos_ts, sin_ts;  // cosf/sinf of theta_n, theta_s (src/Cmem.cpp:204-209)
+    float p0r0;                            // p0 * r0_lin            (:219)
+    float p2c;                             // p2 * charlie           (:217)
+    float p3dn, p3ds;                      // p3 * dn, p3 * ds       (:217)
+    int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
+};
+
 template <bool PRECISE>
-__device__ __forceinline__ float cmem_sample(const birp_cmem_params& P, float x, float y, float z) {
+__device__ __forceinline__ float cmem_sample(const CmemDev& D, float x, float y, float z) {
     typedef M<PRECISE> m;
+    const birp_cmem_params& P = D.P;
     // ShueCoords
     const float r = vec_len3(x, y, z);
     const float theta = (x != 0.f) ? m::acos_(__fdiv_rn(x, r)) : 0.f;
@@ -342,8 +355,7 @@ __device__ __forceinline__ float cmem_sample(const birp_cmem_params& P, float x,
     // LinScaled: the cos(phi - pi/2) factors and the outer acos are fp64 in the reference
     const double c_n = cos((double)phi - CUDART_PI / 2);
     const double c_s = cos((double)phi - (3 * CUDART_PI / 2));
-    const float cos_tn = m::cos_(P.theta_n), sin_tn = m::sin_(P.theta_n);
-    const float cos_ts = m::cos_(P.theta_s), sin_ts = m::sin_(P.theta_s);
+    const float cos_tn = D.cos_tn, sin_tn = D.sin_tn, cos_ts = D.cos_ts, sin_ts = D.sin_ts;
     const float phi_n = (float)acos(
         __dadd_rn((double)__fmul_rn(cos_t, cos_tn), __dmul_rn((double)__fmul_rn(sin_t, sin_tn), c_n)));
     const float phi_s = (float)acos(
@@ -356,16 +368,15 @@ __device__ __forceinline__ float cmem_sample(const birp_cmem_params& P, float x,
         P.p1, __fadd_rn(__fadd_rn(P.beta_c[0], __fmul_rn(P.beta_c[1], cos_p)),
                         __fmul_rn(P.beta_c[3], __fmul_rn(sin_p, sin_p))));
     const float f = m::pow_(fbase, fexp);
-    const float p2c = __fmul_rn(P.p2, P.charlie);
-    const float q = __fadd_rn(
-        __fmul_rn(p2c, m::exp_(__fmul_rn(__fmul_rn(P.p3, P.dn), m::pow_(phi_n, P.a21)))),
-        __fmul_rn(p2c, m::exp_(__fmul_rn(__fmul_rn(P.p3, P.ds), m::pow_(phi_s, P.a21)))));
-    const float radius_mp = __fadd_rn(__fmul_rn(__fmul_rn(P.p0, P.r0_lin), f), q);
+    const float p2c = D.p2c;
+    const float q = __fadd_rn(__fmul_rn(p2c, m::exp_(__fmul_rn(D.p3dn, m::pow_(phi_n, P.a21)))),
+                              __fmul_rn(p2c, m::exp_(__fmul_rn(D.p3ds, m::pow_(phi_s, P.a21)))));
+    const float radius_mp = __fadd_rn(__fmul_rn(D.p0r0, f), q);
 
     // ShueModel(theta, phi, bs, ay_bs, az_bs)
     const float sbase = __fdiv_rn(2.f, __fadd_rn(1.f, cos_t));
     const float ry = __fmul_rn(P.bs, m::pow_(sbase, P.ay_bs));
-    const float rz = __fmul_rn(P.bs, m::pow_(sbase, P.az_bs));
+    const float rz = D.same_flare ? ry : __fmul_rn(P.bs, m::pow_(sbase, P.az_bs));
     const float rzc = __fmul_rn(rz, cos_p);
     const float rys = __fmul_rn(ry, sin_p);
     const float radius_bs =

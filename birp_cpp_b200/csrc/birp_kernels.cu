@@ -12,6 +12,7 @@
 // whole march, so the eight corner loads of a step hit the same handful of 128 B lines
 // (L1 broadcast) and the serial per-pixel accumulation order of the reference is kept.
 #include <atomic>
+#include <cmath>
 
 #include "birp_internal.h"
 
@@ -50,11 +51,28 @@ struct CubeField {
 
 template <bool PRECISE>
 struct CmemField {
-    birp_cmem_params P;
+    CmemDev D;
     __device__ __forceinline__ float operator()(float x, float y, float z, bool&) const {
-        return cmem_sample<PRECISE>(P, x, y, z);
+        return cmem_sample<PRECISE>(D, x, y, z);
     }
 };
+
+// Sample-independent CMEM terms, with the host libm the reference itself calls.
+CmemDev make_cmem_dev(const birp_cmem_params& P) {
+    CmemDev D;
+    D.P = P;
+    D.cos_tn = cosf(P.theta_n);
+    D.sin_tn = sinf(P.theta_n);
+    D.cos_ts = cosf(P.theta_s);
+    D.sin_ts = sinf(P.theta_s);
+    const volatile float p0r0 = P.p0 * P.r0_lin, p2c = P.p2 * P.charlie, p3dn = P.p3 * P.dn, p3ds = P.p3 * P.ds;
+    D.p0r0 = p0r0;
+    D.p2c = p2c;
+    D.p3dn = p3dn;
+    D.p3ds = p3ds;
+    D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
+    return D;
+}
 
 // Which ray this lane owns; false when the lane falls outside the image / row band.
 __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int& j) {
@@ -308,12 +326,11 @@ __global__ void __launch_bounds__(256) sample_cube_kernel(const CubeView c, cons
 }
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(256) sample_cmem_kernel(const birp_cmem_params P,
-                                                          const float* __restrict__ xyz, long n,
+__global__ void __launch_bounds__(256) sample_cmem_kernel(const CmemDev D, const float* __restrict__ xyz, long n,
                                                           float* __restrict__ out) {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    out[p] = cmem_sample<PRECISE>(P, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2]);
+    out[p] = cmem_sample<PRECISE>(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2]);
 }
 
 __global__ void __launch_bounds__(256) ray_directions_kernel(const birp_frame* __restrict__ frame, int W, int H,
@@ -379,10 +396,10 @@ cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame*
                                const RenderGeom& g, const float* d_dist, int flags, float* d_images,
                                unsigned long long* d_valid, cudaStream_t stream) {
     if (flags & BIRP_CMEM_FAST) {
-        CmemField<false> f{params};
+        CmemField<false> f{make_cmem_dev(params)};
         return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
     }
-    CmemField<true> f{params};
+    CmemField<true> f{make_cmem_dev(params)};
     return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
 }
 
@@ -415,10 +432,11 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
                                float* d_out, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
+    const CmemDev D = make_cmem_dev(params);
     if (flags & BIRP_CMEM_FAST)
-        sample_cmem_kernel<false><<<blocks_for(n, 256), 256, 0, stream>>>(params, d_xyz, n, d_out);
+        sample_cmem_kernel<false><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
     else
-        sample_cmem_kernel<true><<<blocks_for(n, 256), 256, 0, stream>>>(params, d_xyz, n, d_out);
+        sample_cmem_kernel<true><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
