@@ -325,7 +325,8 @@ def run_b200(args, wl, name):
                                     extra_flags=EXTRA_FLAGS)
         else:
             capi.render_cmem_device(params, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
-                                    maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr)
+                                    maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr,
+                                    fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
 
     def step():
         launch()
@@ -391,7 +392,7 @@ def run_b200(args, wl, name):
                         out=h_images.array)
         else:
             capi.render_cmem(params, h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, rows=rows,
-                             out=h_images.array)
+                             out=h_images.array, fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
 
     for _ in range(2):
         e2e_step()

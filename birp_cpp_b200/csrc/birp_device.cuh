@@ -320,10 +320,26 @@ template <bool PRECISE>
 struct M {
     static __device__ __forceinline__ float sin_(float x) { return PRECISE ? (float)sin((double)x) : sinf(x); }
     static __device__ __forceinline__ float cos_(float x) { return PRECISE ? (float)cos((double)x) : cosf(x); }
+    static __device__ __forceinline__ void sincos_(float x, float& s, float& c) {
+        if (PRECISE) {
+            double ds, dc;
+            sincos((double)x, &ds, &dc);
+            s = (float)ds;
+            c = (float)dc;
+        } else {
+            sincosf(x, &s, &c);
+        }
+    }
     static __device__ __forceinline__ float acos_(float x) { return PRECISE ? (float)acos((double)x) : acosf(x); }
     static __device__ __forceinline__ float exp_(float x) { return PRECISE ? (float)exp((double)x) : expf(x); }
+    // powf.  For a finite positive base, x^y = 2^(y * log2 x) in fp64: the fp64 log2 / exp2 are good to
+    // ~1 ulp64 and |y * log2 x| < 2^8 here, so the result is within ~2^-44 relative of the true power --
+    // the same "round an almost exact value once" recipe as the other calls, at half the cost of the fp64
+    // pow().  Zero, negative, infinite and NaN bases keep powf's special-case semantics through pow().
     static __device__ __forceinline__ float pow_(float x, float y) {
-        return PRECISE ? (float)pow((double)x, (double)y) : powf(x, y);
+        if (!PRECISE) return powf(x, y);
+        if (x > 0.f && x < CUDART_INF_F) return (float)exp2((double)y * log2((double)x));
+        return (float)pow((double)x, (double)y);
     }
 };
 
@@ -349,8 +365,9 @@ __device__ __forceinline__ float cmem_sample(const CmemDev& D, float x, float y,
     const float phi =
         (y != 0.f) ? m::acos_(__fdiv_rn(y, __fsqrt_rn(__fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))))) : 0.f;
 
-    const float sin_t = m::sin_(theta), cos_t = m::cos_(theta);
-    const float sin_p = m::sin_(phi), cos_p = m::cos_(phi);
+    float sin_t, cos_t, sin_p, cos_p;
+    m::sincos_(theta, sin_t, cos_t);
+    m::sincos_(phi, sin_p, cos_p);
 
     // LinScaled: the cos(phi - pi/2) factors and the outer acos are fp64 in the reference
     const double c_n = cos((double)phi - CUDART_PI / 2);
