@@ -13,12 +13,12 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libbirp_b200.so"
+LIB_PATH = Path(os.environ.get("BIRP_B200_LIB", _HERE / "libbirp_b200.so"))  # override: A/B builds only
 HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
-DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE = 8, 16, 32, 64
+DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY = 8, 16, 32, 64, 128
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),

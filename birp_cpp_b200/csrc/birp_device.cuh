@@ -99,17 +99,16 @@ __device__ __forceinline__ float scale_sample(float s, float ray_width) {
     const float p = __fmul_rn(s, ray_width);
     constexpr double K = BIRP_SCALE_C1 / BIRP_SCALE_C2 / BIRP_SCALE_C3;
     const double d = __dmul_rn((double)p, K);
-    const unsigned lo = (unsigned)__double2loint(d);
-    const unsigned hi = (unsigned)__double2hiint(d) & 0x7fffffffu;
+    const float y = __double2float_rn(d);
     // distance of the 29 dropped mantissa bits from the midpoint pattern, window +-32 ulp64
-    const unsigned frac = lo & 0x1fffffffu;
+    const unsigned frac = (unsigned)__double2loint(d) & 0x1fffffffu;
     const bool near_mid = (frac - (0x10000000u - 32u)) < 64u;
-    // fp64 exponent range in which the fp32 result is a normal number with margin:
-    // 2^-120 .. 2^120  ->  biased 903 .. 1143
-    const unsigned e = hi >> 20;
-    const bool normal = (e - 903u) < 240u;
-    const bool zero = (hi | lo) == 0u;
-    if (__builtin_expect(!near_mid && (normal || zero), 1)) return __double2float_rn(d);
+    // result comfortably inside the normal fp32 range (2^-120 <= |y| < 2^120); zero, subnormal,
+    // overflowing and NaN products fail this test and take the literal chain
+    const float ay = fabsf(y);
+    const bool normal = (ay >= 7.52316384526264e-37f) && (ay < 1.329227995784916e+36f);
+    if (__builtin_expect(normal && !near_mid, 1)) return y;
+    if (p == 0.f) return p;  // (+-0) * C1 / C2 / C3 = +-0
     return scale_sample_chain(p);
 }
 
@@ -222,7 +221,7 @@ __device__ __forceinline__ float lerp_pos(float a, float b, float t) {
 // Returns false when the sample is not inside the hot window (dead ray, NaN coordinate, or an
 // ingress within 2^-100 of the first grid plane: the caller falls back to cube_sample()), true
 // with the sample in `out` otherwise.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, bool TEXGATHER>
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
 __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, float y, float z, float& out) {
     const float xi = __fsub_rn(x, c.ox);
     const float yi = __fsub_rn(y, c.oy);
@@ -246,11 +245,23 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
     const float ty = __fsub_rn(fy, gy);
     const float tz = __fsub_rn(fz, gz);
     float s000, l001, l010, l011, l100, l101, l110, l111;
-    if (TEXGATHER) {
+    // Corner fetch.  TEXGATHER 1: both z layers through the texture unit (two tld4).  TEXGATHER 2:
+    // the lower layer through the texture unit, the upper one through the load/store unit (one tld4 +
+    // four loads): the two units return data to the register file over separate paths, and each of
+    // them alone is what saturates first once the instruction count is down (profiles/r1d, r1e, r1g).
+    if (TEXGATHER == 1) {
         const float u = gx + 1.0f, v = gy + 1.0f;  // exact: small integers
-        const int z0 = (int)gz & 0xffff;           // layers are < 2048 (upload check)
+        const int z0 = (int)gz;
         gather4(c.tex, z0, u, v, l010, l011, l001, s000);
         gather4(c.tex, z0 + 1, u, v, l110, l111, l101, l100);
+    } else if (TEXGATHER == 2) {
+        const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
+        gather4(c.tex, z0, gx + 1.0f, gy + 1.0f, l010, l011, l001, s000);
+        const float* __restrict__ p = c.v + (((z0 + 1) * c.ny + y0) * row + x0);
+        l100 = __ldg(p);
+        l101 = __ldg(p + 1);
+        l110 = __ldg(p + row);
+        l111 = __ldg(p + row + 1);
     } else {
         const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
         const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);

@@ -23,6 +23,7 @@ namespace {
 std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kSmemDist = 2048;  // ray-table entries kept in shared memory by the cube kernel
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
 struct MarchArgs {
@@ -124,40 +125,64 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
 // (6 compares), 3 exact divisions by the spacing, 8 corner loads at fixed offsets from one
 // base address, 7 lerps, the fp64 scale, the fp32 accumulate.  Everything a sample outside
 // the window needs (dead ray, NaN coordinate) is on the cold side of one branch.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, bool TEXGATHER>
-__global__ void __launch_bounds__(kBlockThreads) march_cube_kernel(const MarchArgs a, const CubeView c) {
-    int f, i, j;
-    if (!lane_ray(a, f, i, j)) return;
-    const birp_frame* __restrict__ frp = a.frames + f;
-    float dx, dy, dz;
-    pixel_direction(*frp, i, j, (float)a.W, (float)a.H, dx, dy, dz);
-    const float px = frp->pos[0], py = frp->pos[1], pz = frp->pos[2];
-
-    float* pix = a.images + ((size_t)f * a.H + j) * a.W + i;
-    float acc = a.accumulate ? *pix : 0.f;
-    bool nan_index = false;
-    const float ray_width = a.ray_width;
-    const float* __restrict__ dist = a.dist;
-    int k = 0;
-    for (; k < a.nsamples; ++k) {
-        const float tk = __ldg(dist + k);
-        const float x = __fadd_rn(__fmul_rn(dx, tk), px);
-        const float y = __fadd_rn(__fmul_rn(dy, tk), py);
-        const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
-        float s;
-        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
-            // outside the hot window: almost always a ray leaving the cube (the reference returns
-            // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
-            // generic transcription of DataCube::GetSample decides.
-            s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-        }
-        s = scale_sample(s, ray_width);
-        if (s < 0.f) break;
-        acc = __fadd_rn(acc, s);
+#ifndef BIRP_CUBE_MIN_BLOCKS
+#define BIRP_CUBE_MIN_BLOCKS 6  // resident CTAs per SM the register allocation must allow (48 of 64 warps)
+#endif
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
+__global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
+    // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
+    // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
+    __shared__ float s_dist[kSmemDist];
+    int f = 0, i = 0, j = 0;
+    bool alive = lane_ray(a, f, i, j);  // lanes outside the image still help to stage the table
+    float dx = 0.f, dy = 0.f, dz = 0.f, px = 0.f, py = 0.f, pz = 0.f, acc = 0.f;
+    float* pix = nullptr;
+    if (alive) {
+        const birp_frame* __restrict__ frp = a.frames + f;
+        pixel_direction(*frp, i, j, (float)a.W, (float)a.H, dx, dy, dz);
+        px = frp->pos[0];
+        py = frp->pos[1];
+        pz = frp->pos[2];
+        pix = a.images + ((size_t)f * a.H + j) * a.W + i;
+        acc = a.accumulate ? *pix : 0.f;
     }
-    *pix = acc;
-    if (nan_index) atomicOr(a.status, kStatusNanIndex);
-    if (a.valid) atomicAdd(a.valid, (unsigned long long)k);
+    const bool owns_pixel = alive;
+    const float ray_width = a.ray_width;
+    int nlive = 0;  // samples accumulated by this ray
+    for (int base = 0; base < a.nsamples; base += kSmemDist) {
+        const int chunk = min(kSmemDist, a.nsamples - base);
+        if (base) __syncthreads();
+        for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
+        __syncthreads();
+        if (!alive) continue;
+        int k = 0;
+        for (; k < chunk; ++k) {
+            const float tk = s_dist[k];
+            const float x = __fadd_rn(__fmul_rn(dx, tk), px);
+            const float y = __fadd_rn(__fmul_rn(dy, tk), py);
+            const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
+            float s;
+            if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
+                // outside the hot window: almost always a ray leaving the cube (the reference returns
+                // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
+                // generic transcription of DataCube::GetSample decides.
+                bool nan_index = false;
+                s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+                if (nan_index) atomicOr(a.status, kStatusNanIndex);
+            }
+            s = scale_sample(s, ray_width);
+            if (s < 0.f) {
+                alive = false;  // src/Camera.cpp:207-210: the rest of the ray is ignored
+                break;
+            }
+            acc = __fadd_rn(acc, s);
+        }
+        nlive += k;
+    }
+    if (owns_pixel) {
+        *pix = acc;
+        if (a.valid) atomicAdd(a.valid, (unsigned long long)nlive);
+    }
 }
 
 // Tile shape: split the warp's 32 rays so that the tile is as square as possible in ANGLE
@@ -222,22 +247,24 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, bool POS, bool TEX>
+template <bool TRI, int DIV, bool POS, int TEX>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
     march_cube_kernel<TRI, DIV, POS, TEX><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
 }
 
 template <int DIV>
-cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, bool tex,
+cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, int tex,
                             cudaStream_t stream) {
-    if (!tri) return launch_cube_variant<false, DIV, false, false>(a, c, blocks, stream);
+    if (!tri) return launch_cube_variant<false, DIV, false, 0>(a, c, blocks, stream);
     if (pos) {
-        if (tex) return launch_cube_variant<true, DIV, true, true>(a, c, blocks, stream);
-        return launch_cube_variant<true, DIV, true, false>(a, c, blocks, stream);
+        if (tex == 2) return launch_cube_variant<true, DIV, true, 2>(a, c, blocks, stream);
+        if (tex == 1) return launch_cube_variant<true, DIV, true, 1>(a, c, blocks, stream);
+        return launch_cube_variant<true, DIV, true, 0>(a, c, blocks, stream);
     }
-    if (tex) return launch_cube_variant<true, DIV, false, true>(a, c, blocks, stream);
-    return launch_cube_variant<true, DIV, false, false>(a, c, blocks, stream);
+    if (tex == 2) return launch_cube_variant<true, DIV, false, 2>(a, c, blocks, stream);
+    if (tex == 1) return launch_cube_variant<true, DIV, false, 1>(a, c, blocks, stream);
+    return launch_cube_variant<true, DIV, false, 0>(a, c, blocks, stream);
 }
 
 // upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
@@ -363,7 +390,8 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     int divmode = cube.divmode;
     if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
     if (flags & BIRP_DIV_IEEE) divmode = 2;
-    const bool tex = tri && cube.tex != 0 && !(flags & BIRP_NO_TEXTURE);
+    int tex = 0;  // corner fetch: 0 eight loads, 1 two texture gathers, 2 one gather + four loads
+    if (tri && cube.tex != 0 && !(flags & BIRP_NO_TEXTURE)) tex = (flags & BIRP_TEXTURE_ONLY) ? 1 : 2;
     cudaError_t e;
     switch (divmode) {
         case 0: e = launch_cube_div<0>(a, cube, blocks, tri, pos, tex, stream); break;

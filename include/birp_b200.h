@@ -57,7 +57,10 @@ enum {
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
     BIRP_GENERAL_LERP = 32,  /* full std::lerp semantics even for an all-positive cube */
-    BIRP_NO_TEXTURE = 64     /* read the eight corners with global loads instead of two texture gathers */
+    /* corner fetch of the trilinear kernel; default: lower z layer by one texture gather, upper z
+       layer by four global loads (the two units return data over separate paths) */
+    BIRP_NO_TEXTURE = 64,    /* all eight corners with global loads */
+    BIRP_TEXTURE_ONLY = 128  /* all eight corners with two texture gathers */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */

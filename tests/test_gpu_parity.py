@@ -87,6 +87,8 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
 @pytest.mark.parametrize("neg", [False, True])
 @pytest.mark.parametrize("extra", [0, capi.DIV_TWO_STEP, capi.DIV_IEEE, capi.GENERAL_LERP,
                                    capi.DIV_IEEE | capi.GENERAL_LERP, capi.DIV_TWO_STEP | capi.GENERAL_LERP,
+                                   capi.TEXTURE_ONLY, capi.TEXTURE_ONLY | capi.GENERAL_LERP | capi.DIV_TWO_STEP,
+                                   capi.TEXTURE_ONLY | capi.DIV_IEEE,
                                    capi.NO_TEXTURE, capi.NO_TEXTURE | capi.DIV_TWO_STEP, capi.NO_TEXTURE | capi.DIV_IEEE,
                                    capi.NO_TEXTURE | capi.GENERAL_LERP,
                                    capi.NO_TEXTURE | capi.DIV_IEEE | capi.GENERAL_LERP,
@@ -183,6 +185,16 @@ def test_render_ragged_shapes(dev_cube1, cube1, w, h, n, maxdist):
         got = dev_cube1.render(fp, w, h, nsamples=n, maxdist=maxdist, trilinear=tri)
         want = O.orc_render_cube(zyx, org, sp, tri, fo, w, h, nsamples=n, maxdist=maxdist)
         assert_bit_exact(got, want, f"{w}x{h} n={n}")
+
+
+def test_render_march_longer_than_the_staged_ray_table(dev_cube1, cube1):
+    """more samples than one shared-memory chunk of the ray table (2048): 5000-sample march"""
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES[:2], 9.0, 7.0, 18, 14)
+    for tri in (False, True):
+        got = dev_cube1.render(fp, 18, 14, nsamples=5000, maxdist=44, trilinear=tri)
+        want = O.orc_render_cube(zyx, org, sp, tri, fo, 18, 14, nsamples=5000, maxdist=44)
+        assert_bit_exact(got, want, f"tri={tri}")
 
 
 def test_render_golden_nondefault_march(dev_cube1, golden, cube1_matches_golden):
@@ -284,8 +296,9 @@ def test_config3_256cube_1024_image(gpu, n):
         want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=200, nthreads=16)
         assert_bit_exact(got, want, "256^3, 1024x1024, 200 samples")
         assert c.info()["texture"]
-        assert_bit_exact(c.render(fp, 1024, 1024, nsamples=200, trilinear=True, extra_flags=capi.NO_TEXTURE), want,
-                         "global-load variant")
+        for fl in (capi.NO_TEXTURE, capi.TEXTURE_ONLY):
+            assert_bit_exact(c.render(fp, 1024, 1024, nsamples=200, trilinear=True, extra_flags=fl), want,
+                             f"corner-fetch variant {fl}")
         # fine step: a row band against the oracle, the whole image through band-tiling consistency
         fine = c.render(fp, 1024, 1024, nsamples=2048, trilinear=True)
         want_band = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=2048, rows=(500, 532), nthreads=16)
