@@ -386,7 +386,11 @@ def run_b200(args, wl, name):
     h_frames.array[:] = my_frames
     h_images = capi.PinnedArray((nmine, H, W), np.float32)
 
+    my_poses = poses[f0:f1] if nframes > 1 else poses
+
     def e2e_step():
+        # poses in -> images out: per-frame host setup, H2D of the frame records, render, D2H of the images
+        capi.frames_for_poses(my_poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H, out=h_frames.array)
         if field == "cube":
             cube.render(h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=True, rows=rows,
                         out=h_images.array)
@@ -480,7 +484,7 @@ def run_b200(args, wl, name):
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
                     "h2d_bytes_per_step": int(nmine * 64), "d2h_bytes_per_step": int(nmine * my_rows * W * 4),
-                    "steps": e2e_steps, "api": "birp_render_cube/birp_render_cmem (host buffers, pinned)",
+                    "steps": e2e_steps, "api": "birp_frame_setup_batch + birp_render_cube/birp_render_cmem (host poses in, pinned host images out)",
                     "note": "bytes are per rank; every rank moves its own share"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",

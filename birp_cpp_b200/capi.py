@@ -56,6 +56,8 @@ SIGNATURES = {
     "birp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "birp_host_free": (C.c_int, [_vp]),
     "birp_frame_setup": (C.c_int, [_f32p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
+    "birp_frame_setup_batch": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp,
+                                         C.c_int]),
     "birp_ray_table": (C.c_int, [C.c_int, C.c_int, _f32p, _f32p]),
     "birp_cmem_init": (C.c_int, [C.c_int, _i32p, C.c_int, _i32p, C.c_float, C.c_float, C.c_int, C.c_int,
                                  C.c_int] + [C.c_float] * 9 + [_vp]),
@@ -119,14 +121,15 @@ def frame_setup(pos, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H
     return out
 
 
-def frames_for_poses(poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int) -> np.ndarray:
+def frames_for_poses(poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int, out=None,
+                     nthreads: int = 0) -> np.ndarray:
+    """birp_frame records of a sweep (birp_frame_setup_batch); `out`: optional preallocated FRAME_DTYPE array"""
     poses = _f32(poses).reshape(-1, 3)
-    out = np.zeros(len(poses), dtype=FRAME_DTYPE)
-    fn = lib().birp_frame_setup
-    base = out.ctypes.data
-    for n in range(len(poses)):
-        _check(fn(poses[n].ctypes.data_as(_f32p), aim_x, fov_x_deg, fov_y_deg, W, H,
-                  C.c_void_p(base + n * FRAME_DTYPE.itemsize)))
+    if out is None:
+        out = np.zeros(len(poses), dtype=FRAME_DTYPE)
+    assert out.dtype == FRAME_DTYPE and len(out) == len(poses) and out.flags.c_contiguous
+    _check(lib().birp_frame_setup_batch(_ptr(poses), len(poses), aim_x, fov_x_deg, fov_y_deg, W, H, _ptr(out),
+                                        nthreads))
     return out
 
 

@@ -295,6 +295,15 @@ int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov
     return rc;
 }
 
+int birp_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                           birp_frame* out, int nthreads) {
+    if (n < 0 || (n > 0 && (!poses || !out)) || W <= 0 || H <= 0)
+        return set_error(BIRP_ERR_ARG, "bad frame_setup_batch arguments");
+    int rc = birp::host_frame_setup_batch(poses, n, aim_x, fov_x_deg, fov_y_deg, W, H, out, nthreads);
+    if (rc == BIRP_ERR_SINGULAR) return set_error(rc, "Determinant is 0");
+    return rc;
+}
+
 int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out) {
     if (nsamples <= 0) return set_error(BIRP_ERR_ARG, "nsamples must be positive");
     birp::host_ray_table(nsamples, maxdist, dist_out, ray_width_out);

@@ -5,6 +5,8 @@
 namespace birp {
 int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out);
+int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                           birp_frame* out, int nthreads);
 void host_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);
 void host_cmem_init(int has_v, const int v_in[3], int has_b, const int b_in[3], float dipole, float p0_passed,
                     int p1_passed, int p2_passed, int p3_passed, float B_passed, float alpha, float beta,

@@ -13,8 +13,11 @@
 //                                                     reference src/Helper.cpp:70-98,150-264
 //   birp_ray_table    <- Camera::GenerateRayDistWidth reference src/Camera.cpp:69-81
 //   birp_cmem_init    <- CMEM::Init and helpers       reference src/Cmem.cpp:38-115,250-325
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/birp_b200.h"
 #include "birp_host.h"
@@ -210,6 +213,35 @@ int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov
     out->aspect = (float)W / (float)H;
     out->sun_angle = angle_sun;
     return BIRP_OK;
+}
+
+// frame_setup for a whole sweep: poses are independent, so they are split over host threads
+// (the per-pose math is ~1 us; a 10 000-pose sweep would otherwise cost a fifth of its render time)
+int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                           birp_frame* out, int nthreads) {
+    if (n <= 0) return BIRP_OK;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (nthreads <= 0) nthreads = (int)(hw ? (hw < 16 ? hw : 16) : 4);
+    if (nthreads > (n + 255) / 256) nthreads = (n + 255) / 256;
+    std::atomic<int> status{BIRP_OK};
+    auto work = [&](int begin, int end) {
+        for (int i = begin; i < end; ++i) {
+            int rc = host_frame_setup(poses + 3 * (size_t)i, aim_x, fov_x_deg, fov_y_deg, W, H, out + i);
+            if (rc != BIRP_OK) status.store(rc);
+        }
+    };
+    if (nthreads <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (n + nthreads - 1) / nthreads;
+        for (int t = 0; t < nthreads; ++t) {
+            const int b = t * per, e = b + per < n ? b + per : n;
+            if (b < e) pool.emplace_back(work, b, e);
+        }
+        for (auto& th : pool) th.join();
+    }
+    return status.load();
 }
 
 void host_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out) {

@@ -106,6 +106,10 @@ int birp_host_free(void* p);
 /* replaces Camera::Integrate's per-frame prologue + Camera::Orient (src/Camera.cpp:85-137,309-508) */
 int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out);
+/* the same for n poses (xyz interleaved) with a common aim / field of view: an orbit sweep's frames,
+   computed on up to `nthreads` host threads (0 = choose) */
+int birp_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W,
+                           int H, birp_frame* out, int nthreads);
 /* replaces Camera::GenerateRayDistWidth (src/Camera.cpp:69-81); dist_out may be NULL */
 int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);
 /* replaces CMEM::Init(bool, ...) (src/Cmem.cpp:38-115); has_v/has_b = 0 mean "empty vector" */

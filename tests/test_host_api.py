@@ -39,6 +39,16 @@ def test_frame_setup_matches_oracle():
         assert_bit_exact(got.view(np.float32).reshape(-1, 16), want, "birp_frame_setup")
 
 
+def test_frame_setup_batch_equals_single_calls():
+    poses = S.orbit_poses(1000)
+    batch = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, 27.0, 16.0, 108, 64)
+    one_thread = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, 27.0, 16.0, 108, 64, nthreads=1)
+    singles = np.concatenate([capi.frame_setup(p, S.DEFAULT_AIM_X, 27.0, 16.0, 108, 64) for p in poses[:50]])
+    assert batch.tobytes() == one_thread.tobytes()
+    assert batch[:50].tobytes() == singles.tobytes()
+    assert len(capi.frames_for_poses(np.zeros((0, 3), np.float32), 1.0, 27.0, 16.0, 108, 64)) == 0
+
+
 def test_frame_setup_golden(golden):
     got = capi.frames_for_poses(golden["poses"], float(golden["aim_x"]), 27.0, 16.0, 108, 64)
     assert_bit_exact(got["sun_angle"], golden["orient"])

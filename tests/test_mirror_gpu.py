@@ -149,6 +149,34 @@ def test_reference_cli_datacube_drop_in(gpu, tmp_path, tri):
 @needs_ref
 @pytest.mark.skipif(not (REF_DIR / "birp_main_b200").exists() or not (REF_DIR / "birp_main_ref").exists(),
                     reason="reference CLI builds absent")
+def test_reference_cli_batch_directory_drop_in(gpu, tmp_path):
+    """the reference's batch mode (src/main.cpp:242-264): `birp -i dir/` renders every cube of a
+    directory with one pose -- one upload + one render per cube through our classes"""
+    cubes = tmp_path / "cubes"
+    cubes.mkdir()
+    for n, seed in enumerate((11, 12, 13)):
+        zyx, org, sp = S.make_cube(31, 41, 37, lo=(-10.0, -40.0, -40.0), hi=(40.0, 40.0, 40.0), seed=seed)
+        S.write_dat(cubes / f"px_uni_{n:04d}.dat", zyx, org, sp)
+    for sub in ("ref", "b200"):
+        (tmp_path / sub).mkdir()
+    args = ["-i", str(cubes) + "/", "-t", "-h", "8", "-w", "12", "-s", "0.25"]
+    _run(REF_DIR / "birp_main_ref", args + ["-o", str(tmp_path / "ref") + "/"], tmp_path)
+    _run(REF_DIR / "birp_main_b200", args + ["-o", str(tmp_path / "b200") + "/"], tmp_path)
+    names = sorted(p.name for p in (tmp_path / "ref").glob("*.fits"))
+    assert names == [f"px_uni_{n:04d}.dat.fits" for n in range(3)]
+    images = []
+    for name in names:
+        h_ref, img_ref = M.read_fits(tmp_path / "ref" / name)
+        h_new, img_new = M.read_fits(tmp_path / "b200" / name)
+        assert_bit_exact(img_new, img_ref, name)
+        assert h_new == h_ref
+        images.append(img_ref)
+    assert not np.array_equal(images[0], images[1])  # different cubes really were rendered
+
+
+@needs_ref
+@pytest.mark.skipif(not (REF_DIR / "birp_main_b200").exists() or not (REF_DIR / "birp_main_ref").exists(),
+                    reason="reference CLI builds absent")
 def test_reference_cli_cmem_drop_in(gpu, tmp_path):
     """BASELINE.json configs[1]: `birp -c -h 16 -w 27` (CLI parameters p0=1, alpha=beta=0)"""
     for sub in ("ref", "b200"):
