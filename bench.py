@@ -49,6 +49,11 @@ WORKLOADS = {
                  256, 1024, 1024, 36.0, 36.0, 2048, 1, "cube"),
     "hires512": ("synthetic 512^3 cube (512 MiB), 1024x1024 image, 200 trilinear samples, row bands over ranks",
                  512, 1024, 1024, 36.0, 36.0, 200, 1, "cube"),
+    "hires512x4k": ("synthetic 512^3 cube (512 MiB), 4096x4096 image, 200 trilinear samples, row bands over ranks",
+                    512, 4096, 4096, 36.0, 36.0, 200, 1, "cube"),
+    "orbit-nearest": ("orbit sweep: 10000 SMILE-orbit poses, SXI 64x108 rays x 200 nearest-neighbour samples (the "
+                      "reference CLI's default sampling), synthetic 256^3 cube",
+                      256, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cube-nearest"),
     "cmem": ("orbit sweep: 10000 poses, SXI 64x108 rays x 200 samples of the analytic CMEM field (Init() defaults)",
              0, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cmem"),
 }
@@ -142,9 +147,9 @@ def _ref_worker(args):
     import oracle as O
     key = (field, cube_n)
     if key not in _REF_SPACES:  # one reference DataCube / CMEM object per worker process
-        if field == "cube":
+        if field.startswith("cube"):
             zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n)
-            _REF_SPACES[key] = O.RefCube(zyx, org, sp, True)
+            _REF_SPACES[key] = O.RefCube(zyx, org, sp, field == "cube")
         else:
             _REF_SPACES[key] = O.RefCmem()
     space = _REF_SPACES[key]
@@ -252,6 +257,9 @@ def run_b200(args, wl, name):
     from birp_cpp_b200 import capi, sharding
 
     desc, cube_n, W, H, fov_w, fov_h, nsamples, nframes, field = wl
+    trilinear = field != "cube-nearest"
+    if field == "cube-nearest":
+        field = "cube"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -321,7 +329,7 @@ def run_b200(args, wl, name):
     def launch(valid_ptr=0):
         if field == "cube":
             capi.render_cube_device(cube, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
-                                    maxdist=MAXDIST, trilinear=True, rows=rows, d_valid=valid_ptr, stream=sptr,
+                                    maxdist=MAXDIST, trilinear=trilinear, rows=rows, d_valid=valid_ptr, stream=sptr,
                                     extra_flags=EXTRA_FLAGS)
         else:
             capi.render_cmem_device(params, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
@@ -392,7 +400,7 @@ def run_b200(args, wl, name):
         # poses in -> images out: per-frame host setup, H2D of the frame records, render, D2H of the images
         capi.frames_for_poses(my_poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H, out=h_frames.array)
         if field == "cube":
-            cube.render(h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=True, rows=rows,
+            cube.render(h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, rows=rows,
                         out=h_images.array)
         else:
             capi.render_cmem(params, h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, rows=rows,
@@ -421,7 +429,7 @@ def run_b200(args, wl, name):
         rays_total = frames_total * W * H
         value = frames_total / (total_ms / args.steps / 1e3)
         # algorithmic bytes of this rank's launch (rank 0's share; N=1: everything)
-        bytes_per_sample = 32 if field == "cube" else 0
+        bytes_per_sample = (32 if trilinear else 4) if field == "cube" else 0
         alg_bytes = valid_mine * bytes_per_sample + nmine * my_rows * W * 4
         achieved = alg_bytes / (float(kern_ms.mean()) / 1e3) / 1e9
 
@@ -457,7 +465,7 @@ def run_b200(args, wl, name):
                 zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n)
                 fo = O.orc_frames(poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
                 pr = (rows[0], min(rows[0] + 16, rows[1]))
-                want = O.orc_render_cube(zyx, org, sp, True, fo, W, H, nsamples=nsamples, rows=pr,
+                want = O.orc_render_cube(zyx, org, sp, trilinear, fo, W, H, nsamples=nsamples, rows=pr,
                                          nthreads=len(os.sched_getaffinity(0)))[:, pr[0]:pr[1]]
                 got = e2e_images[:, pr[0]:pr[1]]
             floor = 1e-5 * np.abs(want).max()
@@ -475,7 +483,7 @@ def run_b200(args, wl, name):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples,
-                       "maxdist_RE": MAXDIST, "interpolation": "trilinear" if field == "cube" else "analytic",
+                       "maxdist_RE": MAXDIST, "interpolation": ("trilinear" if trilinear else "nearest") if field == "cube" else "analytic",
                        "frames": frames_total, "cube": cube_n, "parallelism": f"frames x{world}" if nframes > 1 else f"row bands x{world}",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "cube_analysis": cube.info() if cube is not None else None,
@@ -494,7 +502,7 @@ def run_b200(args, wl, name):
                          "note": "achieved = algorithmic bytes (32 B per live trilinear sample + 4 B per pixel) / "
                                  "kernel time; the kernel's real DRAM traffic is ~0.05 % of that (L1/L2 reuse), "
                                  "it is bound by instruction issue and the L1TEX return path (profiles/)",
-                         "kernel": "march_cube_kernel<trilinear>" if field == "cube" else "march_kernel<CmemField>",
+                         "kernel": ("march_cube_kernel<trilinear>" if trilinear else "march_cube_kernel<nearest>") if field == "cube" else "march_kernel<CmemField>",
                          "kernel_ms": float(kern_ms.mean()), "algorithmic_bytes_per_launch": int(alg_bytes),
                          "live_samples_per_launch": int(valid_mine)},
             "cpu_baseline": cpu,
