@@ -74,6 +74,7 @@ SIGNATURES = {
     "birp_render_cube_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
     "birp_render_cmem_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
     "birp_check_device_status": (C.c_int, [_vp]),
+    "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
 }
 
@@ -322,6 +323,12 @@ def render_cmem_device(params: np.ndarray, d_frames: int, nframes: int, W: int, 
 
 def check_device_status(stream: int = 0) -> None:
     _check(lib().birp_check_device_status(_vp(stream)))
+
+
+def selftest_cmem_math(n: int = 1 << 22) -> dict:
+    out = np.zeros(3, dtype=np.float64)
+    _check(lib().birp_selftest_cmem_math(n, _ptr(out)))
+    return dict(zip(("exp2", "log2", "pow"), out.tolist()))
 
 
 def launch_count() -> int:

@@ -11,6 +11,7 @@
 #include <math_constants.h>
 
 #include "../../include/birp_b200.h"
+#include "birp_cmem_math.cuh"
 
 namespace birp {
 
@@ -331,27 +332,35 @@ template <bool PRECISE>
 struct M {
     static __device__ __forceinline__ float sin_(float x) { return PRECISE ? (float)sin((double)x) : sinf(x); }
     static __device__ __forceinline__ float cos_(float x) { return PRECISE ? (float)cos((double)x) : cosf(x); }
-    static __device__ __forceinline__ void sincos_(float x, float& s, float& c) {
+    // sinf(x), cosf(x) and sinf(2x) together: 2x is exact in fp32, and sin(2x) = 2 sin(x) cos(x) holds for
+    // the real numbers, so the fp64 product rounds to the same fp32 value as a separate evaluation would
+    static __device__ __forceinline__ void sincos_(float x, float& s, float& c, float& s2) {
         if (PRECISE) {
             double ds, dc;
             sincos((double)x, &ds, &dc);
             s = (float)ds;
             c = (float)dc;
+            s2 = (float)(2.0 * ds * dc);
         } else {
             sincosf(x, &s, &c);
+            s2 = sinf(__fmul_rn(2.f, x));
         }
     }
-    static __device__ __forceinline__ float acos_(float x) { return PRECISE ? (float)acos((double)x) : acosf(x); }
+    static __device__ __forceinline__ float acos_(float x) {
+        return PRECISE ? (float)acos((double)x) : acosf(x);
+    }
     static __device__ __forceinline__ float exp_(float x) { return PRECISE ? (float)exp((double)x) : expf(x); }
-    // powf.  For a finite positive base, x^y = 2^(y * log2 x) in fp64: the fp64 log2 / exp2 are good to
-    // ~1 ulp64 and |y * log2 x| < 2^8 here, so the result is within ~2^-44 relative of the true power --
-    // the same "round an almost exact value once" recipe as the other calls, at half the cost of the fp64
-    // pow().  Zero, negative, infinite and NaN bases keep powf's special-case semantics through pow().
+    // powf.  For a finite positive base, x^y = 2^(y * log2 x) in fp64, within ~2^-44 relative of the true
+    // power for |y * log2 x| < 2^8 -- the same "round an almost exact value once" recipe as the other
+    // calls.  Zero, negative, infinite and NaN bases keep powf's special-case semantics through pow().
     static __device__ __forceinline__ float pow_(float x, float y) {
         if (!PRECISE) return powf(x, y);
-        if (x > 0.f && x < CUDART_INF_F) return (float)exp2((double)y * log2((double)x));
+        if (x > 0.f && x < CUDART_INF_F) return (float)cm::pow_pos_d((double)x, (double)y);
         return (float)pow((double)x, (double)y);
     }
+    // the two calls the reference itself makes in fp64 (src/Cmem.cpp:203-210)
+    static __device__ __forceinline__ double cos64(double x) { return cos(x); }
+    static __device__ __forceinline__ double acos64(double x) { return acos(x); }
 };
 
 // CMEM parameters plus everything that does not depend on the sample, evaluated once on the
@@ -376,22 +385,23 @@ __device__ __forceinline__ float cmem_sample(const CmemDev& D, float x, float y,
     const float phi =
         (y != 0.f) ? m::acos_(__fdiv_rn(y, __fsqrt_rn(__fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))))) : 0.f;
 
-    float sin_t, cos_t, sin_p, cos_p;
-    m::sincos_(theta, sin_t, cos_t);
-    m::sincos_(phi, sin_p, cos_p);
+    float sin_t, cos_t, sin_2t, sin_p, cos_p, unused;
+    m::sincos_(theta, sin_t, cos_t, sin_2t);
+    m::sincos_(phi, sin_p, cos_p, unused);
 
     // LinScaled: the cos(phi - pi/2) factors and the outer acos are fp64 in the reference
-    const double c_n = cos((double)phi - CUDART_PI / 2);
-    const double c_s = cos((double)phi - (3 * CUDART_PI / 2));
+    // cos(phi - 3pi/2) = -cos(phi - pi/2); the reference evaluates both in fp64 (they agree to ~1e-16)
+    const double c_n = m::cos64((double)phi - CUDART_PI / 2);
+    const double c_s = PRECISE ? -c_n : m::cos64((double)phi - (3 * CUDART_PI / 2));
     const float cos_tn = D.cos_tn, sin_tn = D.sin_tn, cos_ts = D.cos_ts, sin_ts = D.sin_ts;
-    const float phi_n = (float)acos(
+    const float phi_n = (float)m::acos64(
         __dadd_rn((double)__fmul_rn(cos_t, cos_tn), __dmul_rn((double)__fmul_rn(sin_t, sin_tn), c_n)));
-    const float phi_s = (float)acos(
+    const float phi_s = (float)m::acos64(
         __dadd_rn((double)__fmul_rn(cos_t, cos_ts), __dmul_rn((double)__fmul_rn(sin_t, sin_ts), c_s)));
 
     const float fbase = __fadd_rn(
         m::cos_(__fdiv_rn(theta, 2.f)),
-        __fmul_rn(__fmul_rn(P.a5, m::sin_(__fmul_rn(2.f, theta))), __fsub_rn(1.f, m::exp_(-theta))));
+        __fmul_rn(__fmul_rn(P.a5, sin_2t), __fsub_rn(1.f, m::exp_(-theta))));
     const float fexp = __fmul_rn(
         P.p1, __fadd_rn(__fadd_rn(P.beta_c[0], __fmul_rn(P.beta_c[1], cos_p)),
                         __fmul_rn(P.beta_c[3], __fmul_rn(sin_p, sin_p))));

@@ -34,6 +34,7 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
                                float* d_out, cudaStream_t stream);
 
+cudaError_t launch_cmem_math_selftest(long n, unsigned long long* d_err6, cudaStream_t stream);
 cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream);
 
 // upload-time analysis of a resident cube (see CubeView)

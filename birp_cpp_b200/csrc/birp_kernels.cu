@@ -371,6 +371,36 @@ __global__ void __launch_bounds__(256) ray_directions_kernel(const birp_frame* _
     dirs[3 * p + 2] = dz;
 }
 
+// max relative error of the birp::cm fp64 routines against the CUDA fp64 library on pseudo-random
+// arguments from CMEM's ranges; err[3] = {exp2, log2, pow} (double bit patterns reduced with atomicMax)
+__global__ void __launch_bounds__(256) cmem_math_selftest_kernel(long n, unsigned long long* err) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    unsigned h = (unsigned)t * 2654435761u + 99u;
+    auto next01 = [&]() {
+        h ^= h >> 16;
+        h *= 0x85ebca6bu;
+        h ^= h >> 13;
+        h *= 0xc2b2ae35u;
+        h ^= h >> 16;
+        return (double)h * (1.0 / 4294967296.0);
+    };
+    auto rel = [](double got, double want) {
+        const double d = fabs(got - want);
+        return want != 0.0 ? d / fabs(want) : d;
+    };
+    double e[3];
+    const double x = (next01() - 0.5) * 250.0;  // [-125, 125]
+    e[0] = rel(cm::exp2_d(x), exp2(x));
+    const double p = exp2((next01() - 0.5) * 250.0);
+    e[1] = fabs(cm::log2_d(p) - log2(p)) / fmax(fabs(log2(p)), 1.0);
+    const double y = (next01() - 0.5) * 8.0;
+    const double base = exp2((next01() - 0.5) * 24.0);
+    e[2] = rel(cm::pow_pos_d(base, y), pow(base, y));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) atomicMax(err + k, (unsigned long long)__double_as_longlong(e[k]));
+}
+
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -436,6 +466,12 @@ cudaError_t launch_accumulate(const float* d_samples, long nrays, int nsamples, 
     if (nrays <= 0) return cudaSuccess;
     accumulate_kernel<<<blocks_for(nrays, 256), 256, 0, stream>>>(d_samples, nrays, nsamples, ray_width,
                                                                   (flags & BIRP_ACCUMULATE) ? 1 : 0, d_image);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cmem_math_selftest(long n, unsigned long long* d_err6, cudaStream_t stream) {
+    cmem_math_selftest_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(n, d_err6);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

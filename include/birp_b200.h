@@ -168,6 +168,10 @@ int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_
    *_device launches); synchronises `stream`, returns BIRP_OK / BIRP_ERR_RANGE and clears it */
 int birp_check_device_status(void* stream);
 
+/* diagnostics: max relative error of the library's own fp64 exp2 / log2 / pow
+   (used by the CMEM kernel) against the CUDA fp64 math library on n pseudo-random arguments */
+int birp_selftest_cmem_math(long n, double max_rel_err[3]);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long birp_launch_count(void);
 

@@ -319,6 +319,15 @@ KA_TEST2 = [((8, 4, 4), 0.0), ((12, 12, 10), 4.57952495e-07), ((3, 1.5, 1.2), 0.
             ((12, -10, -10), 5.48567925e-07), ((12, 10, -10), 5.48567925e-07)]
 
 
+def test_cmem_math_accuracy(gpu):
+    """the library's own fp64 exp2 / log2 / pow stay within 2^-44 of the CUDA fp64 library, so rounding
+    them once to fp32 is a correctly rounded fp32 result almost everywhere"""
+    err = capi.selftest_cmem_math(1 << 23)
+    print({k: f"2^{np.log2(max(v, 1e-300)):.1f}" for k, v in err.items()})
+    for name, v in err.items():
+        assert v < 2.0 ** -44, (name, v)
+
+
 @pytest.mark.parametrize("fast", [False, True])
 @pytest.mark.parametrize("kw,answers", [({}, KA_DEFAULT), (O.CMEM_TEST2, KA_TEST2)])
 def test_cmem_known_answers_on_device(gpu, kw, answers, fast):
