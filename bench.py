@@ -421,6 +421,27 @@ def run_b200(args, wl, name):
     e2e_s = float(te[0])
     e2e_images = h_images.array
 
+    # ---- single-frame latency through the host-buffer call (BASELINE.json configs[0]/[1]: one SXI image)
+    latency_ms = None
+    if rank == 0 and nframes > 1:
+        one_pose = poses[:1]
+        one_img = np.zeros((1, H, W), np.float32)
+
+        def one_frame():
+            fr = capi.frames_for_poses(one_pose, S.DEFAULT_AIM_X, fov_w, fov_h, W, H, nthreads=1)
+            if field == "cube":
+                cube.render(fr, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, out=one_img)
+            else:
+                capi.render_cmem(params, fr, W, H, nsamples=nsamples, maxdist=MAXDIST, out=one_img,
+                                 fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+
+        for _ in range(5):
+            one_frame()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            one_frame()
+        latency_ms = (time.perf_counter() - t0) / 50 * 1e3
+
     # ---- rank 0: CPU baseline on a bounded sample + parity of the same frames, then the JSON line
     if rank == 0:
         import oracle as O
@@ -495,6 +516,7 @@ def run_b200(args, wl, name):
                     "steps": e2e_steps, "api": "birp_frame_setup_batch + birp_render_cube/birp_render_cmem (host poses in, pinned host images out)",
                     "note": "bytes are per rank; every rank moves its own share"},
             "gpu_launches": int(launches),
+            "single_frame_latency_ms": latency_ms,
             "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,

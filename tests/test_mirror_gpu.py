@@ -116,6 +116,18 @@ def test_todat_and_tofits(gpu, tmp_path, cube1):
     mir.free()
 
 
+# ------------------------------------------------------------------ the reference's own test files, unmodified
+@pytest.mark.skipif(not (REF_DIR / "reference_tests_b200").exists(), reason="reference test build absent")
+def test_reference_test_files_pass_against_our_classes(gpu):
+    """tests/CMEM_test.cpp + tests/Space_test.cpp of the reference, compiled unchanged against
+    birp_cpp_b200's classes (oracle/Makefile: reference_tests_b200): CMEM::GetSample runs on the GPU and
+    the 12 known answers are compared with EXPECT_EQ, i.e. bit-exactly"""
+    out = subprocess.run([str(REF_DIR / "reference_tests_b200")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "3 tests ran, 0 failed" in out.stdout
+    assert "[       OK ] CMEM.BasicSamples" in out.stdout and "[       OK ] CMEM.InitParamsSamples" in out.stdout
+
+
 # ------------------------------------------------------------------ the reference CLI, unmodified
 def _run(exe, args, cwd):
     out = subprocess.run([str(exe)] + args, cwd=cwd, capture_output=True, text=True, timeout=600)

@@ -46,6 +46,17 @@ def test_ray_table():
     assert d[0] == np.float32(44 * (0.5 / 200)) and len(d) == 200
 
 
+def test_reference_test_files_pass_on_the_compiled_reference():
+    """the reference's own tests/CMEM_test.cpp, unmodified, on the unmodified reference classes
+    (oracle/_ref/reference_tests_ref): the pins hold with this toolchain"""
+    import subprocess
+    exe = O.HERE / "_ref" / "reference_tests_ref"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/reference_tests_ref not built")
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "3 tests ran, 0 failed" in out.stdout, out.stdout
+
+
 # ---- (2) against the compiled reference
 @needs_ref
 @pytest.mark.parametrize("tri", [False, True])
