@@ -59,6 +59,15 @@ WORKLOADS = {
 }
 
 
+def workload_config(wl, name, world):
+    """the `config` object both arms print (same workload description for the driver's ratio)"""
+    desc, cube_n, W, H, fov_w, fov_h, nsamples, nframes, field = wl
+    interp = {"cube": "trilinear", "cube-nearest": "nearest", "cmem": "analytic"}[field]
+    return {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples, "maxdist_RE": MAXDIST,
+            "interpolation": interp, "frames": nframes, "cube": cube_n,
+            "parallelism": (f"frames x{world}" if nframes > 1 else f"row bands x{world}")}
+
+
 def measured_traffic(name, world, nframes_total):
     """per-launch DRAM bytes of the dominant kernel, from the committed ncu capture (profiles/traffic.json);
     only valid for the exact configuration that was profiled"""
@@ -237,7 +246,8 @@ def run_reference(args, wl, name):
         "value": frames_per_s, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / max(len(times), 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "name": name},
+        "config": dict(workload_config(WORKLOADS[name] if nframes == 1 else wl, name, args.gpus),
+                       reference_threads=workers),
         "rays_per_sec": rays,
         "cpu_baseline": {"value": frames_per_s, "unit": "frames/s", "cores": workers, "kind": "reference",
                          "sample": sample_note},
@@ -503,12 +513,10 @@ def run_b200(args, wl, name):
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples,
-                       "maxdist_RE": MAXDIST, "interpolation": ("trilinear" if trilinear else "nearest") if field == "cube" else "analytic",
-                       "frames": frames_total, "cube": cube_n, "parallelism": f"frames x{world}" if nframes > 1 else f"row bands x{world}",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
-                       "cube_analysis": cube.info() if cube is not None else None,
-                       "gather": "NCCL grouped send/recv to rank 0, inside the timed region" if world > 1 else "none (1 GPU)"},
+            "config": dict(workload_config(wl, name, world),
+                           l2="flushed between timed steps (256 MiB memset, untimed)",
+                           cube_analysis=cube.info() if cube is not None else None,
+                           gather="NCCL grouped send/recv to rank 0, inside the timed region" if world > 1 else "none (1 GPU)"),
             "rays_per_sec": value * W * H,
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
