@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include "Batch.h"
 #include "Camera.h"
 #include "Cmem.h"
 #include "DataCube.h"
@@ -189,6 +190,22 @@ int mir_render(void* p, int kind, float px_deg, float fov_h, float fov_w, const 
         return fail(e);
     }
     return 0;
+}
+
+// RenderBatchDirectory; returns the number of cubes rendered, -1 on exception
+int mir_render_batch(const char* in_dir, const char* out_dir, float px_deg, float fov_h, float fov_w,
+                     const float* pos, float aim_x, int trilinear, int threads, int* failed) {
+    try {
+        auto res = RenderBatchDirectory(in_dir, out_dir, px_deg, fov_h, fov_w, pos[0], pos[1], pos[2], aim_x,
+                                        trilinear != 0, threads);
+        int ok = 0, bad = 0;
+        for (auto& r : res) (r.error.empty() ? ok : bad)++;
+        if (failed) *failed = bad;
+        return ok;
+    } catch (const std::exception& e) {
+        fail(e);
+        return -1;
+    }
 }
 
 // Helper's public matrix routines (host only)

@@ -49,6 +49,9 @@ def lib():
         L.mir_render.restype = C.c_int
         L.mir_render.argtypes = [_vp, C.c_int, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int, C.c_int,
                                  C.c_int, _vp, _vp, C.c_char_p, C.c_char_p]
+        L.mir_render_batch.restype = C.c_int
+        L.mir_render_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int,
+                                       C.c_int, _vp]
         L.mir_helper_inverse3.restype = C.c_int
         L.mir_helper_inverse3.argtypes = [_vp, _vp]
         _lib = L
@@ -164,6 +167,16 @@ def render(space, pos, aim_x, px_deg, fov_h, fov_w, nsamples=0, maxdist=0, times
                         _p(wh), str(dat).encode() if dat else None, str(fits).encode() if fits else None):
         _raise()
     return img
+
+
+def render_batch(in_dir, out_dir, pos, aim_x, px_deg, fov_h, fov_w, trilinear=True, threads=0):
+    p = _f32(pos, (3,))
+    failed = np.zeros(1, np.int32)
+    ok = lib().mir_render_batch(str(in_dir).encode(), str(out_dir).encode(), px_deg, fov_h, fov_w, _p(p), aim_x,
+                                int(trilinear), threads, _p(failed))
+    if ok < 0:
+        _raise()
+    return ok, int(failed[0])
 
 
 def helper_inverse3(m):

@@ -186,6 +186,28 @@ def test_reference_cli_batch_directory_drop_in(gpu, tmp_path):
     assert not np.array_equal(images[0], images[1])  # different cubes really were rendered
 
 
+def test_pipelined_batch_directory_equals_cube_by_cube(gpu, tmp_path):
+    """RenderBatchDirectory (parse-ahead threads) writes the same files as rendering cube by cube"""
+    cubes = tmp_path / "cubes"
+    cubes.mkdir()
+    data = []
+    for n, seed in enumerate((21, 22, 23, 24, 25)):
+        zyx, org, sp = S.make_cube(25, 33, 29, lo=(-10.0, -40.0, -40.0), hi=(40.0, 40.0, 40.0), seed=seed)
+        S.write_dat(cubes / f"px_uni_{n:04d}.dat", zyx, org, sp)
+        data.append((zyx, org, sp))
+    (cubes / "broken.dat").write_text("not a cube\n")
+    out = tmp_path / "out"
+    out.mkdir()
+    ok, failed = M.render_batch(cubes, out, S.DEFAULT_POS, AIM, 0.25, 8.0, 12.0, trilinear=True, threads=3)
+    assert (ok, failed) == (5, 1)
+    for n, (zyx, org, sp) in enumerate(data):
+        hdr, img = M.read_fits(out / f"px_uni_{n:04d}.dat.fits")
+        cube = M.Cube(zyx, org, sp, True)
+        assert_bit_exact(img, M.render(cube, S.DEFAULT_POS, AIM, 0.25, 8.0, 12.0), f"cube {n}")
+        cube.free()
+    assert not (out / "broken.dat.fits").exists()
+
+
 @needs_ref
 @pytest.mark.skipif(not (REF_DIR / "birp_main_b200").exists() or not (REF_DIR / "birp_main_ref").exists(),
                     reason="reference CLI builds absent")
