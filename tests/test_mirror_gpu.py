@@ -200,9 +200,9 @@ def test_pipelined_batch_directory_equals_cube_by_cube(gpu, tmp_path):
     out.mkdir()
     ok, failed = M.render_batch(cubes, out, S.DEFAULT_POS, AIM, 0.25, 8.0, 12.0, trilinear=True, threads=3)
     assert (ok, failed) == (5, 1)
-    for n, (zyx, org, sp) in enumerate(data):
+    for n in range(len(data)):
         hdr, img = M.read_fits(out / f"px_uni_{n:04d}.dat.fits")
-        cube = M.Cube(zyx, org, sp, True)
+        cube = M.Cube(path=cubes / f"px_uni_{n:04d}.dat", trilinear=True)  # (spacing comes from the file's axes)
         assert_bit_exact(img, M.render(cube, S.DEFAULT_POS, AIM, 0.25, 8.0, 12.0), f"cube {n}")
         cube.free()
     assert not (out / "broken.dat.fits").exists()
