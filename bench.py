@@ -306,9 +306,9 @@ def run_b200(args, wl, name):
     if nframes > 1:
         poses = S.orbit_poses(nframes)
         frames_all = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
-        counts = sharding.block_counts(nframes, world)
-        f0, f1 = sharding.frame_block(nframes, world, rank)
-        my_frames = frames_all[f0:f1]
+        my_idx = sharding.frame_indices(nframes, world, rank, interleave=True)
+        my_frames = np.ascontiguousarray(frames_all[my_idx])
+        counts = [len(sharding.frame_indices(nframes, world, r, True)) for r in range(world)]
         rows = (0, H)
         my_rows = H
         band = None
@@ -327,29 +327,44 @@ def run_b200(args, wl, name):
     d_valid = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = None
-    if world > 1 and rank == 0:
-        gathered = torch.empty((nframes, H, W) if nframes > 1 else (H, W), dtype=torch.float32, device=dev)
+    gatherer = None
+    if world > 1 and nframes > 1:
+        # sweep: the images travel to rank 0 in two pieces, piece 0 while piece 1 is still rendering
+        gatherer = sharding.FrameGather(nframes, world, rank, (H, W), torch.float32, dev, interleave=True, nchunks=2)
+    elif world > 1 and rank == 0:
+        gathered = torch.empty((H, W), dtype=torch.float32, device=dev)
 
-    def gather():
-        if nframes > 1:
-            sharding.gather_frames(d_images, counts, 0, out=gathered)
-        else:
-            sharding.gather_row_bands(d_images[0, rows[0]:rows[1], :], band, 0, out=gathered)
-
-    def launch(valid_ptr=0):
+    def launch(valid_ptr=0, lo=0, hi=None):
+        """enqueue the render of this rank's frames [lo, hi) on the current stream"""
+        hi = nmine if hi is None else hi
+        if hi <= lo:
+            return
+        fr_ptr = d_frames.data_ptr() + lo * 64
+        img_ptr = d_images.data_ptr() + lo * H * W * 4
         if field == "cube":
-            capi.render_cube_device(cube, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
+            capi.render_cube_device(cube, fr_ptr, hi - lo, W, H, img_ptr, nsamples=nsamples,
                                     maxdist=MAXDIST, trilinear=trilinear, rows=rows, d_valid=valid_ptr, stream=sptr,
                                     extra_flags=EXTRA_FLAGS)
         else:
-            capi.render_cmem_device(params, d_frames.data_ptr(), nmine, W, H, d_images.data_ptr(), nsamples=nsamples,
+            capi.render_cmem_device(params, fr_ptr, hi - lo, W, H, img_ptr, nsamples=nsamples,
                                     maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr,
                                     fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
 
-    def step():
+    def render_and_gather():
+        """one step of the job: render this rank's share, images to rank 0 (N > 1)"""
+        if gatherer is not None:
+            for c in range(gatherer.nchunks):
+                lo, hi = gatherer.chunk_bounds(rank, c)
+                launch(lo=lo, hi=hi)
+                gatherer.post(d_images, c)
+            return gatherer.finish()
         launch()
         if world > 1:
-            gather()
+            sharding.gather_row_bands(d_images[0, rows[0]:rows[1], :], band, 0, out=gathered)
+        return gathered
+
+    def step():
+        render_and_gather()
 
     def barrier():
         if world > 1:
@@ -378,10 +393,12 @@ def run_b200(args, wl, name):
             if world > 1:
                 dist.barrier()
             a.record(stream)
-            launch()
-            b.record(stream)
-            if world > 1:
-                gather()
+            if world == 1:
+                launch()
+                b.record(stream)
+            else:
+                render_and_gather()
+                b.record(stream)  # (N > 1: render and gather overlap, there is no separate kernel interval)
             c.record(stream)
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -404,7 +421,7 @@ def run_b200(args, wl, name):
     h_frames.array[:] = my_frames
     h_images = capi.PinnedArray((nmine, H, W), np.float32)
 
-    my_poses = poses[f0:f1] if nframes > 1 else poses
+    my_poses = np.ascontiguousarray(poses[my_idx]) if nframes > 1 else poses
 
     def e2e_step():
         # poses in -> images out: per-frame host setup, H2D of the frame records, render, D2H of the images
@@ -476,7 +493,7 @@ def run_b200(args, wl, name):
             if nframes > 1:
                 nsamp = 16
                 idx = np.linspace(0, nmine - 1, nsamp).astype(int)
-                secs, ref_imgs = reference_sample(wl, poses[idx], 1, want_images=True)
+                secs, ref_imgs = reference_sample(wl, my_poses[idx], 1, want_images=True)
                 cpu = {"value": nsamp / secs, "unit": "frames/s", "cores": 1, "kind": "reference",
                        "sample": f"{nsamp} frames evenly spaced over rank 0's {nmine} frames, unmodified reference "
                                  f"Camera (oracle/_ref), 1 thread, {secs:.1f} s"}

@@ -90,3 +90,74 @@ def gather_row_bands(local_band, bands: Sequence[int], dst: int = 0, out=None):
         views = [out[offs[r]:offs[r] + bands[r]] for r in range(len(bands))]
     _gather_uneven(local_band.contiguous(), views, dst)
     return out if rank == dst else None
+
+
+def frame_indices(nframes: int, world: int, rank: int, interleave: bool = True):
+    """Frames of a sweep owned by `rank`.  Interleaved (frame f -> rank f % world) when the sweep divides
+    evenly: neighbouring poses cost about the same, so every rank gets the same mix of cheap and
+    expensive frames; contiguous blocks otherwise."""
+    import numpy as np
+    if interleave and world > 1 and nframes % world == 0:
+        return np.arange(rank, nframes, world)
+    b, e = frame_block(nframes, world, rank)
+    return np.arange(b, e)
+
+
+class FrameGather:
+    """Gather of a sweep's images to rank `dst` in pieces, so that the transfer of piece c overlaps the
+    render of piece c+1 (the NCCL point-to-point work runs on its own stream; nothing waits on it until
+    finish()).  Works for both frame layouts of frame_indices()."""
+
+    def __init__(self, nframes: int, world: int, rank: int, frame_shape, dtype, device, interleave: bool = True,
+                 nchunks: int = 2, dst: int = 0):
+        import torch
+        self.world, self.rank, self.dst, self.nframes = world, rank, dst, nframes
+        self.interleaved = bool(interleave and world > 1 and nframes % world == 0)
+        self.counts = [len(frame_indices(nframes, world, r, interleave)) for r in range(world)]
+        self.nchunks = max(1, min(nchunks, min(self.counts) if min(self.counts) > 0 else 1))
+        self.works = []
+        self.buffer = None
+        if rank == dst and world > 1:
+            # rank-major staging: frames of rank r at [offs[r], offs[r] + counts[r])
+            self.buffer = torch.empty((nframes,) + tuple(frame_shape), dtype=dtype, device=device)
+        self.offs = [sum(self.counts[:r]) for r in range(world)]
+
+    def chunk_bounds(self, r: int, c: int):
+        n = self.counts[r]
+        return n * c // self.nchunks, n * (c + 1) // self.nchunks
+
+    def post(self, local_images, c: int):
+        """piece c of this rank's images (local order) has been enqueued on the current stream"""
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        ops = []
+        lo, hi = self.chunk_bounds(self.rank, c)
+        if self.rank == self.dst:
+            o = self.offs[self.dst]
+            self.buffer[o + lo:o + hi].copy_(local_images[lo:hi], non_blocking=True)
+            for r in range(self.world):
+                if r == self.dst:
+                    continue
+                rlo, rhi = self.chunk_bounds(r, c)
+                if rhi > rlo:
+                    ops.append(dist.P2POp(dist.irecv, self.buffer[self.offs[r] + rlo:self.offs[r] + rhi], r))
+        elif hi > lo:
+            ops.append(dist.P2POp(dist.isend, local_images[lo:hi], self.dst))
+        if ops:
+            self.works.extend(dist.batch_isend_irecv(ops))
+
+    def finish(self):
+        """wait for every posted piece; on `dst` returns the images in sweep (time) order -- a strided view
+        of the rank-major staging buffer for the interleaved layout, the buffer itself for blocks"""
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.world == 1 or self.rank != self.dst:
+            return None
+        if not self.interleaved:
+            return self.buffer
+        per = self.nframes // self.world
+        shape = tuple(self.buffer.shape[1:])
+        # [per][world][...] view: element (j, r) is frame j * world + r; no copy is made
+        return self.buffer.view((self.world, per) + shape).transpose(0, 1)

@@ -64,6 +64,25 @@ def _worker(rank, world, port, out_path):
         mine = O.orc_render_cube(zyx, org, sp, True, frames[b:e], W, H, nthreads=1)
         full = sh.gather_frames(torch.from_numpy(mine), counts)
 
+        # (a2) the same sweep interleaved over the ranks (8 frames divide evenly), gathered in 3 overlapped pieces
+        poses8 = S.orbit_poses(8) * np.float32(0.4)
+        frames8 = O.orc_frames(poses8, S.DEFAULT_AIM_X, 27.0, 16.0, W, H)
+        idx = sh.frame_indices(8, world, rank, interleave=True)
+        assert list(idx) == list(range(rank, 8, world))
+        mine8 = torch.from_numpy(O.orc_render_cube(zyx, org, sp, True, frames8[idx], W, H, nthreads=1))
+        fg = sh.FrameGather(8, world, rank, (H, W), torch.float32, "cpu", interleave=True, nchunks=3)
+        for c in range(fg.nchunks):
+            fg.post(mine8, c)
+        inter = fg.finish()
+        # and with uneven blocks (7 frames): falls back to contiguous blocks, single layout
+        fg7 = sh.FrameGather(7, world, rank, (H, W), torch.float32, "cpu", interleave=True, nchunks=2)
+        assert not fg7.interleaved
+        b7, e7 = sh.frame_block(7, world, rank)
+        assert list(sh.frame_indices(7, world, rank, True)) == list(range(b7, e7))
+        for c in range(fg7.nchunks):
+            fg7.post(torch.from_numpy(mine), c)
+        blocks7 = fg7.finish()
+
         # (b) one image split into row bands
         bands = sh.block_counts(H, world)
         r0, r1 = sh.row_band(H, world, rank)
@@ -71,9 +90,11 @@ def _worker(rank, world, port, out_path):
         whole = sh.gather_row_bands(torch.from_numpy(img[0, r0:r1].copy()), bands)
         if rank == 0:
             want = O.orc_render_cube(zyx, org, sp, True, frames, W, H, nthreads=1)
-            np.savez(out_path, full=full.numpy(), want=want, whole=whole.numpy())
+            want8 = O.orc_render_cube(zyx, org, sp, True, frames8, W, H, nthreads=1)
+            np.savez(out_path, full=full.numpy(), want=want, whole=whole.numpy(),
+                     inter=inter.reshape(8, H, W).numpy(), want8=want8, blocks7=blocks7.numpy())
         else:
-            assert full is None and whole is None
+            assert full is None and whole is None and inter is None and blocks7 is None
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -87,4 +108,6 @@ def test_two_rank_gather_equals_unsharded(tmp_path):
     assert d["full"].shape == d["want"].shape == (7, 16, 27)
     assert np.array_equal(d["full"].view(np.uint32), d["want"].view(np.uint32))
     assert np.array_equal(d["whole"].view(np.uint32), d["want"][0].view(np.uint32))
+    assert np.array_equal(d["inter"].view(np.uint32), d["want8"].view(np.uint32))
+    assert np.array_equal(d["blocks7"].view(np.uint32), d["want"].view(np.uint32))
     assert d["want"].max() > 0
