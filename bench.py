@@ -328,30 +328,47 @@ def run_b200(args, wl, name):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = None
     gatherer = None
-    if world > 1 and nframes > 1:
+    peer = None
+    gather_mode = os.environ.get("BIRP_GATHER", "peer") if world > 1 else "none"
+    if gather_mode == "peer":
+        # rank 0 owns the result; the other ranks' render kernels store into it over NVLink
+        peer = sharding.PeerGather((nframes if nframes > 1 else 1) * H * W, rank, world, dev)
+    elif world > 1 and nframes > 1:
         # sweep: the images travel to rank 0 in two pieces, piece 0 while piece 1 is still rendering
-        gatherer = sharding.FrameGather(nframes, world, rank, (H, W), torch.float32, dev, interleave=True, nchunks=2)
+        gatherer = sharding.FrameGather(nframes, world, rank, (H, W), torch.float32, dev, interleave=True,
+                                        nchunks=int(os.environ.get("BIRP_GATHER_CHUNKS", "1")))
     elif world > 1 and rank == 0:
         gathered = torch.empty((H, W), dtype=torch.float32, device=dev)
 
-    def launch(valid_ptr=0, lo=0, hi=None):
-        """enqueue the render of this rank's frames [lo, hi) on the current stream"""
+    def launch(valid_ptr=0, lo=0, hi=None, to_peer=False):
+        """enqueue the render of this rank's frames [lo, hi) on the current stream; to_peer: write the
+        pixels into rank 0's gathered buffer (frame f of the sweep at slot f) instead of the local one"""
         hi = nmine if hi is None else hi
         if hi <= lo:
             return
         fr_ptr = d_frames.data_ptr() + lo * 64
-        img_ptr = d_images.data_ptr() + lo * H * W * 4
+        if to_peer:
+            img_ptr = peer.ptr
+            # sweep: my local frame j is sweep frame my_idx[j] = my_idx[0] + j * step; single image: slot 0
+            step = int(my_idx[1] - my_idx[0]) if (nframes > 1 and nmine > 1) else 1
+            off, stride = (int(my_idx[0]) + lo * step, step) if nframes > 1 else (0, 1)
+        else:
+            img_ptr, off, stride = d_images.data_ptr() + lo * H * W * 4, 0, 1
         if field == "cube":
             capi.render_cube_device(cube, fr_ptr, hi - lo, W, H, img_ptr, nsamples=nsamples,
                                     maxdist=MAXDIST, trilinear=trilinear, rows=rows, d_valid=valid_ptr, stream=sptr,
-                                    extra_flags=EXTRA_FLAGS)
+                                    extra_flags=EXTRA_FLAGS, frame_offset=off, frame_stride=stride)
         else:
             capi.render_cmem_device(params, fr_ptr, hi - lo, W, H, img_ptr, nsamples=nsamples,
                                     maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr,
-                                    fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+                                    fast=bool(EXTRA_FLAGS & capi.CMEM_FAST), frame_offset=off, frame_stride=stride)
 
     def render_and_gather():
         """one step of the job: render this rank's share, images to rank 0 (N > 1)"""
+        if peer is not None:
+            launch(to_peer=True)
+            peer.fence()
+            return None
         if gatherer is not None:
             for c in range(gatherer.nchunks):
                 lo, hi = gatherer.chunk_bounds(rank, c)
@@ -403,6 +420,21 @@ def run_b200(args, wl, name):
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = capi.launch_count() - launches0
+    # render-only pass (no gather), per rank: shows what of an N-GPU step is load imbalance between
+    # ranks and what is the exposed tail of the gather
+    kernel_only = None
+    if world > 1:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        k0.record(stream)
+        for _ in range(args.steps):
+            launch()
+        k1.record(stream)
+        torch.cuda.synchronize()
+        mine_ms = torch.tensor([k0.elapsed_time(k1) / args.steps], dtype=torch.float64, device=dev)
+        allk = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(allk, mine_ms)
+        kernel_only = [round(float(x[0]), 4) for x in allk]
     step_ms = np.array([a.elapsed_time(c) for a, b, c in ev])
     kern_ms = np.array([a.elapsed_time(b) for a, b, c in ev])
     t = torch.tensor([step_ms.sum(), kern_ms.mean(), float(valid_mine)], dtype=torch.float64, device=dev)
@@ -415,6 +447,35 @@ def run_b200(args, wl, name):
     else:
         total_ms, kern_ms_mean, valid_total = float(t[0]), float(t[1]), float(t[2])
     capi.check_device_status(sptr)
+
+    # ---- N > 1: what rank 0 holds must be what one GPU renders (a few frames / rows of other ranks' shares)
+    gather_check = None
+    if peer is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            full = peer.tensor((nframes, H, W) if nframes > 1 else (1, H, W))
+            if nframes > 1:
+                probe = np.unique(np.linspace(0, nframes - 1, 24).astype(int))
+                d_pf = torch.from_numpy(frames_all[probe].view(np.float32).reshape(-1, 16).copy()).to(dev)
+                d_pi = torch.zeros((len(probe), H, W), dtype=torch.float32, device=dev)
+                if field == "cube":
+                    capi.render_cube_device(cube, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(), nsamples=nsamples,
+                                            maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
+                else:
+                    capi.render_cmem_device(params, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(),
+                                            nsamples=nsamples, maxdist=MAXDIST, stream=sptr,
+                                            fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+                torch.cuda.synchronize()
+                same = bool(torch.equal(full[torch.from_numpy(probe).to(dev)], d_pi))
+                gather_check = {"frames_compared": int(len(probe)), "identical_to_single_gpu_render": same}
+            else:
+                d_one = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
+                capi.render_cube_device(cube, d_frames.data_ptr(), 1, W, H, d_one.data_ptr(), nsamples=nsamples,
+                                        maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
+                torch.cuda.synchronize()
+                gather_check = {"rows_compared": int(H), "identical_to_single_gpu_render": bool(torch.equal(full, d_one))}
+        dist.barrier()
 
     # ---- e2e: the host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region
     h_frames = capi.PinnedArray((nmine,), capi.FRAME_DTYPE)
@@ -542,6 +603,8 @@ def run_b200(args, wl, name):
                     "note": "bytes are per rank; every rank moves its own share"},
             "gpu_launches": int(launches),
             "single_frame_latency_ms": latency_ms,
+            "render_only_ms_per_rank": kernel_only,
+            "gather_check": gather_check,
             "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
@@ -560,6 +623,8 @@ def run_b200(args, wl, name):
         print(json.dumps(line))
     h_frames.free()
     h_images.free()
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

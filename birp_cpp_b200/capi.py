@@ -73,6 +73,13 @@ SIGNATURES = {
     "birp_sample_cmem": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
     "birp_render_cube_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
     "birp_render_cmem_device": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, _vp, _vp]),
+    "birp_render_cube_device_strided": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, C.c_longlong, C.c_longlong, _vp, _vp]),
+    "birp_render_cmem_device_strided": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp, C.c_longlong, C.c_longlong, _vp, _vp]),
+    "birp_device_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "birp_device_free": (C.c_int, [_vp]),
+    "birp_ipc_export": (C.c_int, [_vp, _vp]),
+    "birp_ipc_import": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "birp_ipc_close": (C.c_int, [_vp]),
     "birp_check_device_status": (C.c_int, [_vp]),
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
@@ -306,19 +313,59 @@ def accumulate(samples, ray_width: float, image: np.ndarray | None = None) -> np
 # ------------------------------------------------------------------ device-buffer entry points
 def render_cube_device(cube: Cube, d_frames: int, nframes: int, W: int, H: int, d_images: int, *, nsamples=200,
                        maxdist=44, trilinear=True, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
-                       stream: int = 0, extra_flags: int = 0) -> None:
+                       stream: int = 0, extra_flags: int = 0, frame_offset: int = 0, frame_stride: int = 1) -> None:
     flags = (TRILINEAR if trilinear else NEAREST) | (ACCUMULATE if accumulate_into else 0) | extra_flags
-    _check(lib().birp_render_cube_device(cube.handle, _vp(d_frames), nframes, W, H, rows[0], rows[1], nsamples,
-                                         maxdist, flags, _vp(d_images), _vp(d_valid), _vp(stream)))
+    _check(lib().birp_render_cube_device_strided(cube.handle, _vp(d_frames), nframes, W, H, rows[0], rows[1],
+                                                 nsamples, maxdist, flags, _vp(d_images), frame_offset, frame_stride,
+                                                 _vp(d_valid), _vp(stream)))
 
 
 def render_cmem_device(params: np.ndarray, d_frames: int, nframes: int, W: int, H: int, d_images: int, *,
                        nsamples=200, maxdist=44, fast=False, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
-                       stream: int = 0) -> None:
+                       stream: int = 0, frame_offset: int = 0, frame_stride: int = 1) -> None:
     params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
     flags = (CMEM_FAST if fast else 0) | (ACCUMULATE if accumulate_into else 0)
-    _check(lib().birp_render_cmem_device(_ptr(params), _vp(d_frames), nframes, W, H, rows[0], rows[1], nsamples,
-                                         maxdist, flags, _vp(d_images), _vp(d_valid), _vp(stream)))
+    _check(lib().birp_render_cmem_device_strided(_ptr(params), _vp(d_frames), nframes, W, H, rows[0], rows[1],
+                                                 nsamples, maxdist, flags, _vp(d_images), frame_offset, frame_stride,
+                                                 _vp(d_valid), _vp(stream)))
+
+
+class DeviceBuffer:
+    """cudaMalloc'ed float32 buffer that other processes of the box can map (CUDA IPC)"""
+
+    def __init__(self, nfloats: int):
+        self.nfloats = int(nfloats)
+        self._p = _vp()
+        self._imported = False
+        _check(lib().birp_device_alloc(self.nfloats * 4, C.byref(self._p)))
+
+    @classmethod
+    def from_handle(cls, handle: bytes, nfloats: int) -> "DeviceBuffer":
+        self = cls.__new__(cls)
+        self.nfloats = int(nfloats)
+        self._p = _vp()
+        self._imported = True
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _check(lib().birp_ipc_import(buf, C.byref(self._p)))
+        return self
+
+    @property
+    def ptr(self) -> int:
+        return int(self._p.value)
+
+    def export_handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _check(lib().birp_ipc_export(self._p, buf))
+        return bytes(buf)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nfloats,), "typestr": "<f4", "data": (self.ptr, False), "version": 2}
+
+    def free(self):
+        if self._p:
+            (lib().birp_ipc_close if self._imported else lib().birp_device_free)(self._p)
+            self._p = _vp()
 
 
 def check_device_status(stream: int = 0) -> None:

@@ -624,7 +624,16 @@ int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, i
 int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
                             int row_begin, int row_end, int nsamples, int maxdist, int flags, float* d_images,
                             unsigned long long* d_valid_samples, void* stream) {
+    return birp_render_cube_device_strided(cube, d_frames, nframes, W, H, row_begin, row_end, nsamples, maxdist,
+                                           flags, d_images, 0, 1, d_valid_samples, stream);
+}
+
+int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                                    int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                                    float* d_images, long long frame_offset, long long frame_stride,
+                                    unsigned long long* d_valid_samples, void* stream) {
     if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
+    if (frame_offset < 0 || frame_stride < 1) return set_error(BIRP_ERR_ARG, "bad frame offset/stride");
     int rc = check_geom(d_frames, nframes, W, H, &row_begin, &row_end, nsamples, d_images);
     if (rc) return rc;
     DeviceCtx* c;
@@ -639,6 +648,8 @@ int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, i
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
     g.tile_w_log2 = c->tile_w_log2;
+    g.out_frame_offset = frame_offset;
+    g.out_frame_stride = frame_stride;
     cudaError_t e = birp::launch_render_cube(cube->view, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, c->d_status, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -648,7 +659,16 @@ int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, i
 int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_frames, int nframes, int W,
                             int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
                             float* d_images, unsigned long long* d_valid_samples, void* stream) {
+    return birp_render_cmem_device_strided(params, d_frames, nframes, W, H, row_begin, row_end, nsamples, maxdist,
+                                           flags, d_images, 0, 1, d_valid_samples, stream);
+}
+
+int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_frame* d_frames, int nframes, int W,
+                                    int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                                    float* d_images, long long frame_offset, long long frame_stride,
+                                    unsigned long long* d_valid_samples, void* stream) {
     if (!params) return set_error(BIRP_ERR_ARG, "null params");
+    if (frame_offset < 0 || frame_stride < 1) return set_error(BIRP_ERR_ARG, "bad frame offset/stride");
     int rc = check_geom(d_frames, nframes, W, H, &row_begin, &row_end, nsamples, d_images);
     if (rc) return rc;
     DeviceCtx* c;
@@ -662,9 +682,54 @@ int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
     g.tile_w_log2 = c->tile_w_log2;
+    g.out_frame_offset = frame_offset;
+    g.out_frame_stride = frame_stride;
     cudaError_t e = birp::launch_render_cmem(*params, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+// ---- device memory that other processes of the box can map (peer stores over NVLink)
+int birp_device_alloc(size_t bytes, void** d_ptr) {
+    if (!d_ptr) return set_error(BIRP_ERR_ARG, "null out pointer");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return set_error(e == cudaErrorMemoryAllocation ? BIRP_ERR_NOMEM : BIRP_ERR_CUDA, "cudaMalloc(%zu): %s", bytes,
+                         cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+int birp_device_free(void* d_ptr) {
+    if (d_ptr) BIRP_CUDA(cudaFree(d_ptr));
+    return BIRP_OK;
+}
+
+int birp_ipc_export(const void* d_ptr, unsigned char handle[64]) {
+    if (!d_ptr || !handle) return set_error(BIRP_ERR_ARG, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    BIRP_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    std::memcpy(handle, &h, 64);
+    return BIRP_OK;
+}
+
+int birp_ipc_import(const unsigned char handle[64], void** d_ptr) {
+    if (!handle || !d_ptr) return set_error(BIRP_ERR_ARG, "null pointer");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    BIRP_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BIRP_OK;
+}
+
+int birp_ipc_close(void* d_ptr) {
+    if (d_ptr) BIRP_CUDA(cudaIpcCloseMemHandle(d_ptr));
     return BIRP_OK;
 }
 

@@ -16,6 +16,8 @@ struct RenderGeom {
     // width (log2, -1 = choose from the angles); only used to shape the per-warp pixel tile
     float pixel_angle_x = 0.f, pixel_angle_y = 0.f;
     int tile_w_log2 = -1;
+    // where frame f lands in the image buffer: slot out_frame_offset + f * out_frame_stride
+    long long out_frame_offset = 0, out_frame_stride = 1;
 };
 
 // bit in the device status word

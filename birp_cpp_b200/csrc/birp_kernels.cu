@@ -40,6 +40,9 @@ struct MarchArgs {
     long long total_tiles;
     float ray_width;
     int accumulate;
+    // frame f of this launch is written to image slot out_offset + f * out_stride of `images`
+    // (1-GPU: 0 / 1; multi-GPU sweeps scatter straight into the gathering rank's buffer)
+    long long out_offset, out_stride;
 };
 
 template <bool TRILINEAR>
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
     float dx, dy, dz;
     pixel_direction(fr, i, j, (float)a.W, (float)a.H, dx, dy, dz);
 
-    float* pix = a.images + ((size_t)f * a.H + j) * a.W + i;
+    float* pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
     float acc = a.accumulate ? *pix : 0.f;
     bool nan_index = false;
     unsigned nvalid = 0;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         px = frp->pos[0];
         py = frp->pos[1];
         pz = frp->pos[2];
-        pix = a.images + ((size_t)f * a.H + j) * a.W + i;
+        pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
         acc = a.accumulate ? *pix : 0.f;
     }
     const bool owns_pixel = alive;
@@ -228,6 +231,8 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.total_tiles = (long long)a.tiles_per_frame * g.nframes;
     a.ray_width = g.ray_width;
     a.accumulate = (flags & BIRP_ACCUMULATE) ? 1 : 0;
+    a.out_offset = g.out_frame_offset;
+    a.out_stride = g.out_frame_stride;
     const long long nb = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     *blocks = (unsigned)nb;
     return nb <= 0x7fffffffLL;

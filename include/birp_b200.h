@@ -164,6 +164,27 @@ int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, i
 int birp_render_cmem_device(const birp_cmem_params* params, const birp_frame* d_frames, int nframes,
                             int W, int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
                             float* d_images, unsigned long long* d_valid_samples, void* stream);
+/* The same with a scatter of the output frames: frame f of the call is written to image slot
+ * frame_offset + f * frame_stride of d_images (the plain entry points are offset 0, stride 1).
+ * d_images may be memory of ANOTHER GPU of the box mapped with birp_ipc_import: the kernel's final
+ * pixel stores then travel over NVLink, i.e. a sweep sharded over several processes is gathered on
+ * one rank by the render kernel itself, with no separate collective. */
+int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                                    int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                                    float* d_images, long long frame_offset, long long frame_stride,
+                                    unsigned long long* d_valid_samples, void* stream);
+int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_frame* d_frames, int nframes,
+                                    int W, int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
+                                    float* d_images, long long frame_offset, long long frame_stride,
+                                    unsigned long long* d_valid_samples, void* stream);
+/* device memory that other processes on the same box can map (CUDA IPC): the owner allocates and exports
+   a 64-byte handle, a peer imports it and gets a pointer valid in its own process */
+int birp_device_alloc(size_t bytes, void** d_ptr);
+int birp_device_free(void* d_ptr);
+int birp_ipc_export(const void* d_ptr, unsigned char handle[64]);
+int birp_ipc_import(const unsigned char handle[64], void** d_ptr);
+int birp_ipc_close(void* d_ptr);
+
 /* device error word of the calling thread's device (BIRP_ERR_RANGE conditions raised by
    *_device launches); synchronises `stream`, returns BIRP_OK / BIRP_ERR_RANGE and clears it */
 int birp_check_device_status(void* stream);
