@@ -1,16 +1,18 @@
 // sm_100a kernels of the line-of-sight integrator.
 //
-//   march_kernel<Field>   K1/K2/K3: ray generation + fixed-step march + field evaluation
-//                         (DataCube gather or CMEM) + scale + terminate + accumulate, for a
-//                         batch of frames (reference src/Camera.cpp:140-232).
+//   march_cube_kernel<..> K1/K3: ray generation + fixed-step march + DataCube sampling (nearest /
+//                         trilinear) + scale + terminate + accumulate, for a batch of frames
+//                         (reference src/Camera.cpp:140-232 x src/DataCube.cpp:203-277).
+//   march_kernel<Field>   K2: the same march around a field functor (CMEM, src/Cmem.cpp:117-288).
 //   accumulate_kernel     K4: scale + terminate + accumulate of host-sampled values
 //                         (reference src/Camera.cpp:201-223), for user-defined Space classes.
-//   sample_*_kernel       Space::GetSample on a list of points.
+//   sample_*_kernel, ray_directions_kernel: Space::GetSample on points; the ray generator alone.
+//   verify_div_kernel, verify_gather_kernel, scan_positive_kernel: upload-time proofs / analysis.
 //
-// Work decomposition of march_kernel: one warp owns an 8x4 pixel tile of one frame, one
-// lane per ray.  The 32 rays of a tile stay within a few voxels of one another along the
-// whole march, so the eight corner loads of a step hit the same handful of 128 B lines
-// (L1 broadcast) and the serial per-pixel accumulation order of the reference is kept.
+// Work decomposition of the march kernels: one warp owns a 4x8 / 8x4 pixel tile of one frame, one
+// lane per ray.  The 32 rays of a tile stay within a few voxels of one another along the whole
+// march, so the corner fetches of a step hit the same handful of cache lines / texture tiles, and
+// the serial per-pixel accumulation order of the reference is kept.
 #include <atomic>
 #include <cmath>
 
@@ -43,14 +45,6 @@ struct MarchArgs {
     // frame f of this launch is written to image slot out_offset + f * out_stride of `images`
     // (1-GPU: 0 / 1; multi-GPU sweeps scatter straight into the gathering rank's buffer)
     long long out_offset, out_stride;
-};
-
-template <bool TRILINEAR>
-struct CubeField {
-    CubeView c;
-    __device__ __forceinline__ float operator()(float x, float y, float z, bool& nan_index) const {
-        return cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-    }
 };
 
 template <bool PRECISE>
