@@ -240,8 +240,10 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
         out = __ldg(c.v + ((z0 * c.ny + y0) * row + x0));
         return true;
     }
-    // indices are in [0, n-1): floor == the reference's truncation; the fractions are exact
-    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    // indices are in [0, n-1): floor == the reference's truncation; the fractions are exact.
+    // One float->int conversion per axis (XU pipe) and the int->float back on the ALU pipe.
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float gx = (float)x0, gy = (float)y0, gz = (float)z0;
     const float tx = __fsub_rn(fx, gx);
     const float ty = __fsub_rn(fy, gy);
     const float tz = __fsub_rn(fz, gz);
@@ -252,11 +254,9 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
     // them alone is what saturates first once the instruction count is down (profiles/r1d, r1e, r1g).
     if (TEXGATHER == 1) {
         const float u = gx + 1.0f, v = gy + 1.0f;  // exact: small integers
-        const int z0 = (int)gz;
         gather4(c.tex, z0, u, v, l010, l011, l001, s000);
         gather4(c.tex, z0 + 1, u, v, l110, l111, l101, l100);
     } else if (TEXGATHER == 2) {
-        const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
         gather4(c.tex, z0, gx + 1.0f, gy + 1.0f, l010, l011, l001, s000);
         const float* __restrict__ p = c.v + (((z0 + 1) * c.ny + y0) * row + x0);
         l100 = __ldg(p);
@@ -264,7 +264,6 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
         l110 = __ldg(p + row);
         l111 = __ldg(p + row + 1);
     } else {
-        const int x0 = (int)gx, y0 = (int)gy, z0 = (int)gz;
         const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
         s000 = __ldg(p);
         l001 = __ldg(p + 1);

@@ -125,59 +125,89 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
 #ifndef BIRP_CUBE_MIN_BLOCKS
 #define BIRP_CUBE_MIN_BLOCKS 6  // resident CTAs per SM the register allocation must allow (48 of 64 warps)
 #endif
+
+struct RayState {
+    float dx, dy, dz;  // unit direction
+    float px, py, pz;  // camera position
+    float acc;         // pixel value so far
+};
+
+// March `count` steps whose distances sit in shared memory at byte address `sdist` (a 32-bit shared
+// window address, advanced by 4 per step: one LDS + one IADD, no per-step address arithmetic).
+// Returns the number of samples accumulated; `alive` is cleared when the ray ended.
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
+__device__ __forceinline__ int march_steps(const CubeView& c, RayState& r, unsigned sdist, int count, float ray_width,
+                                           int* status, bool& alive) {
+    int k = 0;
+    for (; k < count; ++k, sdist += 4) {
+        float tk;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
+        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
+        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
+        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
+        float s;
+        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
+            // outside the hot window: almost always a ray leaving the cube (the reference returns
+            // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
+            // generic transcription of DataCube::GetSample decides.
+            bool nan_index = false;
+            s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+            if (nan_index) atomicOr(status, kStatusNanIndex);
+        }
+        s = scale_sample(s, ray_width);
+        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
+            alive = false;
+            break;
+        }
+        r.acc = __fadd_rn(r.acc, s);
+    }
+    return k;
+}
+
 template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
     __shared__ float s_dist[kSmemDist];
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
+    const int first_chunk = min(kSmemDist, a.nsamples);
+    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    __syncthreads();
+
     int f = 0, i = 0, j = 0;
-    bool alive = lane_ray(a, f, i, j);  // lanes outside the image still help to stage the table
-    float dx = 0.f, dy = 0.f, dz = 0.f, px = 0.f, py = 0.f, pz = 0.f, acc = 0.f;
+    const bool owns_pixel = lane_ray(a, f, i, j);
+    if (!owns_pixel && a.nsamples <= kSmemDist) return;  // (longer marches: keep helping to stage the table)
+    RayState r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float* pix = nullptr;
-    if (alive) {
+    if (owns_pixel) {
         const birp_frame* __restrict__ frp = a.frames + f;
-        pixel_direction(*frp, i, j, (float)a.W, (float)a.H, dx, dy, dz);
-        px = frp->pos[0];
-        py = frp->pos[1];
-        pz = frp->pos[2];
+        pixel_direction(*frp, i, j, (float)a.W, (float)a.H, r.dx, r.dy, r.dz);
+        r.px = frp->pos[0];
+        r.py = frp->pos[1];
+        r.pz = frp->pos[2];
         pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
-        acc = a.accumulate ? *pix : 0.f;
+        r.acc = a.accumulate ? *pix : 0.f;
     }
-    const bool owns_pixel = alive;
-    const float ray_width = a.ray_width;
-    int nlive = 0;  // samples accumulated by this ray
-    for (int base = 0; base < a.nsamples; base += kSmemDist) {
+    bool alive = owns_pixel;
+    int nlive = 0;
+    // Keep the per-axis cube constants in ordinary registers for the whole march: left to itself ptxas
+    // re-loads ~10 of them from the constant bank in every step, and issue slots are the scarce resource
+    // here (+7 % measured).  The empty asm makes each value opaque, so it cannot be rematerialised.
+    CubeView cc = c;
+    asm volatile("" : "+f"(cc.ox), "+f"(cc.oy), "+f"(cc.oz), "+f"(cc.lx), "+f"(cc.ly), "+f"(cc.lz));
+    asm volatile("" : "+f"(cc.rx), "+f"(cc.ry), "+f"(cc.rz), "+f"(cc.sx), "+f"(cc.sy), "+f"(cc.sz));
+    asm volatile("" : "+r"(cc.nx), "+r"(cc.ny), "+l"(cc.v));
+    if (alive) nlive = march_steps<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(cc, r, s_base, first_chunk, a.ray_width, a.status, alive);
+    // marches longer than the staged table: refill it chunk by chunk (every thread of the CTA takes part)
+    for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
-        if (base) __syncthreads();
+        __syncthreads();
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
-        if (!alive) continue;
-        int k = 0;
-        for (; k < chunk; ++k) {
-            const float tk = s_dist[k];
-            const float x = __fadd_rn(__fmul_rn(dx, tk), px);
-            const float y = __fadd_rn(__fmul_rn(dy, tk), py);
-            const float z = __fadd_rn(__fmul_rn(dz, tk), pz);
-            float s;
-            if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
-                // outside the hot window: almost always a ray leaving the cube (the reference returns
-                // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
-                // generic transcription of DataCube::GetSample decides.
-                bool nan_index = false;
-                s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-                if (nan_index) atomicOr(a.status, kStatusNanIndex);
-            }
-            s = scale_sample(s, ray_width);
-            if (s < 0.f) {
-                alive = false;  // src/Camera.cpp:207-210: the rest of the ray is ignored
-                break;
-            }
-            acc = __fadd_rn(acc, s);
-        }
-        nlive += k;
+        if (alive) nlive += march_steps<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(cc, r, s_base, chunk, a.ray_width, a.status, alive);
     }
     if (owns_pixel) {
-        *pix = acc;
+        *pix = r.acc;
         if (a.valid) atomicAdd(a.valid, (unsigned long long)nlive);
     }
 }
