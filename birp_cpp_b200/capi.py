@@ -18,7 +18,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
-DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY = 8, 16, 32, 64, 128
+DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY = 8, 16, 32, 64, 128, 256, 512
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -58,6 +58,9 @@ SIGNATURES = {
     "birp_frame_setup": (C.c_int, [_f32p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
     "birp_frame_setup_batch": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp,
                                          C.c_int]),
+    "birp_frame_setup_device": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, _vp]),
+    "birp_orbit_poses": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, _vp]),
+    "birp_orbit_poses_device": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, _vp, _vp]),
     "birp_ray_table": (C.c_int, [C.c_int, C.c_int, _f32p, _f32p]),
     "birp_cmem_init": (C.c_int, [C.c_int, _i32p, C.c_int, _i32p, C.c_float, C.c_float, C.c_int, C.c_int,
                                  C.c_int] + [C.c_float] * 9 + [_vp]),
@@ -139,6 +142,24 @@ def frames_for_poses(poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W:
     _check(lib().birp_frame_setup_batch(_ptr(poses), len(poses), aim_x, fov_x_deg, fov_y_deg, W, H, _ptr(out),
                                         nthreads))
     return out
+
+
+def frame_setup_device(d_poses: int, n: int, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int,
+                       d_frames: int, stream: int = 0) -> None:
+    """poses already on the device -> frame records on the device (enqueued on `stream`)"""
+    _check(lib().birp_frame_setup_device(_vp(d_poses), n, aim_x, fov_x_deg, fov_y_deg, W, H, _vp(d_frames),
+                                         _vp(stream)))
+
+
+def orbit_poses(n: int, perigee: float = 1.78, apogee: float = 20.0, inclination_deg: float = 73.0) -> np.ndarray:
+    out = np.empty((n, 3), dtype=np.float32)
+    _check(lib().birp_orbit_poses(n, perigee, apogee, inclination_deg, _ptr(out)))
+    return out
+
+
+def orbit_poses_device(n: int, d_poses: int, perigee: float = 1.78, apogee: float = 20.0,
+                       inclination_deg: float = 73.0, stream: int = 0) -> None:
+    _check(lib().birp_orbit_poses_device(n, perigee, apogee, inclination_deg, _vp(d_poses), _vp(stream)))
 
 
 def ray_table(nsamples: int, maxdist: int):
@@ -232,9 +253,9 @@ class Cube:
             pass
 
     def info(self) -> dict:
-        out = (C.c_int * 3)()
+        out = (C.c_int * 4)()
         _check(lib().birp_cube_info(self._h, out))
-        return {"divmode": int(out[0]), "positive": bool(out[1]), "texture": bool(out[2])}
+        return {"divmode": int(out[0]), "positive": bool(out[1]), "texture": bool(out[2]), "quads": bool(out[3])}
 
     def sample(self, xyz, trilinear: bool) -> np.ndarray:
         xyz = _f32(xyz).reshape(-1, 3)

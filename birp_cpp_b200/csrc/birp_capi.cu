@@ -22,6 +22,7 @@ struct birp_cube {
     int device;
     size_t voxels;
     cudaArray_t tex_array = nullptr;  // layered copy for the gather path (optional)
+    float4* d_quad = nullptr;         // quad copy for the 16-byte corner fetch (optional)
 };
 
 // smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
@@ -45,6 +46,28 @@ static float bounds_limit(float spacing, int n) {
     float out;
     std::memcpy(&out, &hi, sizeof(out));
     return out;
+}
+
+// smallest ingress whose quotient by the spacing is >= 1 (monotone, same bisection): below it a
+// sample sits in the first cell of the axis, where the interpolation weight can exceed 1 - 2^-23
+// and the hot path's clamp-free lerp is not proven (birp_device.cuh).  Never below 2^-100, the
+// lower end of the range div_spacing is verified on.
+static float first_cell_limit(float spacing) {
+    auto reached = [&](unsigned bits) {
+        float xi;
+        std::memcpy(&xi, &bits, sizeof(xi));
+        const volatile float index = xi / spacing;
+        return index >= 1.0f;
+    };
+    unsigned lo = 0, hi = 0x7f800000u;  // +0 (never: 0 / s = 0) .. +inf (always)
+    while (hi - lo > 1) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (reached(mid)) hi = mid;
+        else lo = mid;
+    }
+    float out;
+    std::memcpy(&out, &hi, sizeof(out));
+    return out < BIRP_TINY_INGRESS ? BIRP_TINY_INGRESS : out;
 }
 
 namespace {
@@ -178,6 +201,7 @@ int read_status(DeviceCtx* c, cudaStream_t stream) {
     if (st) {
         BIRP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), stream));
         BIRP_CUDA(cudaStreamSynchronize(stream));
+        if (st & birp::kStatusSingular) return set_error(BIRP_ERR_SINGULAR, "Determinant is 0");
         if (st & birp::kStatusNanIndex)
             return set_error(BIRP_ERR_RANGE,
                              "NaN sample coordinate inside the cube bounds test "
@@ -304,6 +328,62 @@ int birp_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_d
     return rc;
 }
 
+int birp_frame_setup_device(const float* d_poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                            birp_frame* d_frames, void* stream) {
+    if (n < 0 || (n > 0 && (!d_poses || !d_frames)) || W <= 0 || H <= 0)
+        return set_error(BIRP_ERR_ARG, "bad frame_setup_device arguments");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    float tx, ty, aspect;
+    birp::host_fov_terms(fov_x_deg, fov_y_deg, W, H, &tx, &ty, &aspect);  // pose-independent: host tanf, exact
+    cudaError_t e = birp::launch_frame_setup(d_poses, n, aim_x, tx, ty, aspect, d_frames, c->d_status,
+                                             (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+static int orbit_constants(int n, double perigee, double apogee, double inclination_deg, double k[9]) {
+    if (n < 0 || !(perigee > 0.0) || !(apogee >= perigee)) return set_error(BIRP_ERR_ARG, "bad orbit arguments");
+    const double pe = perigee, ap = apogee;
+    k[0] = 0.5 * (pe + ap);
+    k[1] = (ap - pe) / (ap + pe);
+    k[2] = std::sqrt(1.0 - k[1] * k[1]);
+    const double inc = inclination_deg * (M_PI / 180.0);
+    k[3] = std::cos(inc), k[4] = 0.0, k[5] = std::sin(inc);                             // apogee direction
+    k[6] = -0.1 * std::sin(inc), k[7] = 0.99498743710662, k[8] = 0.1 * std::cos(inc);  // in-plane, orthogonal
+    return BIRP_OK;
+}
+
+int birp_orbit_poses(int n, double perigee, double apogee, double inclination_deg, float* poses) {
+    double k[9];
+    int rc = orbit_constants(n, perigee, apogee, inclination_deg, k);
+    if (rc) return rc;
+    if (n > 0 && !poses) return set_error(BIRP_ERR_ARG, "null poses");
+    for (int i = 0; i < n; ++i) {
+        const double M = 2.0 * M_PI * ((double)i + 0.5) / (double)n;
+        double E = M;
+        for (int it = 0; it < 60; ++it) E -= (E - k[1] * std::sin(E) - M) / (1.0 - k[1] * std::cos(E));
+        const double xp = k[0] * (std::cos(E) - k[1]);
+        const double yp = k[0] * k[2] * std::sin(E);
+        for (int a = 0; a < 3; ++a) poses[3 * i + a] = (float)((-xp) * k[3 + a] + yp * k[6 + a]);
+    }
+    return BIRP_OK;
+}
+
+int birp_orbit_poses_device(int n, double perigee, double apogee, double inclination_deg, float* d_poses, void* stream) {
+    double k[9];
+    int rc = orbit_constants(n, perigee, apogee, inclination_deg, k);
+    if (rc) return rc;
+    if (n > 0 && !d_poses) return set_error(BIRP_ERR_ARG, "null poses");
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    cudaError_t e = birp::launch_orbit_poses(n, k, d_poses, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
 int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out) {
     if (nsamples <= 0) return set_error(BIRP_ERR_ARG, "nsamples must be positive");
     birp::host_ray_table(nsamples, maxdist, dist_out, ray_width_out);
@@ -409,6 +489,33 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
             cube->tex_array = nullptr;
         }
     }
+    // Quad copy for the 16-byte corner fetch (trilinear only): 4x the grid.  Optional like the
+    // texture: when memory is short or the self-check fails the kernels use the other fetch forms.
+    v.quad = nullptr;
+    if (v.nx >= 2 && v.ny >= 2 && v.nz >= 2 && !getenv("BIRP_DISABLE_QUADS")) {
+        const size_t bytes = cube->voxels * sizeof(float4);
+        size_t free_b = 0, total_b = 0;
+        cudaError_t qe = cudaMemGetInfo(&free_b, &total_b);
+        if (qe == cudaSuccess && free_b / 2 >= bytes) qe = cudaMalloc(&cube->d_quad, bytes);
+        else if (qe == cudaSuccess) qe = cudaErrorMemoryAllocation;
+        if (qe == cudaSuccess) {
+            cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute);
+            qe = birp::launch_pack_quads(v, cube->d_quad, c->d_flags, c->compute);
+            if (qe == cudaSuccess)
+                qe = cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute);
+            if (qe == cudaSuccess) qe = cudaStreamSynchronize(c->compute);
+            if (qe == cudaSuccess && c->h_status[0] == 0) v.quad = cube->d_quad;
+            *c->h_status = 0;
+        }
+        if (!v.quad) {
+            cudaGetLastError();
+            if (cube->d_quad) cudaFree(cube->d_quad);
+            cube->d_quad = nullptr;
+        }
+    }
+    v.lox = first_cell_limit(sp[0]);
+    v.loy = first_cell_limit(sp[1]);
+    v.loz = first_cell_limit(sp[2]);
     v.rx = rcp[0];
     v.ry = rcp[1];
     v.rz = rcp[2];
@@ -456,6 +563,8 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.nx = nx;
     v.ny = ny;
     v.nz = nz;
+    v.slab = nx * ny;
+    v.slab16 = 16LL * nx * ny;
     v.fnx = (float)nx;
     v.fny = (float)ny;
     v.fnz = (float)nz;
@@ -484,17 +593,19 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
     return make_cube(d_zyx, true, nx, ny, nz, origin, spacing, (cudaStream_t)stream, out);
 }
 
-int birp_cube_info(const birp_cube* cube, int info[3]) {
+int birp_cube_info(const birp_cube* cube, int info[4]) {
     if (!cube || !info) return set_error(BIRP_ERR_ARG, "null pointer");
     info[0] = cube->view.divmode;
     info[1] = cube->view.positive;
     info[2] = cube->view.tex != 0;
+    info[3] = cube->view.quad != nullptr;
     return BIRP_OK;
 }
 
 static void destroy_cube(birp_cube* cube) {
     if (cube->view.tex) cudaDestroyTextureObject(cube->view.tex);
     if (cube->tex_array) cudaFreeArray(cube->tex_array);
+    if (cube->d_quad) cudaFree(cube->d_quad);
     cudaFree(cube->d_data);
     delete cube;
 }

@@ -21,18 +21,26 @@ namespace birp {
 struct CubeView {
     const float* __restrict__ v;
     int nx, ny, nz;
+    int slab;             // nx * ny
+    long long slab16;     // 16 * nx * ny: byte distance between the z layers of the quad copy
     float fnx, fny, fnz;  // (float)size.{x,y,z}: right-hand side of the reference's bounds test
     float ox, oy, oz;     // coords_{x,y,z}[0]
     float sx, sy, sz;     // spacing[0..2]
     // ---- derived once at upload (birp_capi.cu: finish_cube) ----
     float rx, ry, rz;     // RN(1 / spacing), for div_spacing
     float lx, ly, lz;     // smallest ingress >= 0 that the reference's bounds test rejects
-                          // (hot window: kTinyIngress <= ingress < l?; everything else is cold)
+    float lox, loy, loz;  // smallest ingress whose quotient by the spacing is >= 1 (and >= 2^-100)
+                          // (hot window: lo? <= ingress < l?, i.e. index in [1, n-1); everything else is cold)
     int divmode;          // cheapest div_spacing variant proven exact for all three axes (0,1) or 2
     int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch)
     // layered 2D texture over the same voxels (layer = z), point-sampled; 0 when the cube exceeds
     // the layered-texture limits or the upload-time gather self-check failed
     cudaTextureObject_t tex;
+    // "quad" copy of the grid for the trilinear corner fetch, or nullptr:
+    //   quad[(z*ny + y)*nx + x] = { v[z][y][x], v[z][y][x+1], v[z][y+1][x], v[z][y+1][x+1] }
+    // (neighbours clamped at the last row / column, which no in-bounds sample reads): the four
+    // corners of one z layer are ONE aligned 16-byte load.
+    const float4* __restrict__ quad;
 };
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
@@ -111,6 +119,26 @@ __device__ __forceinline__ float scale_sample(float s, float ray_width) {
     if (__builtin_expect(normal && !near_mid, 1)) return y;
     if (p == 0.f) return p;  // (+-0) * C1 / C2 / C3 = +-0
     return scale_sample_chain(p);
+}
+
+// The hot-loop form of scale_sample: `y` is the single-multiply result and the return value says
+// whether it is proven equal to the reference chain (same argument as above).  Negative, NaN,
+// subnormal and overflowing results return false (no fabsf: a negative sample ends the ray, which
+// the cold path handles); a zero product is its own exact result when MAYBE_ZERO (cubes that are
+// not strictly positive -- for a positive cube a zero product can only be an underflow).
+#define BIRP_SCALE_K (BIRP_SCALE_C1 / BIRP_SCALE_C2 / BIRP_SCALE_C3)
+#define BIRP_SCALE_SAFE_LO 7.52316384526264e-37f  /* 2^-120 */
+#define BIRP_SCALE_SAFE_HI 1.329227995784916e+36f /* 2^120 */
+template <bool MAYBE_ZERO>
+__device__ __forceinline__ bool scale_fast(float s, float ray_width, double K, float& y) {
+    const float p = __fmul_rn(s, ray_width);
+    const double d = __dmul_rn((double)p, K);
+    y = __double2float_rn(d);
+    const unsigned frac = (unsigned)__double2loint(d) & 0x1fffffffu;
+    const bool near_mid = (frac - (0x10000000u - 32u)) < 64u;
+    bool exact = (y >= BIRP_SCALE_SAFE_LO) && (y < BIRP_SCALE_SAFE_HI);
+    if (MAYBE_ZERO) exact = exact || (p == 0.f);  // (+-0) * C1 / C2 / C3 = +-0 = y
+    return exact && !near_mid;
 }
 
 // libstdc++ 13 std::lerp (<cmath> __lerp), the interpolation the reference calls
@@ -201,70 +229,83 @@ __device__ __forceinline__ float cube_sample(const CubeView& c, float x, float y
     return lerp_ref(low_y, high_y, tz);
 }
 
-// std::lerp restricted to what a strictly positive, finite cube can feed it: a, b > 0 and
-// t in [0,1).  The sign branch of __lerp is never taken, t == 1 and t > 1 cannot happen, and
-// no NaN can appear, so   (t>1)==(b>a) ? (b<x?x:b) : (b>x?x:b)   is min(x,b) when b > a and
-// max(x,b) otherwise.
-__device__ __forceinline__ float lerp_pos(float a, float b, float t) {
-    const float x = __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
-    return (b > a) ? fminf(x, b) : fmaxf(x, b);
-}
-
 // Hot-path form of DataCube::GetSample for the march kernel.  Same results as cube_sample();
 // what changes is the cost:
-//  * the bounds test `0 > ingress || index + 1 >= size` is monotone in the ingress, so it is
-//    a comparison against a precomputed limit (c.l?) -- no division for dead samples;
+//  * the bounds test `0 > ingress || index + 1 >= size` is monotone in the ingress, so it is a
+//    comparison against a precomputed limit (c.l?) -- no division for dead samples -- and the hot
+//    window also leaves the FIRST cell of every axis (index < 1, c.lo?) to the cold path;
 //  * the division by the spacing is div_spacing<DIVMODE>;
-//  * the eight corners are read at fixed offsets from one base address (x0+1, y0+1, z0+1 are
-//    always inside the grid for an in-bounds sample); on an exact integer index the reference
-//    reads the same voxel twice (ceil == floor) -- with weight 0 that gives the same result
-//    for finite data (POSITIVE), otherwise the duplicate is selected explicitly.
-// Returns false when the sample is not inside the hot window (dead ray, NaN coordinate, or an
-// ingress within 2^-100 of the first grid plane: the caller falls back to cube_sample()), true
-// with the sample in `out` otherwise.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
-__device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, float y, float z, float& out) {
-    const float xi = __fsub_rn(x, c.ox);
-    const float yi = __fsub_rn(y, c.oy);
-    const float zi = __fsub_rn(z, c.oz);
-    const bool inb = (xi >= BIRP_TINY_INGRESS) && (xi < c.lx) && (yi >= BIRP_TINY_INGRESS) && (yi < c.ly) &&
-                     (zi >= BIRP_TINY_INGRESS) && (zi < c.lz);
-    if (!inb) return false;
+//  * the eight corners are read at fixed offsets (x0+1, y0+1, z0+1 are always inside the grid for
+//    an in-bounds sample); on an exact integer index the reference reads the same voxel twice
+//    (ceil == floor) -- with weight 0 that gives the same result for finite data (POSITIVE),
+//    otherwise the duplicate is selected explicitly;
+//  * for a POSITIVE cube std::lerp is `a + t*(b-a)`, three instructions (proof below).
+// cube_hot_window() says whether a sample is inside the hot window (false: dead ray, NaN coordinate,
+// first cell of an axis -- the caller falls back to cube_sample()), cube_sample_hot() evaluates it.
+//
+// Corner fetch (FETCH):
+//   0  eight global loads from the linear grid
+//   1  two texture gathers (tld4) on the layered copy
+//   2  lower z layer: one tld4; upper z layer: four global loads
+//   4  two 16-byte loads from the quad copy (default: fewest instructions -- one address, two loads --
+//      and fewest cache lines per warp request; measured fastest, profiles/README.md)
+// (A form 3, tld4 for the lower layer + one quad load for the upper, was measured 9 % slower than 4.)
+// With the 4-byte forms the texture unit and the load/store unit each saturate their return path
+// into the register file first (profiles/r1d, r1e, r1g), hence the mixed form 2.
+//
+// Why the three-instruction lerp is exact here.  std::lerp(a, b, t) for finite a, b > 0 and t < 1 is
+//   x = a + t*(b - a);  return b > a ? min(x, b) : max(x, b)      (libstdc++ <cmath> __lerp)
+// and the clamp can only matter if x overshoots b.  In the hot window the index f is >= 1, so the
+// weight t = f - floor(f) is a multiple of 2^-23 below 1: t <= 1 - 2u with u = 2^-24.  Take b > a,
+// D = b - a (real), d = RN(b - a) <= D(1 + u), and p = RN(t*d):
+//   normal range:    p <= t*d*(1 + u) <= (1 - 2u)(1 + u)^2 D = (1 - 3u^2 - 2u^3) D < D;
+//   subnormal t*d:   p <= t*d + 2^-150 < D(1 - u - 2u^2) + 2^-150 <= D when D >= 2^-126, and when
+//                    D < 2^-126 the difference was exact (d = D) so p = RN(t*d) <= d = D.
+// Hence a + p <= b in real arithmetic and, rounding being monotone and b representable,
+// RN(a + p) <= b: the clamp never fires.  b < a is the mirror image, b == a gives x = a = b.
+// (1) the window test on the ingresses xi = x - coords_x[0], ...
+__device__ __forceinline__ bool cube_hot_window(const CubeView& c, float xi, float yi, float zi) {
+    return (xi >= c.lox) && (xi < c.lx) && (yi >= c.loy) && (yi < c.ly) && (zi >= c.loz) && (zi < c.lz);
+}
+
+// (2) the sample, for ingresses inside the window
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
+__device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, float yi, float zi) {
     const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
     const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);
     const float fz = div_spacing<DIVMODE>(zi, c.sz, c.rz);
     const int row = c.nx;
-    const int slab = c.nx * c.ny;
-    if (!TRILINEAR) {
-        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-        out = __ldg(c.v + ((z0 * c.ny + y0) * row + x0));
-        return true;
-    }
-    // indices are in [0, n-1): floor == the reference's truncation; the fractions are exact.
-    // One float->int conversion per axis (XU pipe) and the int->float back on the ALU pipe.
+    const int slab = c.slab;
+    // indices are in [1, n-1): truncation == floor == the reference's (int) cast
     const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const int cell = (z0 * c.ny + y0) * row + x0;
+    if (!TRILINEAR) return __ldg(c.v + cell);
+    // One float->int conversion per axis (XU pipe) and the int->float back on the ALU pipe;
+    // the fractions are exact.
     const float gx = (float)x0, gy = (float)y0, gz = (float)z0;
     const float tx = __fsub_rn(fx, gx);
     const float ty = __fsub_rn(fy, gy);
     const float tz = __fsub_rn(fz, gz);
     float s000, l001, l010, l011, l100, l101, l110, l111;
-    // Corner fetch.  TEXGATHER 1: both z layers through the texture unit (two tld4).  TEXGATHER 2:
-    // the lower layer through the texture unit, the upper one through the load/store unit (one tld4 +
-    // four loads): the two units return data to the register file over separate paths, and each of
-    // them alone is what saturates first once the instruction count is down (profiles/r1d, r1e, r1g).
-    if (TEXGATHER == 1) {
+    if (FETCH == 1) {
         const float u = gx + 1.0f, v = gy + 1.0f;  // exact: small integers
         gather4(c.tex, z0, u, v, l010, l011, l001, s000);
         gather4(c.tex, z0 + 1, u, v, l110, l111, l101, l100);
-    } else if (TEXGATHER == 2) {
+    } else if (FETCH == 2) {
         gather4(c.tex, z0, gx + 1.0f, gy + 1.0f, l010, l011, l001, s000);
-        const float* __restrict__ p = c.v + (((z0 + 1) * c.ny + y0) * row + x0);
+        const float* __restrict__ p = c.v + slab + cell;
         l100 = __ldg(p);
         l101 = __ldg(p + 1);
         l110 = __ldg(p + row);
         l111 = __ldg(p + row + 1);
+    } else if (FETCH == 4) {
+        const float4* __restrict__ q = c.quad + cell;
+        const float4 lo = __ldg(q);
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(q) + c.slab16));
+        s000 = lo.x, l001 = lo.y, l010 = lo.z, l011 = lo.w;
+        l100 = hi.x, l101 = hi.y, l110 = hi.z, l111 = hi.w;
     } else {
-        const float* __restrict__ p = c.v + ((z0 * c.ny + y0) * row + x0);
+        const float* __restrict__ p = c.v + cell;
         s000 = __ldg(p);
         l001 = __ldg(p + 1);
         l010 = __ldg(p + row);
@@ -275,29 +316,13 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
         l111 = __ldg(p + slab + row + 1);
     }
     if (POSITIVE) {
-        // With a weight t <= 1 - 2^-20 the clamp of std::lerp provably never fires:
-        // RN(t * RN(b - a)) <= (1 - 2^-20)(1 + 2^-24)^2 |b - a| < |b - a| (or, for subnormal products,
-        // RN(t * d) <= d with d = b - a exact), so a + RN(t * RN(b - a)) stays on a's side of b and the
-        // final rounding, being monotone, cannot cross the representable value b.  Then
-        // lerp == a + t * (b - a), three instructions.  Weights within 2^-20 of 1 take the clamped form.
-        if (fmaxf(fmaxf(tx, ty), tz) <= 0.99999904632568359375f) {
-            const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
-            const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
-            const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));
-            const float high_x2 = __fadd_rn(l110, __fmul_rn(tx, __fsub_rn(l111, l110)));
-            const float low_y = __fadd_rn(low_x1, __fmul_rn(ty, __fsub_rn(low_x2, low_x1)));
-            const float high_y = __fadd_rn(high_x1, __fmul_rn(ty, __fsub_rn(high_x2, high_x1)));
-            out = __fadd_rn(low_y, __fmul_rn(tz, __fsub_rn(high_y, low_y)));
-            return true;
-        }
-        const float low_x1 = lerp_pos(s000, l001, tx);
-        const float low_x2 = lerp_pos(l010, l011, tx);
-        const float high_x1 = lerp_pos(l100, l101, tx);
-        const float high_x2 = lerp_pos(l110, l111, tx);
-        const float low_y = lerp_pos(low_x1, low_x2, ty);
-        const float high_y = lerp_pos(high_x1, high_x2, ty);
-        out = lerp_pos(low_y, high_y, tz);
-        return true;
+        const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
+        const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
+        const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));
+        const float high_x2 = __fadd_rn(l110, __fmul_rn(tx, __fsub_rn(l111, l110)));
+        const float low_y = __fadd_rn(low_x1, __fmul_rn(ty, __fsub_rn(low_x2, low_x1)));
+        const float high_y = __fadd_rn(high_x1, __fmul_rn(ty, __fsub_rn(high_x2, high_x1)));
+        return __fadd_rn(low_y, __fmul_rn(tz, __fsub_rn(high_y, low_y)));
     }
     const bool ux = tx > 0.f, uy = ty > 0.f, uz = tz > 0.f;
     const float s010 = uy ? l010 : s000;
@@ -313,8 +338,7 @@ __device__ __forceinline__ bool cube_sample_inb(const CubeView& c, float x, floa
     const float high_x2 = lerp_ref(s110, s111, tx);
     const float low_y = lerp_ref(low_x1, low_x2, ty);
     const float high_y = lerp_ref(high_x1, high_x2, ty);
-    out = lerp_ref(low_y, high_y, tz);
-    return true;
+    return lerp_ref(low_y, high_y, tz);
 }
 
 // ---------------------------------------------------------------------------------

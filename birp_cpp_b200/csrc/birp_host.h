@@ -3,6 +3,9 @@
 #include "../../include/birp_b200.h"
 
 namespace birp {
+// pose-independent frame terms: tanf of the half fields of view, aspect ratio (src/Camera.cpp:137,150-151)
+void host_fov_terms(float fov_x_deg, float fov_y_deg, int W, int H, float* tan_half_x, float* tan_half_y,
+                    float* aspect);
 int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out);
 int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,

@@ -20,199 +20,39 @@
 #include <vector>
 
 #include "../../include/birp_b200.h"
+#include "birp_frame_math.h"
 #include "birp_host.h"
 
 namespace {
 
-struct Vec3 {
-    float x, y, z;
+// the functions the reference itself calls (fp32 overloads of <cmath> -> glibc sinf, cosf, ...)
+struct HostMath {
+    static float sqrt(float x) { return std::sqrt(x); }
+    static float sin(float x) { return std::sin(x); }
+    static float cos(float x) { return std::cos(x); }
+    static float acos(float x) { return std::acos(x); }
+    static float asin(float x) { return std::asin(x); }
+    static float atan2(float y, float x) { return std::atan2(y, x); }
+    static float abs(float x) { return std::abs(x); }
 };
-struct Mat3 {
-    float m[3][3];
-};
-
-inline float dot3(const Vec3& a, const Vec3& b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
-inline float norm3(const Vec3& a) { return std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
-
-// n x n product with a running fp32 sum started at 0 (src/Helper.cpp:80-91)
-Mat3 mul(const Mat3& a, const Mat3& b) {
-    Mat3 r;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            float acc = 0.0f;
-            for (int k = 0; k < 3; ++k) acc = acc + (a.m[i][k] * b.m[k][j]);
-            r.m[i][j] = acc;
-        }
-    return r;
-}
-
-// 2x2 minor obtained by deleting row `skip_r` and column `skip_c`
-inline float minor2(const Mat3& a, int skip_r, int skip_c) {
-    float s[4];
-    int n = 0;
-    for (int r = 0; r < 3; ++r) {
-        if (r == skip_r) continue;
-        for (int c = 0; c < 3; ++c) {
-            if (c == skip_c) continue;
-            s[n++] = a.m[r][c];
-        }
-    }
-    return s[0] * s[3] - s[1] * s[2];
-}
-
-// Laplace expansion along row 0 with an alternating integer sign (src/Helper.cpp:170-193)
-float det(const Mat3& a) {
-    float result = 0;
-    int sign = 1;
-    for (int i = 0; i < 3; ++i) {
-        result = result + sign * a.m[0][i] * minor2(a, 0, i);
-        sign = -sign;
-    }
-    return result;
-}
-
-// transpose(cofactor) scaled by 1/det (src/Helper.cpp:241-263); false when det == 0
-bool inverse(const Mat3& a, Mat3* out) {
-    if (det(a) == 0) return false;
-    const float d = 1.f / det(a);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            // cofactor (j,i): pow(-1, j+i) is evaluated in double in the reference (:235)
-            float c = (float)(std::pow(-1, j + i) * minor2(a, j, i));
-            c *= d;
-            out->m[i][j] = c;
-        }
-    return true;
-}
-
-struct SunProjection {
-    float xo, yo;
-};
-
-// Camera::PointToPlane for the quantities Orient consumes (xo, yo)
-SunProjection project_to_image_plane(const Vec3& obj, float plac, const Vec3& cam, const Vec3& look,
-                                     const Vec3& look_unit, const Vec3& north, const Vec3& right) {
-    const float to_deg = 180 / M_PI;
-    const float snumer = (look.x * obj.x) + (look.y * obj.y) + (look.z * obj.z) + plac;
-    const float sdenom = dot3(look, look_unit);
-    const float scalar = snumer / sdenom;
-    const Vec3 q = {obj.x - (scalar * look_unit.x), obj.y - (scalar * look_unit.y),
-                    obj.z - (scalar * look_unit.z)};
-    const Vec3 rel = {q.x - cam.x, q.y - cam.y, q.z - cam.z};
-    float dp = std::sqrt((rel.x * rel.x) + (rel.y * rel.y) + (rel.z * rel.z));
-    const Vec3 rel_unit = {rel.x / dp, rel.y / dp, rel.z / dp};
-    dp = std::sqrt((rel_unit.x * rel_unit.x) + (rel_unit.y * rel_unit.y) + (rel_unit.z * rel_unit.z));
-
-    auto clamped_angle_deg = [&](const Vec3& axis, bool clamp_low) {
-        const float num = dot3(rel_unit, axis);
-        const float den = dp * std::sqrt((axis.x * axis.x) + (axis.y * axis.y) + (axis.z * axis.z));
-        float c = num / den;
-        if (c > 1) c = 1.f;
-        else if (clamp_low && c < -1) c = -1.f;
-        return to_deg * std::acos(c);
-    };
-    const float angle_from_north = clamped_angle_deg(north, true);
-    const float angle_from_right = clamped_angle_deg(right, true);
-    const float sign_x = (angle_from_right > 90) ? -1.f : 1.f;
-    const float sign_y = 1.f;
-
-    Vec3 to_obj = {obj.x - cam.x, obj.y - cam.y, obj.z - cam.z};
-    const float to_obj_len = std::sqrt((to_obj.x * to_obj.x) + (to_obj.y * to_obj.y) + (to_obj.z * to_obj.z));
-    to_obj = {to_obj.x / to_obj_len, to_obj.y / to_obj_len, to_obj.z / to_obj_len};
-    const float t7 = dot3(to_obj, look_unit);
-    const float t8 = std::sqrt((to_obj.x * to_obj.x) + (to_obj.y * to_obj.y) + (to_obj.z * to_obj.z));
-    float t9 = t7 / t8;
-    if (t9 > 1) t9 = 1.f;
-    const float off_axis_deg = to_deg * std::acos(t9);
-
-    SunProjection out = {0.f, 0.f};
-    if (off_axis_deg > 0.000001f) {
-        out.xo = sign_x * off_axis_deg * std::sin(angle_from_north / to_deg);
-        out.yo = sign_y * off_axis_deg * std::cos(angle_from_north / to_deg);
-    }
-    return out;
-}
-
-// Camera::Orient: roll angle (degrees, [0,360]) that lays the Sun-Earth line horizontally
-float sun_roll_angle(const Vec3& cam, const Vec3& aim) {
-    const float to_deg = 180.f / M_PI;
-    const Vec3 look = {aim.x - cam.x, aim.y - cam.y, aim.z - cam.z};
-    const float len = norm3(look);
-    const Vec3 u = {look.x / len, look.y / len, look.z / len};
-
-    const float phi = std::acos(u.z);
-    const float s = std::sin(phi);
-    // (the reference also derives a theta1 from u.x the same way; nothing reads it)
-    float theta2;
-    if (std::abs(s) < std::abs(u.y)) {
-        // degrees stored where radians are used below: reference behaviour (:352-357)
-        theta2 = (s * u.y < 0) ? (float)(std::acos(-1) * to_deg) : (float)(std::acos(1) * to_deg);
-    } else {
-        theta2 = std::asin(u.y / s);
-    }
-    Vec3 north = {-1.f * std::cos(theta2) * std::cos(phi), -1.f * std::sin(theta2) * std::cos(phi),
-                  std::sin(phi)};
-    // octant sign table of :368-392: sign of north.{x,y} as a function of the signs of u
-    const bool xn = u.x < 0, yn = u.y < 0, zn = u.z < 0;
-    if ((u.x >= 0 || xn) && (u.y >= 0 || yn) && (u.z >= 0 || zn)) {  // false only for NaN components
-        const float sx = (xn != zn) ? 1.f : -1.f;
-        const float sy = (yn != zn) ? 1.f : -1.f;
-        north.x = sx * std::abs(north.x);
-        north.y = sy * std::abs(north.y);
-    }
-    north.z = std::abs(north.z);
-
-    const Vec3 right = {(u.y * north.z) - (u.z * north.y), (u.z * north.x) - (u.x * north.z),
-                        (u.x * north.y) - (u.y * north.x)};
-    const float plac = (-1.f * look.x * cam.x) + (-1.f * look.y * cam.y) + (-1.f * look.z * cam.z);
-    const Vec3 sun = {23455.f, 0.f, 0.f};
-    const SunProjection p = project_to_image_plane(sun, plac, cam, look, u, north, right);
-    float angle = 270 - (to_deg * std::atan2(0 - p.xo, 0 - p.yo));
-    if (angle > 360) angle = angle - 360;
-    else if (angle < 0) angle = angle + 360;
-    return angle;
-}
-
-Mat3 rot_z(float a) {
-    return Mat3{{{std::cos(a), -std::sin(a), 0}, {std::sin(a), std::cos(a), 0}, {0, 0, 1}}};
-}
-Mat3 rot_x(float a) {
-    return Mat3{{{1, 0, 0}, {0, std::cos(a), -std::sin(a)}, {0, std::sin(a), std::cos(a)}}};
-}
 
 }  // namespace
 
 namespace birp {
 
+void host_fov_terms(float fov_x_deg, float fov_y_deg, int W, int H, float* tan_half_x, float* tan_half_y,
+                    float* aspect) {
+    const float to_rad = M_PI / 180.f;
+    *tan_half_x = std::tan(to_rad * (fov_x_deg / 2));  // src/Camera.cpp:150
+    *tan_half_y = std::tan(to_rad * (fov_y_deg / 2));  // src/Camera.cpp:151
+    *aspect = (float)W / (float)H;                     // src/Camera.cpp:137
+}
+
 int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out) {
-    const float to_rad = M_PI / 180.f;
-    const Vec3 cam = {pos[0], pos[1], pos[2]};
-    const Vec3 aim = {aim_x, 0.f, 0.f};
-    const float angle_sun = sun_roll_angle(cam, aim);
-    const float angle_sun_corrected = 180.f - angle_sun;
-
-    const float x_diff = aim.x - cam.x;
-    const float theta = (2 * M_PI) - std::atan2(x_diff, cam.y);
-    const float hypotenuse = std::sqrt(x_diff * x_diff + cam.y * cam.y);
-    const float phi = std::atan2(hypotenuse, cam.z);
-
-    const Mat3 rz = rot_z(theta);
-    const Mat3 rx = rot_x(phi);
-    const Mat3 rz2 = rot_z(angle_sun_corrected * to_rad);
-    const Mat3 rotation = mul(mul(rz2, rx), rz);
-    Mat3 inv;
-    if (!inverse(rotation, &inv)) return BIRP_ERR_SINGULAR;
-
-    out->pos[0] = cam.x;
-    out->pos[1] = cam.y;
-    out->pos[2] = cam.z;
-    std::memcpy(out->rinv, inv.m, sizeof(out->rinv));
-    out->tan_half_x = std::tan(to_rad * (fov_x_deg / 2));
-    out->tan_half_y = std::tan(to_rad * (fov_y_deg / 2));
-    out->aspect = (float)W / (float)H;
-    out->sun_angle = angle_sun;
-    return BIRP_OK;
+    float tx, ty, aspect;
+    host_fov_terms(fov_x_deg, fov_y_deg, W, H, &tx, &ty, &aspect);
+    return fm::frame_setup_T<HostMath>(pos, aim_x, tx, ty, aspect, out);
 }
 
 // frame_setup for a whole sweep: poses are independent, so they are split over host threads

@@ -20,8 +20,9 @@ struct RenderGeom {
     long long out_frame_offset = 0, out_frame_stride = 1;
 };
 
-// bit in the device status word
-constexpr int kStatusNanIndex = 1;
+// bits in the device status word
+constexpr int kStatusNanIndex = 1;  // BIRP_ERR_RANGE
+constexpr int kStatusSingular = 2;  // BIRP_ERR_SINGULAR (device frame setup)
 
 cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames, const RenderGeom& g,
                                const float* d_dist, int flags, float* d_images,
@@ -36,11 +37,17 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
                                float* d_out, cudaStream_t stream);
 
+// per-frame setup / orbit poses on the device (k = {a, e, sqrt(1-e^2), u[3], w[3]})
+cudaError_t launch_frame_setup(const float* d_poses, int n, float aim_x, float tan_half_x, float tan_half_y,
+                               float aspect, birp_frame* d_frames, int* d_status, cudaStream_t stream);
+cudaError_t launch_orbit_poses(int n, const double k[9], float* d_poses, cudaStream_t stream);
 cudaError_t launch_cmem_math_selftest(long n, unsigned long long* d_err6, cudaStream_t stream);
 cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream);
 
 // upload-time analysis of a resident cube (see CubeView)
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream);
+// build the quad copy of the grid and compare every entry with the linear copy (*d_bad |= 1 on a mismatch)
+cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 

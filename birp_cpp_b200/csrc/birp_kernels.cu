@@ -15,7 +15,9 @@
 // the serial per-pixel accumulation order of the reference is kept.
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 
+#include "birp_frame_math.h"
 #include "birp_internal.h"
 
 namespace birp {
@@ -42,6 +44,7 @@ struct MarchArgs {
     long long total_tiles;
     float ray_width;
     int accumulate;
+    double scale_k;  // BIRP_SCALE_K: a kernel parameter so the fp64 multiply reads it from the constant bank
     // frame f of this launch is written to image slot out_offset + f * out_stride of `images`
     // (1-GPU: 0 / 1; multi-GPU sweeps scatter straight into the gathering rank's buffer)
     long long out_offset, out_stride;
@@ -132,47 +135,119 @@ struct RayState {
     float acc;         // pixel value so far
 };
 
-// March `count` steps whose distances sit in shared memory at byte address `sdist` (a 32-bit shared
-// window address, advanced by 4 per step: one LDS + one IADD, no per-step address arithmetic).
-// Returns the number of samples accumulated; `alive` is cleared when the ray ended.
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
-__device__ __forceinline__ int march_steps(const CubeView& c, RayState& r, unsigned sdist, int count, float ray_width,
-                                           int* status, bool& alive) {
-    int k = 0;
-    for (; k < count; ++k, sdist += 4) {
+// March the steps whose distances sit in shared memory at byte addresses [sdist, send) (32-bit
+// shared-window addresses, advanced by 4 per step: one LDS + one IADD, no per-step index
+// arithmetic and no separate step counter).  Returns the address of the first step NOT
+// accumulated (send when the ray is still alive); `alive` is cleared when the ray ended.
+//
+// Control flow: the inner loop is the hot path only -- a sample inside the hot window whose
+// single-multiply scale is proven exact.  Anything else (ray leaving the cube, first cell of an
+// axis, NaN, a scale product next to a rounding midpoint, ...) BREAKS out of it; the lane then
+// waits at the loop exit for the rest of its warp, evaluates that one sample with the literal
+// transcription (cube_sample + scale_sample) and, if the ray lives on, re-enters the hot loop.
+// So the hot loop carries no reconvergence bookkeeping and no cold code; almost every break is a
+// ray ending, and a lane that re-enters alone (about 1 warp in 1000) costs its warp at most one
+// extra pass.
+// Make a warp-uniform kernel parameter opaque to ptxas AND keep it in a uniform register: the OR-reduction
+// of 32 identical words is the word itself, the result of redux.sync lives in the uniform register
+// file, and ptxas cannot rematerialise it from the constant bank inside the march loop (left to
+// itself it re-loads a dozen constants in every step; issue slots are the scarce resource here).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void pin_uniform(float& v) {
+    v = __uint_as_float(__reduce_or_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+__device__ __forceinline__ void pin_uniform(int& v) { v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v); }
+__device__ __forceinline__ void pin_uniform(long long& v) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)((unsigned long long)v >> 32));
+    v = (long long)(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ void pin_uniform(double& v) {
+    long long b = __double_as_longlong(v);
+    pin_uniform(b);
+    v = __longlong_as_double(b);
+}
+
+// ingresses of the sample whose distance sits at shared address `sdist`, and whether it is hot
+__device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& r, unsigned sdist, float& xi, float& yi,
+                                             float& zi) {
+    float tk;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
+    // Helper::MatrixScalarMultiply then "+ position" (src/Camera.cpp:183-189): two roundings,
+    // then DataCube::GetSample's `x - coords_x[0]` (src/DataCube.cpp:205)
+    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
+    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
+    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
+    return cube_hot_window(c, xi, yi, zi);
+}
+
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
+__device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
+                                                float ray_width, double K, int* status, bool& alive) {
+    for (;;) {
+        // (an opaque statement of the OUTER loop only: keeps the compiler from merging the two loops
+        // into one, which would put the cold code and its reconvergence barrier back into every step)
+        asm volatile("" : "+r"(sdist));
+        if (sdist == send) return sdist;
+        float xi, yi, zi;
+        if (step_ingress(c, r, sdist, xi, yi, zi)) {
+            // Hot loop, rotated by hand: the body evaluates the sample at `sdist` (known to be in the
+            // window) AND the window test of the next one, so a step has a single branch.  (The table
+            // has one padding entry: the look-ahead of the last step reads it and discards the result.)
+            bool more;
+            do {
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, POSITIVE, FETCH>(c, xi, yi, zi);
+                float v;
+                const bool exact = scale_fast<!POSITIVE>(s, ray_width, K, v);
+                const bool hot_next = step_ingress(c, r, sdist + 4, xi, yi, zi);
+                if (exact) {
+                    r.acc = __fadd_rn(r.acc, v);
+                    sdist += 4;
+                }
+                more = exact && hot_next && (sdist != send);
+            } while (more);
+            if (sdist == send) return sdist;
+        }
         float tk;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
         const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
         const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
         const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
-        float s;
-        if (!cube_sample_inb<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(c, x, y, z, s)) {
-            // outside the hot window: almost always a ray leaving the cube (the reference returns
-            // -1, which ends the ray); also NaN coordinates and ingresses below 2^-100.  The
-            // generic transcription of DataCube::GetSample decides.
-            bool nan_index = false;
-            s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-            if (nan_index) atomicOr(status, kStatusNanIndex);
-        }
+        bool nan_index = false;
+        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+        if (nan_index) atomicOr(status, kStatusNanIndex);
         s = scale_sample(s, ray_width);
         if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
             alive = false;
-            break;
+            return sdist;
         }
         r.acc = __fadd_rn(r.acc, s);
+        sdist += 4;
     }
-    return k;
 }
 
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int TEXGATHER>
+template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
-    __shared__ float s_dist[kSmemDist];
+    __shared__ float s_dist[kSmemDist + 1];  // + the look-ahead padding entry
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
     const int first_chunk = min(kSmemDist, a.nsamples);
     for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
     __syncthreads();
+    CubeView cc = c;
+    double K = a.scale_k;
+    float ray_width = a.ray_width;
+    pin_uniform(cc.ox), pin_uniform(cc.oy), pin_uniform(cc.oz);
+    pin_uniform(cc.lox), pin_uniform(cc.loy), pin_uniform(cc.loz);
+    pin_uniform(cc.lx), pin_uniform(cc.ly), pin_uniform(cc.lz);
+    pin_uniform(cc.rx), pin_uniform(cc.ry), pin_uniform(cc.rz);
+    pin_uniform(cc.sx), pin_uniform(cc.sy), pin_uniform(cc.sz);
+    pin_uniform(ray_width);
+    pin_uniform(K);
+    pin_uniform(cc.nx), pin_uniform(cc.ny), pin_uniform(cc.slab16);
 
     int f = 0, i = 0, j = 0;
     const bool owns_pixel = lane_ray(a, f, i, j);
@@ -189,26 +264,23 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         r.acc = a.accumulate ? *pix : 0.f;
     }
     bool alive = owns_pixel;
-    int nlive = 0;
-    // Keep the per-axis cube constants in ordinary registers for the whole march: left to itself ptxas
-    // re-loads ~10 of them from the constant bank in every step, and issue slots are the scarce resource
-    // here (+7 % measured).  The empty asm makes each value opaque, so it cannot be rematerialised.
-    CubeView cc = c;
-    asm volatile("" : "+f"(cc.ox), "+f"(cc.oy), "+f"(cc.oz), "+f"(cc.lx), "+f"(cc.ly), "+f"(cc.lz));
-    asm volatile("" : "+f"(cc.rx), "+f"(cc.ry), "+f"(cc.rz), "+f"(cc.sx), "+f"(cc.sy), "+f"(cc.sz));
-    asm volatile("" : "+r"(cc.nx), "+r"(cc.ny), "+l"(cc.v));
-    if (alive) nlive = march_steps<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(cc, r, s_base, first_chunk, a.ray_width, a.status, alive);
+    unsigned nlive4 = 0;  // 4 x the number of samples accumulated
+    if (alive)
+        nlive4 = march_steps<TRILINEAR, DIVMODE, POSITIVE, FETCH>(cc, r, s_base, s_base + 4u * first_chunk, ray_width,
+                                                                  K, a.status, alive) - s_base;
     // marches longer than the staged table: refill it chunk by chunk (every thread of the CTA takes part)
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
         __syncthreads();
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
-        if (alive) nlive += march_steps<TRILINEAR, DIVMODE, POSITIVE, TEXGATHER>(cc, r, s_base, chunk, a.ray_width, a.status, alive);
+        if (alive)
+            nlive4 += march_steps<TRILINEAR, DIVMODE, POSITIVE, FETCH>(cc, r, s_base, s_base + 4u * chunk, ray_width,
+                                                                       K, a.status, alive) - s_base;
     }
     if (owns_pixel) {
         *pix = r.acc;
-        if (a.valid) atomicAdd(a.valid, (unsigned long long)nlive);
+        if (a.valid) atomicAdd(a.valid, (unsigned long long)(nlive4 >> 2));
     }
 }
 
@@ -255,6 +327,7 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.total_tiles = (long long)a.tiles_per_frame * g.nframes;
     a.ray_width = g.ray_width;
     a.accumulate = (flags & BIRP_ACCUMULATE) ? 1 : 0;
+    a.scale_k = BIRP_SCALE_K;
     a.out_offset = g.out_frame_offset;
     a.out_stride = g.out_frame_stride;
     const long long nb = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -276,24 +349,31 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, bool POS, int TEX>
+template <bool TRI, int DIV, bool POS, int FETCH>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
-    march_cube_kernel<TRI, DIV, POS, TEX><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    march_cube_kernel<TRI, DIV, POS, FETCH><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
 }
 
-template <int DIV>
-cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, int tex,
-                            cudaStream_t stream) {
-    if (!tri) return launch_cube_variant<false, DIV, false, 0>(a, c, blocks, stream);
-    if (pos) {
-        if (tex == 2) return launch_cube_variant<true, DIV, true, 2>(a, c, blocks, stream);
-        if (tex == 1) return launch_cube_variant<true, DIV, true, 1>(a, c, blocks, stream);
-        return launch_cube_variant<true, DIV, true, 0>(a, c, blocks, stream);
+template <int DIV, bool POS>
+cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, cudaStream_t stream) {
+    switch (fetch) {
+        case 1: return launch_cube_variant<true, DIV, POS, 1>(a, c, blocks, stream);
+        case 2: return launch_cube_variant<true, DIV, POS, 2>(a, c, blocks, stream);
+        case 4: return launch_cube_variant<true, DIV, POS, 4>(a, c, blocks, stream);
+        default: return launch_cube_variant<true, DIV, POS, 0>(a, c, blocks, stream);
     }
-    if (tex == 2) return launch_cube_variant<true, DIV, false, 2>(a, c, blocks, stream);
-    if (tex == 1) return launch_cube_variant<true, DIV, false, 1>(a, c, blocks, stream);
-    return launch_cube_variant<true, DIV, false, 0>(a, c, blocks, stream);
+}
+
+template <int DIV>
+cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, int fetch,
+                            cudaStream_t stream) {
+    if (!tri) {
+        if (pos) return launch_cube_variant<false, DIV, true, 0>(a, c, blocks, stream);
+        return launch_cube_variant<false, DIV, false, 0>(a, c, blocks, stream);
+    }
+    if (pos) return launch_cube_fetch<DIV, true>(a, c, blocks, fetch, stream);
+    return launch_cube_fetch<DIV, false>(a, c, blocks, fetch, stream);
 }
 
 // upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
@@ -326,6 +406,37 @@ __global__ void __launch_bounds__(256) verify_gather_kernel(const CubeView c, in
     if (!ok) atomicOr(bad, 1);
 }
 
+// quad copy: quad[(z*ny + y)*nx + x] = {v[z][y][x], v[z][y][x+1], v[z][y+1][x], v[z][y+1][x+1]}, neighbours
+// clamped at the last row / column (entries no in-bounds sample reads)
+__global__ void __launch_bounds__(256) pack_quads_kernel(const float* __restrict__ v, int nx, int ny, int nz,
+                                                         float4* __restrict__ quad) {
+    const size_t n = (size_t)nx * ny * nz;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int y = (int)((t / nx) % ny);
+        const int dx = (x + 1 < nx) ? 1 : 0;
+        const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+        quad[t] = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
+    }
+}
+
+// upload-time self-check of the quad copy, every entry, bit for bit, through the load the march uses
+__global__ void __launch_bounds__(256) verify_quads_kernel(const float* __restrict__ v, int nx, int ny, int nz,
+                                                           const float4* __restrict__ quad, int* bad) {
+    const size_t n = (size_t)nx * ny * nz;
+    bool ok = true;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int y = (int)((t / nx) % ny);
+        const int dx = (x + 1 < nx) ? 1 : 0;
+        const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+        const float4 q = __ldg(quad + t);
+        ok &= __float_as_uint(q.x) == __float_as_uint(v[t]) && __float_as_uint(q.y) == __float_as_uint(v[t + dx]) &&
+              __float_as_uint(q.z) == __float_as_uint(v[t + dy]) && __float_as_uint(q.w) == __float_as_uint(v[t + dy + dx]);
+    }
+    if (!ok) atomicOr(bad, 1);
+}
+
 // ---- upload-time analysis kernels -------------------------------------------------------
 // flag |= 1 unless every voxel is finite and > 0
 __global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restrict__ v, size_t n, int* flag) {
@@ -353,6 +464,54 @@ __global__ void __launch_bounds__(256) verify_div_kernel(float s, float r, unsig
     }
     if (__any_sync(0xffffffffu, b0) && (threadIdx.x & 31) == 0) atomicOr(bad + 0, 1);
     if (__any_sync(0xffffffffu, b1) && (threadIdx.x & 31) == 0) atomicOr(bad + 1, 1);
+}
+
+// ---- per-frame setup on the device ----------------------------------------------
+// The math provider of birp_frame_math.h for the device: every transcendental in fp64, rounded
+// once to fp32 (glibc's fp32 functions, which the host instantiation and the reference call, are
+// correctly rounded in the vast majority of cases; the two agree except within ~1e-8 of an fp32
+// rounding boundary).  sqrt and the arithmetic between the calls are IEEE fp32 in both.
+struct DeviceFrameMath {
+    static __host__ __device__ float sqrt(float x) { return sqrtf(x); }
+    static __host__ __device__ float sin(float x) { return (float)::sin((double)x); }
+    static __host__ __device__ float cos(float x) { return (float)::cos((double)x); }
+    static __host__ __device__ float acos(float x) { return (float)::acos((double)x); }
+    static __host__ __device__ float asin(float x) { return (float)::asin((double)x); }
+    static __host__ __device__ float atan2(float y, float x) { return (float)::atan2((double)y, (double)x); }
+    static __host__ __device__ float abs(float x) { return fabsf(x); }
+};
+
+// one thread per pose: Camera::Integrate's prologue + Camera::Orient (src/Camera.cpp:85-137,309-508)
+__global__ void __launch_bounds__(128) frame_setup_kernel(const float* __restrict__ poses, int n, float aim_x,
+                                                          float tan_half_x, float tan_half_y, float aspect,
+                                                          birp_frame* __restrict__ out, int* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float pos[3] = {poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]};
+    birp_frame fr;
+    const int rc = fm::frame_setup_T<DeviceFrameMath>(pos, aim_x, tan_half_x, tan_half_y, aspect, &fr);
+    if (rc != BIRP_OK) {
+        atomicOr(status, kStatusSingular);
+        return;
+    }
+    out[i] = fr;
+}
+
+// n camera positions, uniform in time, on a Kepler ellipse (fp64, Newton on Kepler's equation, in
+// the operation order of birp_cpp_b200/synthetic.py: orbit_poses): pos = -xp * u + yp * w
+__global__ void __launch_bounds__(128) orbit_poses_kernel(int n, double a, double e, double b_over_a, double ux,
+                                                          double uy, double uz, double wx, double wy, double wz,
+                                                          float* __restrict__ poses) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double M = 2.0 * BIRP_PI * ((double)i + 0.5) / (double)n;
+    double E = M;
+    for (int it = 0; it < 60; ++it) E -= (E - e * sin(E) - M) / (1.0 - e * cos(E));
+    const double xp = a * (cos(E) - e);
+    const double yp = a * b_over_a * sin(E);
+    poses[3 * i + 0] = (float)((-xp) * ux + yp * wx);
+    poses[3 * i + 1] = (float)((-xp) * uy + yp * wy);
+    poses[3 * i + 2] = (float)((-xp) * uz + yp * wz);
 }
 
 // K4: one thread per ray, samples[ray][k] (row-major, as the host sampled them)
@@ -449,13 +608,26 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     int divmode = cube.divmode;
     if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
     if (flags & BIRP_DIV_IEEE) divmode = 2;
-    int tex = 0;  // corner fetch: 0 eight loads, 1 two texture gathers, 2 one gather + four loads
-    if (tri && cube.tex != 0 && !(flags & BIRP_NO_TEXTURE)) tex = (flags & BIRP_TEXTURE_ONLY) ? 1 : 2;
+    // corner fetch of the trilinear kernel (cube_sample_hot): what the cube has, minus what the flags forbid
+    const bool has_tex = cube.tex != 0 && !(flags & BIRP_NO_TEXTURE);
+    const bool has_quad = cube.quad != nullptr && !(flags & BIRP_NO_QUADS);
+    int fetch = 0;
+    if (tri) {
+        if (has_tex && (flags & BIRP_TEXTURE_ONLY)) fetch = 1;
+        else if (has_quad) fetch = 4;
+        else if (has_tex) fetch = 2;
+    }
+    CubeView view = cube;
+    if (!tri) {  // nearest neighbour has no interpolation weight to protect: the first cells stay hot
+        view.lox = BIRP_TINY_INGRESS;
+        view.loy = view.lox;
+        view.loz = view.lox;
+    }
     cudaError_t e;
     switch (divmode) {
-        case 0: e = launch_cube_div<0>(a, cube, blocks, tri, pos, tex, stream); break;
-        case 1: e = launch_cube_div<1>(a, cube, blocks, tri, pos, tex, stream); break;
-        default: e = launch_cube_div<2>(a, cube, blocks, tri, pos, tex, stream); break;
+        case 0: e = launch_cube_div<0>(a, view, blocks, tri, pos, fetch, stream); break;
+        case 1: e = launch_cube_div<1>(a, view, blocks, tri, pos, fetch, stream); break;
+        default: e = launch_cube_div<2>(a, view, blocks, tri, pos, fetch, stream); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e;
@@ -464,6 +636,15 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream) {
     scan_positive_kernel<<<148 * 8, 256, 0, stream>>>(d_v, n, d_flag);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, cudaStream_t stream) {
+    pack_quads_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_quad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    verify_quads_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_quad, d_bad);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
@@ -495,6 +676,23 @@ cudaError_t launch_accumulate(const float* d_samples, long nrays, int nsamples, 
     if (nrays <= 0) return cudaSuccess;
     accumulate_kernel<<<blocks_for(nrays, 256), 256, 0, stream>>>(d_samples, nrays, nsamples, ray_width,
                                                                   (flags & BIRP_ACCUMULATE) ? 1 : 0, d_image);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame_setup(const float* d_poses, int n, float aim_x, float tan_half_x, float tan_half_y,
+                               float aspect, birp_frame* d_frames, int* d_status, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    frame_setup_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(d_poses, n, aim_x, tan_half_x, tan_half_y, aspect,
+                                                              d_frames, d_status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_orbit_poses(int n, const double k[9], float* d_poses, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    orbit_poses_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(n, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7],
+                                                              k[8], d_poses);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

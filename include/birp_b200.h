@@ -57,10 +57,13 @@ enum {
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
     BIRP_GENERAL_LERP = 32,  /* full std::lerp semantics even for an all-positive cube */
-    /* corner fetch of the trilinear kernel; default: lower z layer by one texture gather, upper z
-       layer by four global loads (the two units return data over separate paths) */
-    BIRP_NO_TEXTURE = 64,    /* all eight corners with global loads */
-    BIRP_TEXTURE_ONLY = 128  /* all eight corners with two texture gathers */
+    /* corner fetch of the trilinear kernel; default: one 16-byte load per z layer from the quad
+       copy of the grid */
+    BIRP_NO_TEXTURE = 64,    /* no texture gathers */
+    BIRP_TEXTURE_ONLY = 128, /* all eight corners with two texture gathers */
+    BIRP_NO_QUADS = 256,     /* do not use the quad copy (lower layer: one texture gather, upper layer:
+                                four global loads; with BIRP_NO_TEXTURE: eight global loads) */
+    BIRP_QUADS_ONLY = 512    /* (the default when the quad copy exists; kept for explicit A/B runs) */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */
@@ -110,6 +113,19 @@ int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov
    computed on up to `nthreads` host threads (0 = choose) */
 int birp_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W,
                            int H, birp_frame* out, int nthreads);
+/* The same on the device, for sweeps whose poses never visit the host: d_poses (xyz interleaved) ->
+   d_frames, one thread per pose, enqueued on `stream`.  Same operation order as the host version
+   (one shared source, birp_frame_math.h) with every libm call evaluated in fp64 and rounded once,
+   so a frame differs from the host's only where a glibc fp32 result is within ~1e-8 of a rounding
+   boundary (measured: see tests/test_gpu_parity.py::test_device_frame_setup).  A singular rotation
+   sets a status bit: birp_check_device_status returns BIRP_ERR_SINGULAR. */
+int birp_frame_setup_device(const float* d_poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                            birp_frame* d_frames, void* stream);
+/* n camera positions, uniform in time, on a Kepler ellipse with its apogee at `inclination_deg` above
+   the +x axis in the x-z plane (the synthetic SMILE-like sweep of SURVEY 8(d) config 5; fp64 Newton
+   on Kepler's equation): host and device versions, poses xyz interleaved */
+int birp_orbit_poses(int n, double perigee, double apogee, double inclination_deg, float* poses);
+int birp_orbit_poses_device(int n, double perigee, double apogee, double inclination_deg, float* d_poses, void* stream);
 /* replaces Camera::GenerateRayDistWidth (src/Camera.cpp:69-81); dist_out may be NULL */
 int birp_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);
 /* replaces CMEM::Init(bool, ...) (src/Cmem.cpp:38-115); has_v/has_b = 0 mean "empty vector" */
@@ -128,8 +144,9 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
 void birp_cube_free(birp_cube* cube);
 /* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
    spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0,
-   info[2] = 1 when the layered-texture copy exists and passed its gather self-check */
-int birp_cube_info(const birp_cube* cube, int info[3]);
+   info[2] = 1 when the layered-texture copy exists and passed its gather self-check,
+   info[3] = 1 when the quad copy (16-byte corner fetch) exists and passed its self-check */
+int birp_cube_info(const birp_cube* cube, int info[4]);
 
 /* ------------------------------------------------------------------ the hot path, host buffers
  * frames: nframes records (host).  images: nframes*H*W floats (host), row j = image y, top row
@@ -185,8 +202,8 @@ int birp_ipc_export(const void* d_ptr, unsigned char handle[64]);
 int birp_ipc_import(const unsigned char handle[64], void** d_ptr);
 int birp_ipc_close(void* d_ptr);
 
-/* device error word of the calling thread's device (BIRP_ERR_RANGE conditions raised by
-   *_device launches); synchronises `stream`, returns BIRP_OK / BIRP_ERR_RANGE and clears it */
+/* device error word of the calling thread's device (BIRP_ERR_RANGE / BIRP_ERR_SINGULAR conditions raised
+   by *_device launches); synchronises `stream`, returns BIRP_OK or the error and clears it */
 int birp_check_device_status(void* stream);
 
 /* diagnostics: max relative error of the library's own fp64 exp2 / log2 / pow

@@ -83,18 +83,19 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
     assert want[0].min() > 0 and want[2].max() == 0  # inside / outside the cube
 
 
+# corner fetch (default: two quad loads; tld4 + quad load (BIRP_FETCH=3 only); tld4 + 4 loads; two tld4; 8 loads)
+# x division x lerp flavour
+_FETCH = [0, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
+_DIV = [0, capi.DIV_TWO_STEP, capi.DIV_IEEE]
+_LERP = [0, capi.GENERAL_LERP]
+
+
 @pytest.mark.parametrize("tri", [False, True])
 @pytest.mark.parametrize("neg", [False, True])
-@pytest.mark.parametrize("extra", [0, capi.DIV_TWO_STEP, capi.DIV_IEEE, capi.GENERAL_LERP,
-                                   capi.DIV_IEEE | capi.GENERAL_LERP, capi.DIV_TWO_STEP | capi.GENERAL_LERP,
-                                   capi.TEXTURE_ONLY, capi.TEXTURE_ONLY | capi.GENERAL_LERP | capi.DIV_TWO_STEP,
-                                   capi.TEXTURE_ONLY | capi.DIV_IEEE,
-                                   capi.NO_TEXTURE, capi.NO_TEXTURE | capi.DIV_TWO_STEP, capi.NO_TEXTURE | capi.DIV_IEEE,
-                                   capi.NO_TEXTURE | capi.GENERAL_LERP,
-                                   capi.NO_TEXTURE | capi.DIV_IEEE | capi.GENERAL_LERP,
-                                   capi.NO_TEXTURE | capi.DIV_TWO_STEP | capi.GENERAL_LERP])
+@pytest.mark.parametrize("extra", [f | d | l for f in _FETCH for d in _DIV for l in _LERP])
 def test_every_kernel_variant_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tri, neg, extra):
-    """all template variants of the DataCube march kernel (division x lerp flavour) agree with the oracle"""
+    """all template variants of the DataCube march kernel (corner fetch x division x lerp flavour) agree with
+    the oracle"""
     zyx, org, sp = cube1_neg if neg else cube1
     dev = dev_cube1_neg if neg else dev_cube1
     fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
@@ -106,6 +107,7 @@ def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
     a, b = dev_cube1.info(), dev_cube1_neg.info()
     assert a["positive"] and not b["positive"]
     assert a["texture"] and b["texture"], "layered-texture copy missing or failed its gather self-check"
+    assert a["quads"] and b["quads"], "quad copy missing or failed its self-check"
     assert a["divmode"] in (0, 1, 2) and a["divmode"] == b["divmode"]
     print("division variant proven exact for spacing 0.5:", a["divmode"])
     # awkward spacings: whatever variant is chosen, the renders must stay bit-exact
@@ -154,6 +156,57 @@ def test_rays_in_a_grid_plane_take_the_cold_path(gpu):
         c.free()
 
 
+def test_first_cells_and_near_one_weights(gpu):
+    """cameras inside and next to the first cell of every axis, looking both ways: those samples are outside
+    the hot window (index < 1, where the interpolation weight can exceed 1 - 2^-23 and std::lerp's clamp
+    is live) and must come out of the literal sampler bit for bit; rays cross the window edge repeatedly"""
+    rng = np.random.default_rng(33)
+    zyx = rng.uniform(1e-7, 1e-5, size=(24, 26, 28)).astype(np.float32)
+    org = np.array([-2.0, 1.0, 0.5], np.float32)
+    sp = np.array([0.3137255, 0.25, 0.4], np.float32)
+    poses = []
+    for fx, fy, fz in ((0.5, 0.5, 0.5), (0.999999, 3.2, 4.1), (5.3, 0.99999994, 2.2), (6.1, 4.4, 0.9999999),
+                       (1.0000001, 1.0000001, 1.0000001), (0.25, 12.0, 0.75), (20.0, 0.3, 11.0)):
+        poses.append((org[0] + fx * sp[0], org[1] + fy * sp[1], org[2] + fz * sp[2]))
+    poses = np.array(poses, np.float32)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        assert c.info()["positive"]
+        for aim in (3.0, -30.0):
+            fp = capi.frames_for_poses(poses, aim, 60.0, 60.0, 40, 40)
+            fo = O.orc_frames(poses, aim, 60.0, 60.0, 40, 40)
+            for fl in _FETCH:
+                got = c.render(fp, 40, 40, nsamples=600, maxdist=12, trilinear=True, extra_flags=fl)
+                want = O.orc_render_cube(zyx, org, sp, True, fo, 40, 40, nsamples=600, maxdist=12)
+                assert_bit_exact(got, want, f"aim={aim} flags={fl}")
+            assert want.max() > 0
+    finally:
+        c.free()
+
+
+def test_cube_with_zero_regions_stays_bit_exact(gpu):
+    """emissivity grids of real runs are zero inside the magnetosphere: zero samples must stay on the hot path
+    (their scaled value is exactly zero) and the std::lerp sign branch fires at every zero corner"""
+    zyx, org, sp = S.make_cube(64, 64, 64)
+    zyx = zyx.copy()
+    x = org[0] + sp[0] * np.arange(64)
+    r = np.sqrt(x[None, None, :] ** 2 + x[None, :, None] ** 2 + x[:, None, None] ** 2)
+    zyx[r < 12.0] = 0.0
+    zyx[40:44, :, :] = -0.0  # and a slab of negative zeros
+    c = capi.Cube(zyx, org, sp)
+    try:
+        assert not c.info()["positive"]
+        poses = np.array([S.DEFAULT_POS, (20.0, -15.0, 3.0), (0.5, 0.25, 1.0)], np.float32)
+        fp, fo = frames_pair(poses, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+        for tri in (False, True):
+            want = O.orc_render_cube(zyx, org, sp, tri, fo, W, H)
+            for fl in (_FETCH if tri else [0]):
+                assert_bit_exact(c.render(fp, W, H, trilinear=tri, extra_flags=fl), want, f"tri={tri} flags={fl}")
+            assert want.max() > 0
+    finally:
+        c.free()
+
+
 def test_cube_beyond_texture_limits_uses_global_loads(gpu):
     """more z slices than a layered texture can hold (2048): no texture copy, the global-load kernel runs"""
     rng = np.random.default_rng(21)
@@ -162,12 +215,13 @@ def test_cube_beyond_texture_limits_uses_global_loads(gpu):
     sp = np.array([0.5, 0.5, 0.01], np.float32)
     c = capi.Cube(zyx, org, sp)
     try:
-        assert not c.info()["texture"] and c.info()["positive"]
+        assert not c.info()["texture"] and c.info()["positive"] and c.info()["quads"]
         fp, fo = frames_pair(np.array([(0.2, 0.3, 5.0), (0.5, 0.1, -3.0)], np.float32), 36.0, 36.0, 24, 24)
-        got = c.render(fp, 24, 24, nsamples=400, maxdist=30, trilinear=True)
         want = O.orc_render_cube(zyx, org, sp, True, fo, 24, 24, nsamples=400, maxdist=30)
-        assert_bit_exact(got, want)
         assert want.max() > 0
+        for fl in (0, capi.NO_QUADS):  # two 16-byte quad loads / eight global loads
+            got = c.render(fp, 24, 24, nsamples=400, maxdist=30, trilinear=True, extra_flags=fl)
+            assert_bit_exact(got, want, f"flags={fl}")
     finally:
         c.free()
 
@@ -323,6 +377,54 @@ def test_render_constant_cube_counts_samples(gpu):
         c.free()
 
 
+# ------------------------------------------------------------------ device-side sweep setup
+def test_device_orbit_poses_and_frame_setup(gpu, dev_cube1, cube1):
+    """poses generated and turned into frame records on the device: against the host path (glibc, bit-identical
+    to the reference).  The device evaluates every libm call in fp64 and rounds once, so a value can differ
+    from glibc's fp32 result only where that result sits on a rounding boundary."""
+    import torch
+
+    n = 10000
+    dev = torch.device("cuda", 0)
+    d_poses = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d_frames = torch.zeros((n, 16), dtype=torch.float32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    capi.orbit_poses_device(n, d_poses.data_ptr(), stream=s)
+    capi.frame_setup_device(d_poses.data_ptr(), n, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, d_frames.data_ptr(), stream=s)
+    capi.check_device_status(s)
+    poses_dev = d_poses.cpu().numpy()
+    poses = S.orbit_poses(n)
+    same_pose = (poses_dev.view(np.uint32) == poses.view(np.uint32)).all(axis=1).mean()
+    assert same_pose >= 0.999 and np.abs(poses_dev - poses).max() <= 2e-6, (same_pose, np.abs(poses_dev - poses).max())
+
+    # frame records from the SAME poses: host (glibc) vs device
+    d_poses.copy_(torch.from_numpy(poses))
+    capi.frame_setup_device(d_poses.data_ptr(), n, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, d_frames.data_ptr(), stream=s)
+    capi.check_device_status(s)
+    got = d_frames.cpu().numpy()
+    want = capi.frames_for_poses(poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H).view(np.float32).reshape(-1, 16)
+    identical = (got.view(np.uint32) == want.view(np.uint32)).all(axis=1).mean()
+    print(f"device frame setup: {identical:.4%} of {n} frame records bit-identical to the host's")
+    assert np.array_equal(got[:, :3], want[:, :3]) and np.array_equal(got[:, 12:15], want[:, 12:15])
+    assert np.abs(got[:, 3:12] - want[:, 3:12]).max() <= 5e-7      # rotation_inverse entries (|r| <= 1)
+    assert np.abs(got[:, 15] - want[:, 15]).max() <= 1e-4          # sun angle, degrees (ulp at 360 is 3e-5)
+    assert identical >= 0.95
+
+    # and what it means for the images: every 50th frame, device-made records vs host-made records
+    idx = np.arange(0, n, 50)
+    zyx, org, sp = cube1
+    fr_dev = np.zeros(len(idx), capi.FRAME_DTYPE)
+    fr_dev.view(np.float32).reshape(-1, 16)[:] = got[idx]
+    fr_host = np.zeros(len(idx), capi.FRAME_DTYPE)
+    fr_host.view(np.float32).reshape(-1, 16)[:] = want[idx]
+    a = dev_cube1.render(fr_dev, W, H, trilinear=True)
+    b = dev_cube1.render(fr_host, W, H, trilinear=True)
+    frac = pixel_fraction_within(a, b)
+    print(f"images from device-made frame records: {frac:.4%} of pixels within 1e-5 of the host-made ones")
+    assert frac >= 0.999
+    assert abs(a.sum(dtype=np.float64) - b.sum(dtype=np.float64)) <= 1e-4 * b.sum(dtype=np.float64)
+
+
 # ------------------------------------------------------------------ full-size configs (BASELINE.json configs[2], [3])
 @pytest.mark.parametrize("n", [256])
 def test_config3_256cube_1024_image(gpu, n):
@@ -334,7 +436,8 @@ def test_config3_256cube_1024_image(gpu, n):
         want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=200, nthreads=16)
         assert_bit_exact(got, want, "256^3, 1024x1024, 200 samples")
         assert c.info()["texture"]
-        for fl in (capi.NO_TEXTURE, capi.TEXTURE_ONLY):
+        assert c.info()["quads"]
+        for fl in (capi.NO_TEXTURE, capi.TEXTURE_ONLY, capi.NO_QUADS, capi.QUADS_ONLY, capi.NO_QUADS | capi.NO_TEXTURE):
             assert_bit_exact(c.render(fp, 1024, 1024, nsamples=200, trilinear=True, extra_flags=fl), want,
                              f"corner-fetch variant {fl}")
         # fine step: a row band against the oracle, the whole image through band-tiling consistency

@@ -63,6 +63,17 @@ def test_frame_setup_on_x_axis_is_nan_like_reference():
     assert np.array_equal(np.isnan(fr.view(np.float32).reshape(16)), np.isnan(want))
 
 
+def test_orbit_poses_equal_the_numpy_generator():
+    """birp_orbit_poses (C, fp64 Newton on Kepler's equation) == synthetic.orbit_poses (numpy), bit for bit"""
+    for n in (1, 7, 1000, 10000):
+        got, want = capi.orbit_poses(n), S.orbit_poses(n)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
+    other = capi.orbit_poses(64, perigee=2.5, apogee=12.0, inclination_deg=40.0)
+    assert np.array_equal(other.view(np.uint32), S.orbit_poses(64, 2.5, 12.0, 40.0).view(np.uint32))
+    with pytest.raises(capi.BirpError):
+        capi.orbit_poses(4, perigee=5.0, apogee=1.0)
+
+
 def test_ray_table_matches_oracle():
     for n, m in ((200, 44), (2048, 44), (517, 31), (1, 44), (2, 5)):
         d, w = capi.ray_table(n, m)
