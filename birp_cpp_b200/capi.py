@@ -18,7 +18,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
-DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY = 8, 16, 32, 64, 128, 256, 512
+DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY, CMEM_LIBM64, CMEM_NO_FILTER = 8, 16, 32, 64, 128, 256, 512, 1024, 2048
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -85,6 +85,7 @@ SIGNATURES = {
     "birp_ipc_close": (C.c_int, [_vp]),
     "birp_check_device_status": (C.c_int, [_vp]),
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
+    "birp_selftest_cmem_filter": (C.c_int, [_vp, C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
 }
 
@@ -283,12 +284,22 @@ class Cube:
         return images
 
 
+def _cmem_mode(fast) -> int:
+    """fast: False = default (own fp64 blocks behind the region filter), True = fp32 libdevice calls,
+    "libm64" = CUDA fp64 library, "nofilter" = own fp64 blocks for every sample"""
+    if fast == "libm64":
+        return CMEM_LIBM64
+    if fast == "nofilter":
+        return CMEM_NO_FILTER
+    return CMEM_FAST if fast else 0
+
+
 def render_cmem(params: np.ndarray, frames: np.ndarray, W: int, H: int, nsamples: int = 200, maxdist: int = 44,
                 fast: bool = False, rows=(0, 0), images: np.ndarray | None = None,
                 out: np.ndarray | None = None) -> np.ndarray:
     frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
     params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
-    flags = CMEM_FAST if fast else 0
+    flags = _cmem_mode(fast)
     if images is not None:
         flags |= ACCUMULATE
     elif out is not None:
@@ -306,7 +317,7 @@ def sample_cmem(params: np.ndarray, xyz, fast: bool = False) -> np.ndarray:
     params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
     xyz = _f32(xyz).reshape(-1, 3)
     out = np.empty(len(xyz), dtype=np.float32)
-    _check(lib().birp_sample_cmem(_ptr(params), _ptr(xyz), len(xyz), CMEM_FAST if fast else 0, _ptr(out)))
+    _check(lib().birp_sample_cmem(_ptr(params), _ptr(xyz), len(xyz), _cmem_mode(fast), _ptr(out)))
     return out
 
 
@@ -345,7 +356,7 @@ def render_cmem_device(params: np.ndarray, d_frames: int, nframes: int, W: int, 
                        nsamples=200, maxdist=44, fast=False, rows=(0, 0), accumulate_into=False, d_valid: int = 0,
                        stream: int = 0, frame_offset: int = 0, frame_stride: int = 1) -> None:
     params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
-    flags = (CMEM_FAST if fast else 0) | (ACCUMULATE if accumulate_into else 0)
+    flags = _cmem_mode(fast) | (ACCUMULATE if accumulate_into else 0)
     _check(lib().birp_render_cmem_device_strided(_ptr(params), _vp(d_frames), nframes, W, H, rows[0], rows[1],
                                                  nsamples, maxdist, flags, _vp(d_images), frame_offset, frame_stride,
                                                  _vp(d_valid), _vp(stream)))
@@ -394,9 +405,16 @@ def check_device_status(stream: int = 0) -> None:
 
 
 def selftest_cmem_math(n: int = 1 << 22) -> dict:
-    out = np.zeros(3, dtype=np.float64)
+    out = np.zeros(6, dtype=np.float64)
     _check(lib().birp_selftest_cmem_math(n, _ptr(out)))
-    return dict(zip(("exp2", "log2", "pow"), out.tolist()))
+    return dict(zip(("exp2", "log2", "pow", "exp", "acos", "angle"), out.tolist()))
+
+
+def selftest_cmem_filter(params: np.ndarray, n: int = 1 << 24) -> dict:
+    params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
+    out = np.zeros(3, dtype=np.float64)
+    _check(lib().birp_selftest_cmem_filter(_ptr(params), n, _ptr(out)))
+    return dict(zip(("margin_used_mp", "margin_used_bs", "trusted_fraction"), out.tolist()))
 
 
 def launch_count() -> int:

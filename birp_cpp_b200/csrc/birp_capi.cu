@@ -852,8 +852,8 @@ int birp_check_device_status(void* stream) {
     return read_status(c, (cudaStream_t)stream);
 }
 
-int birp_selftest_cmem_math(long n, double max_rel_err[3]) {
-    if (n <= 0 || !max_rel_err) return set_error(BIRP_ERR_ARG, "bad arguments");
+int birp_selftest_cmem_math(long n, double max_err[6]) {
+    if (n <= 0 || !max_err) return set_error(BIRP_ERR_ARG, "bad arguments");
     DeviceCtx* c;
     int rc = get_ctx(&c);
     if (rc) return rc;
@@ -861,11 +861,32 @@ int birp_selftest_cmem_math(long n, double max_rel_err[3]) {
     rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
     if (rc) return rc;
     unsigned long long* d_err = reinterpret_cast<unsigned long long*>(c->d_scratch);
-    BIRP_CUDA(cudaMemsetAsync(d_err, 0, 3 * sizeof(unsigned long long), c->compute));
+    BIRP_CUDA(cudaMemsetAsync(d_err, 0, 6 * sizeof(unsigned long long), c->compute));
     cudaError_t e = birp::launch_cmem_math_selftest(n, d_err, c->compute);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    BIRP_CUDA(cudaMemcpyAsync(max_rel_err, d_err, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaMemcpyAsync(max_err, d_err, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->compute));
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    return BIRP_OK;
+}
+
+int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out[3]) {
+    if (!params || n <= 0 || !out) return set_error(BIRP_ERR_ARG, "bad arguments");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
+    if (rc) return rc;
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_scratch);
+    BIRP_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), c->compute));
+    cudaError_t e = birp::launch_cmem_filter_selftest(*params, n, d_out, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    unsigned long long h[3];
+    BIRP_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    std::memcpy(&out[0], &h[0], sizeof(double));
+    std::memcpy(&out[1], &h[1], sizeof(double));
+    out[2] = (double)h[2] / (double)n;
     return BIRP_OK;
 }
 

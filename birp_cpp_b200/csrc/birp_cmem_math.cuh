@@ -1,11 +1,16 @@
-// powf for CMEM, evaluated in fp64: x^y = 2^(y * log2 x) with a table-driven log2 and a short
-// exp2, ~2^-47 relative accuracy (checked on the device against the CUDA fp64 library,
-// tests/test_gpu_parity.py::test_cmem_math_accuracy).  CMEM makes 5-6 powf calls per sample; the
-// general-purpose fp64 pow() costs ~250 instructions and exp2(y*log2(x)) through the library ~110,
-// this version ~45 (Taylor coefficients are exact rationals; the only table is 32 x {1/c, -ln(1/c)}).
-// The other transcendental calls of CMEM go through the CUDA fp64 library: hand-written Taylor
-// versions of sincos / exp / acos were measured and were slower (more fp64 operations than the
-// library's minimax polynomials) -- see DESIGN.md.
+// fp64 building blocks of the CMEM kernel (sm_100a): exp, log2, pow, acos and the sin / cos of an
+// angle that is itself a rounded acos.  ~1e-15 accurate, i.e. rounding one of them to fp32 gives the
+// correctly rounded fp32 result except within ~1e-8 of a rounding boundary (checked on the device
+// against the CUDA fp64 library, tests/test_gpu_parity.py::test_cmem_math_accuracy).
+//
+// Why not the CUDA fp64 library: it inlines every polynomial coefficient as a 64-bit immediate, and
+// sm_100 materialises each one with two UMOV / IMAD.MOV instructions in front of the DFMA that uses
+// it -- in the library-based kernel those were 600 of 2800 static instructions (profiles/r1l), and
+// issue slots are what that kernel runs out of.  Here every coefficient sits in __constant__ memory
+// (NOT `const`: a const table is folded back into immediates) and is read by the DFMA itself as a
+// constant-bank operand.  And the geometry of CMEM (theta = acosf(x/r), then sinf / cosf / cosf(theta/2)
+// of that very theta) lets the sines and cosines come from two square roots instead of two sincos
+// evaluations (angle_from_cosine).
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -13,35 +18,52 @@
 namespace birp {
 namespace cm {
 
+// Taylor coefficients 1/11! ... 1/2! of e^r (exact rationals rounded), highest first
+static __constant__ double kExpC[10] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                                        1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0,     0.5};
+// log1p(z) = z - z^2/2 + ... + z^7/7, highest first
+static __constant__ double kLog1pC[6] = {1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -0.5};
+// asin(t) = t + t^3 R(t^2), |t| <= 1/2, R of degree 10 in z = t^2, highest first; max abs error 5.0e-16
+// (tools/gen_cmem_coeffs.py 10: Chebyshev-node interpolant computed with mpmath, error measured in fp64 Horner form)
+static __constant__ double kAsinC[11] = {0x1.c8a4a8d5d7026p-6,  -0x1.bf16e7c9f283cp-8, 0x1.fa1b2b4831188p-7, 0x1.512bc40e88a9ep-7,
+                                         0x1.cf5ed14c7cb7ep-7,  0x1.1c0d74beb3610p-6,  0x1.6e8f34a32a3ecp-6, 0x1.f1c6ff7f5507fp-6,
+                                         0x1.6db6dba99e56dp-5,  0x1.33333333030cfp-4,  0x1.55555555555bbp-3};
+// {ln2 high part (32 trailing zero bits), ln2 low part, log2(e), 1/sqrt(2), pi, pi/2, ln2}
+static __constant__ double kMisc[7] = {0x1.62e42fefa3800p-1, 0x1.ef35793c76730p-45, 1.44269504088896338700e+00,
+                                       0.70710678118654752440, 3.14159265358979323846, 1.57079632679489661923,
+                                       6.93147180559945286227e-01};
+
 // ---- exp / exp2 --------------------------------------------------------------------------------
-// e^r for |r| <= ln2/2, Taylor to r^11: truncation < 2^-47
+// e^r for |r| <= ln2/2, Taylor to r^11: truncation < 2^-47 relative... (r^12/12! <= 6.3e-15)
 __device__ __forceinline__ double expm_core(double r) {
-    double p = 1.0 / 39916800.0;           // 1/11!
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
+    double p = kExpC[0];
+#pragma unroll
+    for (int k = 1; k < 10; ++k) p = fma(p, r, kExpC[k]);
     p = fma(p, r, 1.0);
     return fma(p, r, 1.0);
 }
 
-// multiply by 2^k for |k| <= 1000 (two steps keep every factor a normal number)
+// v * 2^k for v in [0.5, 2) and |k| <= 1000: one integer add on the exponent field
 __device__ __forceinline__ double scale2(double v, int k) {
-    const int k1 = k / 2, k2 = k - k1;
-    const double f1 = __hiloint2double((1023 + k1) << 20, 0);
-    const double f2 = __hiloint2double((1023 + k2) << 20, 0);
-    return v * f1 * f2;
+    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
 
+static __device__ __noinline__ double exp2_slow(double t) { return exp2(t); }
+static __device__ __noinline__ double exp_slow(double x) { return exp(x); }
+
 __device__ __forceinline__ double exp2_d(double t) {
-    if (!(fabs(t) < 1000.0)) return exp2(t);
+    if (!(fabs(t) < 1000.0)) return exp2_slow(t);
     const double kd = rint(t);
-    const double r = (t - kd) * 6.93147180559945286227e-01;  // exact difference, |r| <= ln2/2
+    const double r = (t - kd) * kMisc[6];  // exact difference, |r| <= ln2/2
+    return scale2(expm_core(r), (int)kd);
+}
+
+// e^x: Cody-Waite reduction x = k ln2 + r with ln2 split in two, so r carries no argument-size error
+__device__ __forceinline__ double exp_d(double x) {
+    if (!(fabs(x) < 690.0)) return exp_slow(x);
+    const double kd = rint(x * kMisc[2]);
+    double r = fma(-kd, kMisc[0], x);
+    r = fma(-kd, kMisc[1], r);
     return scale2(expm_core(r), (int)kd);
 }
 
@@ -92,18 +114,68 @@ __device__ __forceinline__ double log2_d(double x) {
     const double2 t = kLogTab[idx];
     const double z = fma(m, t.x, -1.0);
     // log1p(z), alternating Taylor series to z^7: truncation < 2^-51
-    double p = 1.0 / 7.0;
-    p = fma(p, z, -1.0 / 6.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, -1.0 / 4.0);
-    p = fma(p, z, 1.0 / 3.0);
-    p = fma(p, z, -0.5);
+    double p = kLog1pC[0];
+#pragma unroll
+    for (int k = 1; k < 6; ++k) p = fma(p, z, kLog1pC[k]);
     const double ln_m = fma(p * z, z, z) + t.y;
-    return fma(ln_m, 1.44269504088896338700e+00, (double)e);
+    return fma(ln_m, kMisc[2], (double)e);
 }
 
 // x^y for finite x > 0 (other bases: the caller keeps powf's special cases through pow())
 __device__ __forceinline__ double pow_pos_d(double x, double y) { return exp2_d(y * log2_d(x)); }
+static __device__ __noinline__ double pow_slow(double x, double y) { return pow(x, y); }
+
+// ---- acos and the angle bundle ------------------------------------------------------------------
+// asin(t) for |t| <= 1/2
+__device__ __forceinline__ double asin_core(double t) {
+    const double z = t * t;
+    double p = kAsinC[0];
+#pragma unroll
+    for (int k = 1; k < 11; ++k) p = fma(p, z, kAsinC[k]);
+    return fma(t * z, p, t);
+}
+
+// acos(x) for any double x (NaN outside [-1,1], like the library):
+//   |x| < 1/2:  pi/2 - asin(x);   x >= 1/2:  2 asin(sqrt((1-x)/2));   x <= -1/2:  pi - 2 asin(sqrt((1+x)/2))
+__device__ __forceinline__ double acos_d(double x) {
+    const double ax = fabs(x);
+    if (ax < 0.5) return kMisc[5] - asin_core(x);
+    const double t = 2.0 * asin_core(sqrt((1.0 - ax) * 0.5));
+    return x > 0.0 ? t : kMisc[4] - t;
+}
+
+// Everything CMEM needs of an angle a = RN32(acos(q)), q an fp32 cosine (src/Cmem.cpp:224-246 then
+// :196-216): the fp32 angle itself and, in fp64, sin(a), cos(a), cos(a/2) of THAT rounded angle.
+// With A = sqrt(1+q), B = sqrt(1-q) (1 +- q are exact in fp64):  sin(acos q) = A B,
+// cos(acos(q)/2) = A / sqrt2, sin(acos(q)/2) = B / sqrt2, and acos(q) itself is 2 asin(B / sqrt2)
+// (or pi - 2 asin(A / sqrt2), or pi/2 - asin(q)).  The rounded angle differs from acos(q) by
+// d = a - acos(q), |d| <= 1.2e-7, so   cos a = q cos d - AB sin d,   sin a = AB cos d + q sin d,
+// cos(a/2) = (A cos(d/2) - B sin(d/2)) / sqrt2   with cos d = 1 - d^2/2, sin d = d (next terms < 1e-21).
+// Two square roots and one asin polynomial replace acos + sincos + cos.
+struct Angle {
+    float a;        // RN32(acos(q))
+    double s, c;    // sin(a), cos(a)
+    double c_half;  // cos(a / 2)
+};
+
+__device__ __forceinline__ Angle angle_from_cosine(float qf) {
+    const double q = (double)qf;
+    const double A = sqrt(1.0 + q), B = sqrt(1.0 - q);
+    const double aq = fabs(q);
+    // one asin_core for all three ranges
+    const double t = (aq < 0.5) ? q : ((q > 0.0 ? B : A) * kMisc[3]);
+    const double as = asin_core(t);
+    const double acq = (aq < 0.5) ? (kMisc[5] - as) : (q > 0.0 ? 2.0 * as : fma(-2.0, as, kMisc[4]));
+    Angle r;
+    r.a = (float)acq;
+    const double d = (double)r.a - acq;
+    const double h = 0.5 * d * d;
+    const double sq = A * B;
+    r.c = fma(-q, h, fma(-sq, d, q));
+    r.s = fma(-sq, h, fma(q, d, sq));
+    r.c_half = fma(-B, 0.5 * d, fma(-A, 0.25 * h, A)) * kMisc[3];
+    return r;
+}
 
 }  // namespace cm
 }  // namespace birp

@@ -479,4 +479,191 @@ __device__ __forceinline__ float cmem_sample(const CmemDev& D, float x, float y,
     return b2;
 }
 
+// ---------------------------------------------------------------------------------
+// CMEM::GetSample once more, the default: the same "fp64, rounded once to fp32" evaluation of every
+// libm call as cmem_sample<true>, with the building blocks of birp_cmem_math.cuh instead of the CUDA
+// fp64 library -- coefficients read from the constant bank, and the sines / cosines of theta and phi
+// taken from the square roots the two acos evaluations need anyway (cm::angle_from_cosine).  Types
+// and operation order between the calls are the reference's, as above.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float pow32(float x, float y) {
+    if (x > 0.f && x < CUDART_INF_F) return (float)cm::pow_pos_d((double)x, (double)y);
+    return (float)cm::pow_slow((double)x, (double)y);  // zero, negative, infinite, NaN bases: powf's special cases
+}
+
+// the cosines ShueCoords takes its angles from: theta = acosf(q_t) (or 0 when x == 0: acos(1) = 0 gives the
+// same angle), phi = acosf(q_p) (or 0 when y == 0); src/Cmem.cpp:224-246
+__device__ __forceinline__ void cmem_cosines(float x, float y, float z, float& r, float& q_t, float& q_p) {
+    r = vec_len3(x, y, z);
+    q_t = (x != 0.f) ? __fdiv_rn(x, r) : 1.f;
+    q_p = (y != 0.f) ? __fdiv_rn(y, __fsqrt_rn(__fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z)))) : 1.f;
+}
+
+// b1 of src/Cmem.cpp:155-160: the magnetosheath emissivity, from the rounded theta and its fp32 sine
+__device__ __forceinline__ float cmem_b1(const birp_cmem_params& P, float r, float theta, float sin_t) {
+    const float h = __fdiv_rn(theta, 2.f);
+    const float h4 = __fmul_rn(__fmul_rn(__fmul_rn(h, h), h), h);
+    const float e = (float)cm::exp_d((double)__fmul_rn(-P.B, h4));
+    const float pw = pow32(__fdiv_rn(r, 10.f), __fsub_rn(-P.alpha, __fmul_rn(P.beta, __fmul_rn(sin_t, sin_t))));
+    return __fmul_rn(__fmul_rn(P.A1, e), pw);
+}
+
+// b2 of src/Cmem.cpp:162-173: beyond the magnetosheath, computed in double from the fp32 quotient r/10
+__device__ __forceinline__ float cmem_b2(const birp_cmem_params& P, float r) {
+    const double sd = (double)__fdiv_rn(r, 10.f);
+    const double cube = __dmul_rn(__dmul_rn(sd, sd), sd);
+    return __double2float_rn(__dmul_rn((double)P.A2, __ddiv_rn(1.0, cube)));
+}
+
+// magnetopause (LinScaled, :188-222) and bow-shock (ShueModel, :280-288) radii in the sample's direction
+__device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float q_p, float& theta, float& sin_t,
+                                              float& radius_mp, float& radius_bs) {
+    const birp_cmem_params& P = D.P;
+    const cm::Angle T = cm::angle_from_cosine(q_t);
+    const cm::Angle F = cm::angle_from_cosine(q_p);
+    theta = T.a;
+    sin_t = (float)T.s;
+    const float cos_t = (float)T.c;
+    // sinf(2 theta): 2 theta is exact in fp32 and sin 2a = 2 sin a cos a
+    const float sin_2t = (float)(2.0 * T.s * T.c);
+    const float sin_p = (float)F.s, cos_p = (float)F.c;
+
+    // cos(phi - pi/2) = sin(phi) and cos(phi - 3pi/2) = -sin(phi): the reference evaluates both in fp64
+    // (they agree with these to ~1e-16), as well as the outer acos
+    const double c_n = F.s, c_s = -F.s;
+    const float phi_n = (float)cm::acos_d(
+        __dadd_rn((double)__fmul_rn(cos_t, D.cos_tn), __dmul_rn((double)__fmul_rn(sin_t, D.sin_tn), c_n)));
+    const float phi_s = (float)cm::acos_d(
+        __dadd_rn((double)__fmul_rn(cos_t, D.cos_ts), __dmul_rn((double)__fmul_rn(sin_t, D.sin_ts), c_s)));
+
+    const float fbase = __fadd_rn((float)T.c_half,  // cosf(theta / 2): theta / 2 is exact in fp32
+                                  __fmul_rn(__fmul_rn(P.a5, sin_2t), __fsub_rn(1.f, (float)cm::exp_d(-(double)theta))));
+    const float fexp = __fmul_rn(
+        P.p1, __fadd_rn(__fadd_rn(P.beta_c[0], __fmul_rn(P.beta_c[1], cos_p)),
+                        __fmul_rn(P.beta_c[3], __fmul_rn(sin_p, sin_p))));
+    const float f = pow32(fbase, fexp);
+    const float p2c = D.p2c;
+    const float q = __fadd_rn(__fmul_rn(p2c, (float)cm::exp_d((double)__fmul_rn(D.p3dn, pow32(phi_n, P.a21)))),
+                              __fmul_rn(p2c, (float)cm::exp_d((double)__fmul_rn(D.p3ds, pow32(phi_s, P.a21)))));
+    radius_mp = __fadd_rn(__fmul_rn(D.p0r0, f), q);
+
+    const float sbase = __fdiv_rn(2.f, __fadd_rn(1.f, cos_t));
+    const float ry = __fmul_rn(P.bs, pow32(sbase, P.ay_bs));
+    const float rz = D.same_flare ? ry : __fmul_rn(P.bs, pow32(sbase, P.az_bs));
+    const float rzc = __fmul_rn(rz, cos_p);
+    const float rys = __fmul_rn(ry, sin_p);
+    radius_bs = __fdiv_rn(__fmul_rn(ry, rz), __fsqrt_rn(__fadd_rn(__fmul_rn(rzc, rzc), __fmul_rn(rys, rys))));
+}
+
+#define BIRP_CMEM_HALF_THICKNESS 0.025f /* 0.05f / 2, src/Cmem.cpp:133 */
+
+// the five regions of CMEM::GetSample (:135-176) for known radii
+__device__ __forceinline__ float cmem_regions(const birp_cmem_params& P, float r, float theta, float sin_t,
+                                              float radius_mp, float radius_bs) {
+    const float half_thickness = BIRP_CMEM_HALF_THICKNESS;
+    const float mp_lo = __fsub_rn(radius_mp, half_thickness), mp_hi = __fadd_rn(radius_mp, half_thickness);
+    const float bs_lo = __fsub_rn(radius_bs, half_thickness), bs_hi = __fadd_rn(radius_bs, half_thickness);
+
+    if (r < mp_lo) return 0.f;
+
+    const bool in_mp_layer = (r >= mp_lo && r <= mp_hi);
+    const bool in_sheath = (r > mp_hi && r < bs_lo);
+    const bool in_bs_layer = (r >= bs_lo && r <= bs_hi);
+
+    float b1 = 0.f;
+    if (in_mp_layer || in_sheath || in_bs_layer) b1 = cmem_b1(P, r, theta, sin_t);
+    if (in_mp_layer) {
+        const float shue_norm = __fdiv_rn(__fsub_rn(r, mp_lo), mp_hi);
+        return lerp_ref(0.f, b1, shue_norm);
+    }
+    if (in_sheath) return b1;
+    const float b2 = cmem_b2(P, r);
+    if (in_bs_layer) {
+        const float shue_norm = __fdiv_rn(__fsub_rn(r, bs_lo), bs_hi);
+        return lerp_ref(b1, b2, shue_norm);
+    }
+    return b2;
+}
+
+__device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float y, float z) {
+    float r, q_t, q_p, theta, sin_t, radius_mp, radius_bs;
+    cmem_cosines(x, y, z, r, q_t, q_p);
+    cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
+    return cmem_regions(D.P, r, theta, sin_t, radius_mp, radius_bs);
+}
+
+// ---------------------------------------------------------------------------------
+// Region filter.  Three samples in four lie well inside the magnetopause (emissivity 0) or well beyond
+// the bow shock (emissivity A2 / (r/10)^3, a function of r alone), and the rest mostly in the open
+// magnetosheath, whose emissivity needs theta but neither radius.  WHICH region a sample is in follows
+// from comparing r with the two radii -- and away from the boundaries a cheap fp32 estimate of the radii
+// (hardware exp2 / log2 / rsqrt approximations, ~1e-6 relative) decides that with certainty: if r clears
+// a boundary by more than the estimate can possibly be off (BIRP_CMEM_MARGIN_*, more than 20x the largest deviation found
+// by the device self-test over 10^8 directions, tests/test_gpu_parity.py::test_cmem_filter_margin), the
+// exact evaluation would take the same branch, so its result is reproduced bit for bit at a fraction of
+// the cost.  Everything else -- within the margin of a boundary, directions where the estimate is
+// ill-conditioned (near the -x axis, near a cusp), NaNs -- takes the full evaluation.
+// ---------------------------------------------------------------------------------
+#define BIRP_CMEM_MARGIN_REL 5e-3f
+#define BIRP_CMEM_MARGIN_ABS 5e-3f
+
+// fp32 estimates of the two radii; false when the direction is one where the estimate is not trusted
+__device__ __forceinline__ bool cmem_radii_estimate(const CmemDev& D, float q_t, float q_p, float& radius_mp,
+                                                    float& radius_bs) {
+    const birp_cmem_params& P = D.P;
+    const float cos_t = q_t, cos_p = q_p;  // cos(acos q) = q
+    const float sin_t = sqrtf((1.f - q_t) * (1.f + q_t));
+    const float sin_p = sqrtf((1.f - q_p) * (1.f + q_p));
+    const float theta = acosf(q_t);
+    const float arg_n = cos_t * D.cos_tn + sin_t * D.sin_tn * sin_p;
+    const float arg_s = cos_t * D.cos_ts - sin_t * D.sin_ts * sin_p;
+    const float fbase = sqrtf(0.5f * (1.f + q_t)) + P.a5 * (2.f * sin_t * cos_t) * (1.f - __expf(-theta));
+    // ill-conditioned directions: 1 + cos(theta) -> 0 (both radii blow up), acos near +-1 (cusps)
+    const bool trusted = (1.f + q_t > 0.02f) && (fabsf(arg_n) < 0.9995f) && (fabsf(arg_s) < 0.9995f) && (fbase > 0.05f);
+    const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * cos_p + P.beta_c[3] * sin_p * sin_p);
+    const float f = __powf(fbase, fexp);
+    const float phi_n = acosf(arg_n), phi_s = acosf(arg_s);
+    const float q = D.p2c * (__expf(D.p3dn * __powf(phi_n, P.a21)) + __expf(D.p3ds * __powf(phi_s, P.a21)));
+    radius_mp = D.p0r0 * f + q;
+    const float sbase = 2.f / (1.f + cos_t);
+    const float ry = P.bs * __powf(sbase, P.ay_bs);
+    const float rz = P.bs * __powf(sbase, P.az_bs);
+    const float rzc = rz * cos_p, rys = ry * sin_p;
+    radius_bs = ry * rz * rsqrtf(rzc * rzc + rys * rys);
+    return trusted;
+}
+
+template <bool FILTER>
+__device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
+    float r, q_t, q_p;
+    cmem_cosines(x, y, z, r, q_t, q_p);
+    if (FILTER) {
+        float mp, bs;
+        const bool trusted = cmem_radii_estimate(D, q_t, q_p, mp, bs);
+        const float ht = BIRP_CMEM_HALF_THICKNESS;
+        const float m_mp = BIRP_CMEM_MARGIN_REL * fabsf(mp) + BIRP_CMEM_MARGIN_ABS;
+        const float m_bs = BIRP_CMEM_MARGIN_REL * fabsf(bs) + BIRP_CMEM_MARGIN_ABS;
+        // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
+        if (trusted && r < mp - ht - m_mp) return 0.f;                       // certainly r < mp_lo
+        const bool above_mp = trusted && r > mp + ht + m_mp;                 // certainly r > mp_hi
+        if (above_mp && r > bs + ht + m_bs) return cmem_b2(D.P, r);          // certainly r > bs_hi: not sheath, not layer
+        if (above_mp && r < bs - ht - m_bs) {                                // certainly mp_hi < r < bs_lo: sheath
+            const cm::Angle T = cm::angle_from_cosine(q_t);
+            return cmem_b1(D.P, r, T.a, (float)T.s);
+        }
+    }
+    float theta, sin_t, radius_mp, radius_bs;
+    cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
+    return cmem_regions(D.P, r, theta, sin_t, radius_mp, radius_bs);
+}
+
+// CMEM evaluation mode: 0 fp32 libdevice calls, 1 CUDA fp64 library rounded once, 2 own fp64 blocks,
+// 3 (default) own fp64 blocks behind the region filter
+template <int MODE>
+__device__ __forceinline__ float cmem_sample_mode(const CmemDev& D, float x, float y, float z) {
+    if (MODE == 3) return cmem_sample_v5<true>(D, x, y, z);
+    if (MODE == 2) return cmem_sample_v4(D, x, y, z);
+    return cmem_sample<MODE == 1>(D, x, y, z);
+}
+
 }  // namespace birp

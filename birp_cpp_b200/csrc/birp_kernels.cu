@@ -50,11 +50,11 @@ struct MarchArgs {
     long long out_offset, out_stride;
 };
 
-template <bool PRECISE>
+template <int MODE>  // 0 fp32 libdevice, 1 CUDA fp64 library, 2 own fp64 blocks, 3 + region filter (cmem_sample_mode)
 struct CmemField {
     CmemDev D;
     __device__ __forceinline__ float operator()(float x, float y, float z, bool&) const {
-        return cmem_sample<PRECISE>(D, x, y, z);
+        return cmem_sample_mode<MODE>(D, x, y, z);
     }
 };
 
@@ -540,12 +540,12 @@ __global__ void __launch_bounds__(256) sample_cube_kernel(const CubeView c, cons
     if (nan_index) atomicOr(status, kStatusNanIndex);
 }
 
-template <bool PRECISE>
+template <int MODE>
 __global__ void __launch_bounds__(256) sample_cmem_kernel(const CmemDev D, const float* __restrict__ xyz, long n,
                                                           float* __restrict__ out) {
     const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    out[p] = cmem_sample<PRECISE>(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2]);
+    out[p] = cmem_sample_mode<MODE>(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2]);
 }
 
 __global__ void __launch_bounds__(256) ray_directions_kernel(const birp_frame* __restrict__ frame, int W, int H,
@@ -559,8 +559,10 @@ __global__ void __launch_bounds__(256) ray_directions_kernel(const birp_frame* _
     dirs[3 * p + 2] = dz;
 }
 
-// max relative error of the birp::cm fp64 routines against the CUDA fp64 library on pseudo-random
-// arguments from CMEM's ranges; err[3] = {exp2, log2, pow} (double bit patterns reduced with atomicMax)
+// max error of the birp::cm fp64 routines against the CUDA fp64 library on pseudo-random arguments from
+// CMEM's ranges; err[6] = {exp2, log2, pow, exp (relative), acos (absolute), angle bundle (absolute: sin, cos,
+// cos(a/2) of the rounded angle, and how far the fp32 angle is from a correct rounding of acos)}
+// (double bit patterns reduced with atomicMax)
 __global__ void __launch_bounds__(256) cmem_math_selftest_kernel(long n, unsigned long long* err) {
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(256) cmem_math_selftest_kernel(long n, unsigne
         const double d = fabs(got - want);
         return want != 0.0 ? d / fabs(want) : d;
     };
-    double e[3];
+    double e[6];
     const double x = (next01() - 0.5) * 250.0;  // [-125, 125]
     e[0] = rel(cm::exp2_d(x), exp2(x));
     const double p = exp2((next01() - 0.5) * 250.0);
@@ -585,8 +587,65 @@ __global__ void __launch_bounds__(256) cmem_math_selftest_kernel(long n, unsigne
     const double y = (next01() - 0.5) * 8.0;
     const double base = exp2((next01() - 0.5) * 24.0);
     e[2] = rel(cm::pow_pos_d(base, y), pow(base, y));
+    const double xe = (next01() - 0.5) * 80.0;  // [-40, 40]
+    e[3] = rel(cm::exp_d(xe), exp(xe));
+    // acos on [-1, 1], with extra weight on the ends and on the +-1/2 seams
+    double u = 2.0 * next01() - 1.0;
+    const unsigned pick = h & 7u;
+    if (pick == 0) u = 1.0 - next01() * 1e-6;
+    if (pick == 1) u = -1.0 + next01() * 1e-6;
+    if (pick == 2) u = 0.5 + (next01() - 0.5) * 1e-6;
+    if (pick == 3) u = -0.5 + (next01() - 0.5) * 1e-6;
+    e[4] = fabs(cm::acos_d(u) - acos(u));
+    const float qf = (float)u;
+    const cm::Angle A = cm::angle_from_cosine(qf);
+    const double a = (double)A.a, want_a = acos((double)qf);
+    const double ulp = (double)__uint_as_float(__float_as_uint(fmaxf(A.a, 1e-30f)) + 1u) - (double)fmaxf(A.a, 1e-30f);
+    double ea = fmax(fabs(A.s - sin(a)), fabs(A.c - cos(a)));
+    ea = fmax(ea, fabs(A.c_half - cos(0.5 * a)));
+    ea = fmax(ea, fmax(0.0, fabs(a - want_a) - 0.5 * ulp));
+    e[5] = ea;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) atomicMax(err + k, (unsigned long long)__double_as_longlong(e[k]));
+    for (int k = 0; k < 6; ++k) atomicMax(err + k, (unsigned long long)__double_as_longlong(e[k]));
+}
+
+// How much of the region filter's margin do the fp32 radius estimates actually use?  n pseudo-random sample
+// positions (a box of +-35 RE, plus positions squeezed towards the planes / axes where an angle degenerates):
+// out[0] / out[1] = max over the trusted directions of |estimate - exact| / margin for the magnetopause / the
+// bow-shock radius, out[2] = fraction of positions whose direction is trusted (double bit patterns, atomicMax;
+// out[2] accumulates a count)
+__global__ void __launch_bounds__(256) cmem_filter_selftest_kernel(const CmemDev D, long n, unsigned long long* out) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    unsigned h = (unsigned)t * 2654435761u + 12345u;
+    auto next01 = [&]() {
+        h ^= h >> 16;
+        h *= 0x85ebca6bu;
+        h ^= h >> 13;
+        h *= 0xc2b2ae35u;
+        h ^= h >> 16;
+        return (float)h * (1.0f / 4294967296.0f);
+    };
+    float x = (next01() - 0.5f) * 70.f, y = (next01() - 0.5f) * 70.f, z = (next01() - 0.5f) * 70.f;
+    const unsigned pick = h & 15u;  // squeeze some positions towards degenerate directions
+    const float tiny = exp2f(-20.f * next01());
+    if (pick == 0) y *= tiny;
+    if (pick == 1) z *= tiny;
+    if (pick == 2) x *= tiny;
+    if (pick == 3) y *= tiny, z *= tiny;
+    if (pick == 4) x = -fabsf(x), y *= 0.2f * tiny, z *= 0.2f * tiny;  // around the -x axis guard
+    float r, q_t, q_p;
+    cmem_cosines(x, y, z, r, q_t, q_p);
+    float mp_e, bs_e;
+    if (!cmem_radii_estimate(D, q_t, q_p, mp_e, bs_e)) return;
+    float theta, sin_t, mp, bs;
+    cmem_radii_v4(D, q_t, q_p, theta, sin_t, mp, bs);
+    const double u_mp = fabs((double)mp_e - (double)mp) / (double)(BIRP_CMEM_MARGIN_REL * fabsf(mp_e) + BIRP_CMEM_MARGIN_ABS);
+    const double u_bs = fabs((double)bs_e - (double)bs) / (double)(BIRP_CMEM_MARGIN_REL * fabsf(bs_e) + BIRP_CMEM_MARGIN_ABS);
+    // a NaN on either side would make the filter's comparisons false (full evaluation); count it as unused margin
+    if (u_mp == u_mp) atomicMax(out + 0, (unsigned long long)__double_as_longlong(u_mp));
+    if (u_bs == u_bs) atomicMax(out + 1, (unsigned long long)__double_as_longlong(u_bs));
+    atomicAdd(out + 2, 1ull);
 }
 
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -664,10 +723,18 @@ cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame*
                                const RenderGeom& g, const float* d_dist, int flags, float* d_images,
                                unsigned long long* d_valid, cudaStream_t stream) {
     if (flags & BIRP_CMEM_FAST) {
-        CmemField<false> f{make_cmem_dev(params)};
+        CmemField<0> f{make_cmem_dev(params)};
         return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
     }
-    CmemField<true> f{make_cmem_dev(params)};
+    if (flags & BIRP_CMEM_LIBM64) {
+        CmemField<1> f{make_cmem_dev(params)};
+        return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
+    }
+    if (flags & BIRP_CMEM_NO_FILTER) {
+        CmemField<2> f{make_cmem_dev(params)};
+        return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
+    }
+    CmemField<3> f{make_cmem_dev(params)};
     return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
 }
 
@@ -703,6 +770,13 @@ cudaError_t launch_cmem_math_selftest(long n, unsigned long long* d_err6, cudaSt
     return cudaGetLastError();
 }
 
+cudaError_t launch_cmem_filter_selftest(const birp_cmem_params& params, long n, unsigned long long* d_out3,
+                                        cudaStream_t stream) {
+    cmem_filter_selftest_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(make_cmem_dev(params), n, d_out3);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream) {
     ray_directions_kernel<<<blocks_for((long)W * H, 256), 256, 0, stream>>>(d_frame, W, H, d_dirs);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -725,9 +799,13 @@ cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xy
     if (n <= 0) return cudaSuccess;
     const CmemDev D = make_cmem_dev(params);
     if (flags & BIRP_CMEM_FAST)
-        sample_cmem_kernel<false><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
+        sample_cmem_kernel<0><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
+    else if (flags & BIRP_CMEM_LIBM64)
+        sample_cmem_kernel<1><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
+    else if (flags & BIRP_CMEM_NO_FILTER)
+        sample_cmem_kernel<2><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
     else
-        sample_cmem_kernel<true><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
+        sample_cmem_kernel<3><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

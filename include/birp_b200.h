@@ -63,7 +63,13 @@ enum {
     BIRP_TEXTURE_ONLY = 128, /* all eight corners with two texture gathers */
     BIRP_NO_QUADS = 256,     /* do not use the quad copy (lower layer: one texture gather, upper layer:
                                 four global loads; with BIRP_NO_TEXTURE: eight global loads) */
-    BIRP_QUADS_ONLY = 512    /* (the default when the quad copy exists; kept for explicit A/B runs) */
+    BIRP_QUADS_ONLY = 512,   /* (the default when the quad copy exists; kept for explicit A/B runs) */
+    BIRP_CMEM_LIBM64 = 1024, /* CMEM only: the fp64-then-round evaluation through the CUDA fp64 math library
+                                instead of the library's own fp64 blocks (same results but for ~1e-8 of the
+                                calls; slower; kept as the cross-check of those blocks) */
+    BIRP_CMEM_NO_FILTER = 2048 /* CMEM only: evaluate both radii exactly for every sample instead of deciding
+                                  the region of samples far from a boundary with fp32 estimates (identical
+                                  results; kept as the cross-check of the filter) */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */
@@ -206,9 +212,15 @@ int birp_ipc_close(void* d_ptr);
    by *_device launches); synchronises `stream`, returns BIRP_OK or the error and clears it */
 int birp_check_device_status(void* stream);
 
-/* diagnostics: max relative error of the library's own fp64 exp2 / log2 / pow
-   (used by the CMEM kernel) against the CUDA fp64 math library on n pseudo-random arguments */
-int birp_selftest_cmem_math(long n, double max_rel_err[3]);
+/* diagnostics: max error of the library's own fp64 exp2 / log2 / pow / exp (relative), acos and the
+   angle bundle sin, cos, cos(a/2) (absolute) -- the blocks of the CMEM kernel -- against the CUDA fp64
+   math library on n pseudo-random arguments */
+int birp_selftest_cmem_math(long n, double max_err[6]);
+
+/* diagnostics of the CMEM region filter: out[0] / out[1] = the largest fraction of the filter's margin that
+   the fp32 estimate of the magnetopause / bow-shock radius was off by, over n pseudo-random sample positions
+   (must stay far below 1), out[2] = fraction of the positions whose direction the filter trusts */
+int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out[3]);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long birp_launch_count(void);

@@ -18,6 +18,36 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
+def time_cmem(args, capi, S, torch, dev, stream, sptr):
+    W, H = S.SXI_W, S.SXI_H
+    poses = S.orbit_poses(args.frames)
+    frames = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    d_frames = torch.from_numpy(frames.view(np.float32).reshape(-1, 16).copy()).to(dev)
+    d_img = torch.zeros((len(poses), H, W), dtype=torch.float32, device=dev)
+    P = capi.cmem_init()
+    out = {"workload": "cmem", "frames": len(poses)}
+    ref = None
+    for fl in [int(x) for x in args.flags.split(",")]:
+        mode = {capi.CMEM_FAST: True, capi.CMEM_LIBM64: "libm64", capi.CMEM_NO_FILTER: "nofilter"}.get(fl, False)
+        ms = []
+        for it in range(args.steps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            capi.render_cmem_device(P, d_frames.data_ptr(), len(poses), W, H, d_img.data_ptr(), stream=sptr, fast=mode)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if it >= 1:
+                ms.append(e0.elapsed_time(e1))
+        img = d_img.clone()
+        if ref is None:
+            ref = img
+        rel = ((img - ref).abs() <= 1e-5 * ref.abs().clamp_min(1e-5 * float(ref.max()))).float().mean().item()
+        out[f"flags_{fl}"] = {"ms_min": round(min(ms), 3), "frames_per_s": round(len(poses) / (min(ms) * 1e-3), 1),
+                              "pixels_within_1e-5_of_first": rel,
+                              "bit_identical_to_first": float((img.view(torch.int32) == ref.view(torch.int32)).float().mean())}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="orbit")
@@ -34,6 +64,8 @@ def main():
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     tri = args.workload != "nearest"
+    if args.workload == "cmem":
+        return time_cmem(args, capi, S, torch, dev, stream, sptr)
     if args.workload in ("orbit", "nearest"):
         n, W, H, fw, fh, ns = 256, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200
         poses = S.orbit_poses(args.frames)
