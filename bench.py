@@ -41,6 +41,18 @@ from birp_cpp_b200 import synthetic as S  # noqa: E402
 NSAMPLES, MAXDIST = 200, 44
 EXTRA_FLAGS = 0
 
+
+def cmem_mode():
+    """--extra-flags -> the `fast` argument of the capi CMEM calls (False = default: own fp64 blocks + region filter)"""
+    from birp_cpp_b200 import capi
+    if EXTRA_FLAGS & capi.CMEM_FAST:
+        return True
+    if EXTRA_FLAGS & capi.CMEM_LIBM64:
+        return "libm64"
+    if EXTRA_FLAGS & capi.CMEM_NO_FILTER:
+        return "nofilter"
+    return False
+
 WORKLOADS = {
     # name: (description, cube n, W, H, fov_w, fov_h, nsamples, frames, field)
     "orbit": ("orbit sweep: 10000 SMILE-orbit poses, SXI 64x108 rays x 200 trilinear samples, synthetic 256^3 cube",
@@ -361,7 +373,7 @@ def run_b200(args, wl, name):
         else:
             capi.render_cmem_device(params, fr_ptr, hi - lo, W, H, img_ptr, nsamples=nsamples,
                                     maxdist=MAXDIST, rows=rows, d_valid=valid_ptr, stream=sptr,
-                                    fast=bool(EXTRA_FLAGS & capi.CMEM_FAST), frame_offset=off, frame_stride=stride)
+                                    fast=cmem_mode(), frame_offset=off, frame_stride=stride)
 
     def render_and_gather():
         """one step of the job: render this rank's share, images to rank 0 (N > 1)"""
@@ -465,7 +477,7 @@ def run_b200(args, wl, name):
                 else:
                     capi.render_cmem_device(params, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(),
                                             nsamples=nsamples, maxdist=MAXDIST, stream=sptr,
-                                            fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+                                            fast=cmem_mode())
                 torch.cuda.synchronize()
                 same = bool(torch.equal(full[torch.from_numpy(probe).to(dev)], d_pi))
                 gather_check = {"frames_compared": int(len(probe)), "identical_to_single_gpu_render": same}
@@ -492,7 +504,7 @@ def run_b200(args, wl, name):
                         out=h_images.array)
         else:
             capi.render_cmem(params, h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, rows=rows,
-                             out=h_images.array, fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+                             out=h_images.array, fast=cmem_mode())
 
     for _ in range(2):
         e2e_step()
@@ -521,7 +533,7 @@ def run_b200(args, wl, name):
                 cube.render(fr, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, out=one_img)
             else:
                 capi.render_cmem(params, fr, W, H, nsamples=nsamples, maxdist=MAXDIST, out=one_img,
-                                 fast=bool(EXTRA_FLAGS & capi.CMEM_FAST))
+                                 fast=cmem_mode())
 
         for _ in range(5):
             one_frame()
@@ -529,6 +541,31 @@ def run_b200(args, wl, name):
         for _ in range(50):
             one_frame()
         latency_ms = (time.perf_counter() - t0) / 50 * 1e3
+
+    # ---- sweep set-up without the host: orbit poses and frame records made on the device
+    device_setup = None
+    if rank == 0 and nframes > 1:
+        d_poses = torch.empty((nframes, 3), dtype=torch.float32, device=dev)
+        d_fr2 = torch.empty((nframes, 16), dtype=torch.float32, device=dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(3):
+            if it == 2:
+                s0.record(stream)
+            capi.orbit_poses_device(nframes, d_poses.data_ptr(), stream=sptr)
+            capi.frame_setup_device(d_poses.data_ptr(), nframes, S.DEFAULT_AIM_X, fov_w, fov_h, W, H, d_fr2.data_ptr(),
+                                    stream=sptr)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        capi.check_device_status(sptr)
+        t0 = time.perf_counter()
+        capi.frames_for_poses(capi.orbit_poses(nframes), S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
+        host_ms = (time.perf_counter() - t0) * 1e3
+        same = (d_fr2.cpu().numpy().view(np.uint32) == frames_all.view(np.uint32).reshape(-1, 16)).all(axis=1).mean()
+        device_setup = {"ms": s0.elapsed_time(s1), "host_ms": host_ms, "frames": nframes,
+                        "records_bit_identical_to_host": float(same),
+                        "note": "birp_orbit_poses_device + birp_frame_setup_device (two kernels) against the threaded "
+                                "host path; the device rounds fp64 results once, glibc's fp32 atan2f/acosf/asinf are "
+                                "not correctly rounded, hence the differing records (<= 2.2e-6 in a rotation entry)"}
 
     # ---- rank 0: CPU baseline on a bounded sample + parity of the same frames, then the JSON line
     if rank == 0:
@@ -594,7 +631,10 @@ def run_b200(args, wl, name):
             "config": dict(workload_config(wl, name, world),
                            l2="flushed between timed steps (256 MiB memset, untimed)",
                            cube_analysis=cube.info() if cube is not None else None,
-                           gather="NCCL grouped send/recv to rank 0, inside the timed region" if world > 1 else "none (1 GPU)"),
+                           gather={"none": "none (1 GPU)",
+                                   "peer": "render kernels store their pixels into rank 0's buffer over NVLink (CUDA IPC), "
+                                           "one all-reduce fence; inside the timed region",
+                                   }.get(gather_mode, "NCCL grouped send/recv to rank 0, inside the timed region")),
             "rays_per_sec": value * W * H,
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
@@ -602,6 +642,7 @@ def run_b200(args, wl, name):
                     "steps": e2e_steps, "api": "birp_frame_setup_batch + birp_render_cube/birp_render_cmem (host poses in, pinned host images out)",
                     "note": "bytes are per rank; every rank moves its own share"},
             "gpu_launches": int(launches),
+            "device_setup": device_setup,
             "single_frame_latency_ms": latency_ms,
             "render_only_ms_per_rank": kernel_only,
             "gather_check": gather_check,
@@ -610,8 +651,9 @@ def run_b200(args, wl, name):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
                          "gather_microbench_GBs": l2_gather,
                          "note": "achieved = algorithmic bytes (32 B per live trilinear sample + 4 B per pixel) / "
-                                 "kernel time; the kernel's real DRAM traffic is ~0.05 % of that (L1/L2 reuse), "
-                                 "it is bound by instruction issue and the L1TEX return path (profiles/)",
+                                 "kernel time; the kernel's real DRAM traffic is ~0.06 % of that (the cube is served "
+                                 "from L1/L2), it is bound by instruction issue (86 % issue-active at 78 instructions "
+                                 "per warp-sample) with the L1TEX return path behind (74 %): profiles/r1q_march_orbit_v8.md",
                          "kernel": ("march_cube_kernel<trilinear>" if trilinear else "march_cube_kernel<nearest>") if field == "cube" else "march_kernel<CmemField>",
                          "kernel_ms": float(kern_ms.mean()), "algorithmic_bytes_per_launch": int(alg_bytes),
                          "live_samples_per_launch": int(valid_mine)},

@@ -607,61 +607,100 @@ __device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float
 #define BIRP_CMEM_MARGIN_REL 5e-3f
 #define BIRP_CMEM_MARGIN_ABS 5e-3f
 
+// hardware approximations for the estimate (MUFU.SQRT / MUFU.RCP, ~2^-22 relative)
+__device__ __forceinline__ float est_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// acos(x), |error| < 1e-7: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) (a0 + a1 x + ... + a7 x^7) on [0, 1]
+// (|eps| <= 2e-8), mirrored for x < 0
+__device__ __forceinline__ float est_acos(float x) {
+    const float ax = fabsf(x);
+    float p = -0.0012624911f;
+    p = fmaf(p, ax, 0.0066700901f);
+    p = fmaf(p, ax, -0.0170881256f);
+    p = fmaf(p, ax, 0.0308918810f);
+    p = fmaf(p, ax, -0.0501743046f);
+    p = fmaf(p, ax, 0.0889789874f);
+    p = fmaf(p, ax, -0.2145988016f);
+    p = fmaf(p, ax, 1.5707963050f);
+    const float a = est_sqrt(1.f - ax) * p;
+    return x < 0.f ? 3.14159265f - a : a;
+}
+
 // fp32 estimates of the two radii; false when the direction is one where the estimate is not trusted
 __device__ __forceinline__ bool cmem_radii_estimate(const CmemDev& D, float q_t, float q_p, float& radius_mp,
                                                     float& radius_bs) {
     const birp_cmem_params& P = D.P;
     const float cos_t = q_t, cos_p = q_p;  // cos(acos q) = q
-    const float sin_t = sqrtf((1.f - q_t) * (1.f + q_t));
-    const float sin_p = sqrtf((1.f - q_p) * (1.f + q_p));
-    const float theta = acosf(q_t);
-    const float arg_n = cos_t * D.cos_tn + sin_t * D.sin_tn * sin_p;
-    const float arg_s = cos_t * D.cos_ts - sin_t * D.sin_ts * sin_p;
-    const float fbase = sqrtf(0.5f * (1.f + q_t)) + P.a5 * (2.f * sin_t * cos_t) * (1.f - __expf(-theta));
+    const float sin_t = est_sqrt((1.f - q_t) * (1.f + q_t));
+    const float sin_p = est_sqrt((1.f - q_p) * (1.f + q_p));
+    const float theta = est_acos(q_t);
+    const float sn = sin_t * sin_p;
+    const float arg_n = fmaf(cos_t, D.cos_tn, sn * D.sin_tn);
+    const float arg_s = fmaf(cos_t, D.cos_ts, -sn * D.sin_ts);
+    const float fbase = fmaf(P.a5 * (2.f * sin_t * cos_t), 1.f - __expf(-theta), est_sqrt(0.5f * (1.f + q_t)));
     // ill-conditioned directions: 1 + cos(theta) -> 0 (both radii blow up), acos near +-1 (cusps)
     const bool trusted = (1.f + q_t > 0.02f) && (fabsf(arg_n) < 0.9995f) && (fabsf(arg_s) < 0.9995f) && (fbase > 0.05f);
     const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * cos_p + P.beta_c[3] * sin_p * sin_p);
     const float f = __powf(fbase, fexp);
-    const float phi_n = acosf(arg_n), phi_s = acosf(arg_s);
+    const float phi_n = est_acos(arg_n), phi_s = est_acos(arg_s);
     const float q = D.p2c * (__expf(D.p3dn * __powf(phi_n, P.a21)) + __expf(D.p3ds * __powf(phi_s, P.a21)));
-    radius_mp = D.p0r0 * f + q;
-    const float sbase = 2.f / (1.f + cos_t);
+    radius_mp = fmaf(D.p0r0, f, q);
+    const float sbase = __fdividef(2.f, 1.f + cos_t);
     const float ry = P.bs * __powf(sbase, P.ay_bs);
-    const float rz = P.bs * __powf(sbase, P.az_bs);
+    const float rz = D.same_flare ? ry : P.bs * __powf(sbase, P.az_bs);
     const float rzc = rz * cos_p, rys = ry * sin_p;
-    radius_bs = ry * rz * rsqrtf(rzc * rzc + rys * rys);
+    radius_bs = ry * rz * rsqrtf(fmaf(rzc, rzc, rys * rys));
     return trusted;
 }
 
-template <bool FILTER>
-__device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
-    float r, q_t, q_p;
+// The filter: true with the sample in `value` when its region is certain; false when the full evaluation
+// (cmem_full) has to decide.  r, q_t, q_p are returned either way.
+__device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& r, float& q_t,
+                                                float& q_p, float& value) {
     cmem_cosines(x, y, z, r, q_t, q_p);
-    if (FILTER) {
-        float mp, bs;
-        const bool trusted = cmem_radii_estimate(D, q_t, q_p, mp, bs);
-        const float ht = BIRP_CMEM_HALF_THICKNESS;
-        const float m_mp = BIRP_CMEM_MARGIN_REL * fabsf(mp) + BIRP_CMEM_MARGIN_ABS;
-        const float m_bs = BIRP_CMEM_MARGIN_REL * fabsf(bs) + BIRP_CMEM_MARGIN_ABS;
-        // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
-        if (trusted && r < mp - ht - m_mp) return 0.f;                       // certainly r < mp_lo
-        const bool above_mp = trusted && r > mp + ht + m_mp;                 // certainly r > mp_hi
-        if (above_mp && r > bs + ht + m_bs) return cmem_b2(D.P, r);          // certainly r > bs_hi: not sheath, not layer
-        if (above_mp && r < bs - ht - m_bs) {                                // certainly mp_hi < r < bs_lo: sheath
-            const cm::Angle T = cm::angle_from_cosine(q_t);
-            return cmem_b1(D.P, r, T.a, (float)T.s);
-        }
+    float mp, bs;
+    const bool trusted = cmem_radii_estimate(D, q_t, q_p, mp, bs);
+    const float ht = BIRP_CMEM_HALF_THICKNESS;
+    const float m_mp = BIRP_CMEM_MARGIN_REL * fabsf(mp) + BIRP_CMEM_MARGIN_ABS;
+    const float m_bs = BIRP_CMEM_MARGIN_REL * fabsf(bs) + BIRP_CMEM_MARGIN_ABS;
+    // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
+    if (trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
+        value = 0.f;
+        return true;
     }
+    const bool above_mp = trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
+    if (above_mp && r > bs + ht + m_bs) {                 // certainly r > bs_hi: neither sheath nor layer
+        value = cmem_b2(D.P, r);
+        return true;
+    }
+    if (above_mp && r < bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
+        const cm::Angle T = cm::angle_from_cosine(q_t);
+        value = cmem_b1(D.P, r, T.a, (float)T.s);
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ float cmem_full(const CmemDev& D, float r, float q_t, float q_p) {
     float theta, sin_t, radius_mp, radius_bs;
     cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
     return cmem_regions(D.P, r, theta, sin_t, radius_mp, radius_bs);
+}
+
+__device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
+    float r, q_t, q_p, value;
+    if (cmem_try_filter(D, x, y, z, r, q_t, q_p, value)) return value;
+    return cmem_full(D, r, q_t, q_p);
 }
 
 // CMEM evaluation mode: 0 fp32 libdevice calls, 1 CUDA fp64 library rounded once, 2 own fp64 blocks,
 // 3 (default) own fp64 blocks behind the region filter
 template <int MODE>
 __device__ __forceinline__ float cmem_sample_mode(const CmemDev& D, float x, float y, float z) {
-    if (MODE == 3) return cmem_sample_v5<true>(D, x, y, z);
+    if (MODE == 3) return cmem_sample_v5(D, x, y, z);
     if (MODE == 2) return cmem_sample_v4(D, x, y, z);
     return cmem_sample<MODE == 1>(D, x, y, z);
 }

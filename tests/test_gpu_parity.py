@@ -559,6 +559,19 @@ def test_cmem_render_vs_oracle_and_golden(gpu, golden, name, kw, fast):
         assert assert_image_parity(g, w, f"cmem {name} vs reference-rendered fixture") >= 0.99
 
 
+def test_cmem_render_modes_are_bit_identical(gpu):
+    """the default CMEM march (region filter) against the unfiltered evaluation and the CUDA-library one: same
+    bits in every pixel; odd image sizes leave partially filled warps"""
+    P = capi.cmem_init()
+    poses = np.concatenate([S.orbit_poses(40), [S.DEFAULT_POS, (30.0, -25.0, 28.0), (-15.0, 3.0, 2.0)]]).astype(np.float32)
+    for (w, h, fw, fh) in ((W, H, S.SXI_FOV_W, S.SXI_FOV_H), (37, 21, 40.0, 25.0)):
+        fp = capi.frames_for_poses(poses, AIM, fw, fh, w, h)
+        a = capi.render_cmem(P, fp, w, h)
+        assert_bit_exact(a, capi.render_cmem(P, fp, w, h, fast="nofilter"), "filtered vs unfiltered")
+        assert_bit_exact(a, capi.render_cmem(P, fp, w, h, fast="libm64"), "own fp64 blocks vs CUDA fp64 library")
+        assert a.max() > 0
+
+
 def test_cmem_row_bands_and_accumulate(gpu):
     P = capi.cmem_init()
     fp, _ = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
