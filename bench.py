@@ -497,14 +497,18 @@ def run_b200(args, wl, name):
     my_poses = np.ascontiguousarray(poses[my_idx]) if nframes > 1 else poses
 
     def e2e_step():
-        # poses in -> images out: per-frame host setup, H2D of the frame records, render, D2H of the images
+        # poses in -> images out.  Sweep: one call (birp_render_*_sweep) that makes the frame records of a chunk on
+        # the host threads while the GPU renders the previous chunk and the copy engine drains the one before;
+        # single image: per-frame host setup, H2D of the frame record, render, D2H of the image
+        if nframes > 1:
+            capi.render_sweep(cube if field == "cube" else params, my_poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H,
+                              nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, fast=cmem_mode(), rows=rows,
+                              extra_flags=(EXTRA_FLAGS if field == "cube" else 0), frames_out=h_frames.array,
+                              out=h_images.array)
+            return
         capi.frames_for_poses(my_poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H, out=h_frames.array)
-        if field == "cube":
-            cube.render(h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, rows=rows,
-                        out=h_images.array)
-        else:
-            capi.render_cmem(params, h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, rows=rows,
-                             out=h_images.array, fast=cmem_mode())
+        cube.render(h_frames.array, W, H, nsamples=nsamples, maxdist=MAXDIST, trilinear=trilinear, rows=rows,
+                    out=h_images.array, extra_flags=EXTRA_FLAGS)
 
     for _ in range(2):
         e2e_step()
@@ -639,7 +643,9 @@ def run_b200(args, wl, name):
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
                     "h2d_bytes_per_step": int(nmine * 64), "d2h_bytes_per_step": int(nmine * my_rows * W * 4),
-                    "steps": e2e_steps, "api": "birp_frame_setup_batch + birp_render_cube/birp_render_cmem (host poses in, pinned host images out)",
+                    "steps": e2e_steps,
+                    "api": ("birp_render_cube_sweep / birp_render_cmem_sweep" if nframes > 1 else
+                            "birp_frame_setup + birp_render_cube") + " (host poses in, pinned host images out)",
                     "note": "bytes are per rank; every rank moves its own share"},
             "gpu_launches": int(launches),
             "device_setup": device_setup,

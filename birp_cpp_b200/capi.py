@@ -70,6 +70,8 @@ SIGNATURES = {
     "birp_cube_info": (C.c_int, [_vp, _i32p]),
     "birp_render_cube": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
+    "birp_render_cube_sweep": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 + [_vp, _vp]),
+    "birp_render_cmem_sweep": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 + [_vp, _vp]),
     "birp_accumulate": (C.c_int, [_vp, C.c_long, C.c_int, C.c_float, C.c_int, _vp]),
     "birp_ray_directions": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "birp_sample_cube": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
@@ -282,6 +284,30 @@ class Cube:
         _check(lib().birp_render_cube(self._h, _ptr(frames), len(frames), W, H, rows[0], rows[1], nsamples, maxdist,
                                       flags, _ptr(images)))
         return images
+
+
+def render_sweep(field, poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int, *, nsamples: int = 200,
+                 maxdist: int = 44, trilinear: bool = True, fast=False, rows=(0, 0), extra_flags: int = 0,
+                 frames_out: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """poses (host) -> images (host) in one call; `field` is a Cube or a CMEM parameter record"""
+    poses = _f32(poses).reshape(-1, 3)
+    n = len(poses)
+    images = out if out is not None else np.zeros((n, H, W), dtype=np.float32)
+    assert images.dtype == np.float32 and images.flags.c_contiguous and images.size == n * H * W
+    fr = _vp(0)
+    if frames_out is not None:
+        assert frames_out.dtype == FRAME_DTYPE and len(frames_out) == n and frames_out.flags.c_contiguous
+        fr = _ptr(frames_out)
+    if isinstance(field, Cube):
+        flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
+        _check(lib().birp_render_cube_sweep(field.handle, _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H, rows[0],
+                                            rows[1], nsamples, maxdist, flags, fr, _ptr(images)))
+    else:
+        params = np.ascontiguousarray(field, dtype=CMEM_DTYPE)
+        _check(lib().birp_render_cmem_sweep(_ptr(params), _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H, rows[0],
+                                            rows[1], nsamples, maxdist, _cmem_mode(fast) | extra_flags, fr,
+                                            _ptr(images)))
+    return images
 
 
 def _cmem_mode(fast) -> int:

@@ -213,9 +213,18 @@ int read_status(DeviceCtx* c, cudaStream_t stream) {
 // Shared host-buffer pipeline: frames are rendered in chunks of up to ~64 MiB of pixels,
 // chunk c rendering on the compute stream while chunk c-1 drains to the host on the copy
 // stream (two device image buffers).
+// Poses of a sweep whose frame records are still to be made (birp_render_*_sweep): the records of chunk c are
+// computed on the host threads while the GPU renders chunk c-1.
+struct SweepPoses {
+    const float* poses = nullptr;  // xyz interleaved, nframes of them; nullptr: `frames` is already filled
+    float aim_x = 0.f, fov_x_deg = 0.f, fov_y_deg = 0.f;
+    birp_frame* frames_out = nullptr;  // host buffer the records are written to (caller's or a scratch vector)
+};
+
 template <class Launch>
 int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int H, int row_begin, int row_end,
-                int nsamples, int maxdist, int flags, float* images, Launch&& launch) {
+                int nsamples, int maxdist, int flags, float* images, Launch&& launch,
+                const SweepPoses* sweep = nullptr) {
     std::lock_guard<std::mutex> lk(c->mu);
     RayTable table;
     int rc = get_ray_table(c, nsamples, maxdist, c->compute, &table);
@@ -226,6 +235,9 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     const size_t band_px = (size_t)W * (row_end - row_begin);
     const size_t band_off = (size_t)W * row_begin;
     size_t chunk = (size_t(16) << 20) / frame_px;  // 16 Mi pixels = 64 MiB per buffer
+    // at least four chunks for a batch of many small frames, so that the D2H copy of one chunk (and the host
+    // set-up of the next, for a sweep) overlaps the render of another
+    if ((size_t)nframes >= 256 && chunk > ((size_t)nframes + 3) / 4) chunk = ((size_t)nframes + 3) / 4;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)nframes) chunk = nframes;
     rc = ensure(&c->d_frames, &c->frames_cap, (size_t)nframes);
@@ -239,14 +251,24 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         if (rc) return rc;
         c->images_cap = cap;
     }
-    BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
-                              c->compute));
+    if (!sweep)
+        BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
+                                  c->compute));
     const bool full_rows = (row_begin == 0 && row_end == H);
     int nchunks = 0;
     for (size_t f0 = 0; f0 < (size_t)nframes; f0 += chunk, ++nchunks) {
         const int b = nchunks & 1;
         const int nf = (int)((f0 + chunk <= (size_t)nframes) ? chunk : (size_t)nframes - f0);
         float* d_img = c->d_images[b];
+        if (sweep) {
+            // frame records of this chunk: host threads now (the GPU is busy with the previous chunk), then H2D
+            int src = birp::host_frame_setup_batch(sweep->poses + 3 * f0, nf, sweep->aim_x, sweep->fov_x_deg,
+                                                   sweep->fov_y_deg, W, H, sweep->frames_out + f0, 0);
+            if (src == BIRP_ERR_SINGULAR) return set_error(src, "Determinant is 0");
+            if (src) return src;
+            BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, sweep->frames_out + f0, sizeof(birp_frame) * nf,
+                                      cudaMemcpyHostToDevice, c->compute));
+        }
         if (nchunks >= 2) BIRP_CUDA(cudaStreamWaitEvent(c->compute, c->drained[b], 0));
         if (flags & BIRP_ACCUMULATE) {
             if (full_rows) {
@@ -647,6 +669,68 @@ int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, i
                            cudaStream_t s) {
                            return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
                        });
+}
+
+static int check_sweep(const float* poses, int nframes, birp_frame* frames_out, std::vector<birp_frame>* scratch,
+                       SweepPoses* sw, float aim_x, float fov_x_deg, float fov_y_deg) {
+    if (nframes > 0 && !poses) return set_error(BIRP_ERR_ARG, "null poses");
+    sw->poses = poses;
+    sw->aim_x = aim_x;
+    sw->fov_x_deg = fov_x_deg;
+    sw->fov_y_deg = fov_y_deg;
+    if (frames_out) {
+        sw->frames_out = frames_out;
+    } else {
+        scratch->resize(nframes > 0 ? nframes : 1);
+        sw->frames_out = scratch->data();
+    }
+    return BIRP_OK;
+}
+
+int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                           float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                           int flags, birp_frame* frames_out, float* images) {
+    if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
+    std::vector<birp_frame> scratch;
+    SweepPoses sw;
+    int rc = check_sweep(poses, nframes, frames_out, &scratch, &sw, aim_x, fov_x_deg, fov_y_deg);
+    if (rc) return rc;
+    rc = check_geom(sw.frames_out, nframes, W, H, &row_begin, &row_end, nsamples, images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    const birp::CubeView view = cube->view;
+    int* d_status = c->d_status;
+    return render_host(c, sw.frames_out, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
+                       [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
+                           cudaStream_t s) {
+                           return birp::launch_render_cube(view, d_fr, g, d_dist, flags, d_img, nullptr, d_status, s);
+                       },
+                       &sw);
+}
+
+int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                           float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
+                           int maxdist, int flags, birp_frame* frames_out, float* images) {
+    if (!params) return set_error(BIRP_ERR_ARG, "null params");
+    std::vector<birp_frame> scratch;
+    SweepPoses sw;
+    int rc = check_sweep(poses, nframes, frames_out, &scratch, &sw, aim_x, fov_x_deg, fov_y_deg);
+    if (rc) return rc;
+    rc = check_geom(sw.frames_out, nframes, W, H, &row_begin, &row_end, nsamples, images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    const birp_cmem_params P = *params;
+    return render_host(c, sw.frames_out, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
+                       [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
+                           cudaStream_t s) {
+                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
+                       },
+                       &sw);
 }
 
 int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags, float* image) {

@@ -396,6 +396,7 @@ struct CmemDev {
     float p2c;                             // p2 * charlie           (:217)
     float p3dn, p3ds;                      // p3 * dn, p3 * ds       (:217)
     int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
+    int q_nonpositive;                     // p2 * charlie <= 0: the cusp term of LinScaled can only lower the radius
 };
 
 template <bool PRECISE>
@@ -629,71 +630,98 @@ __device__ __forceinline__ float est_acos(float x) {
     return x < 0.f ? 3.14159265f - a : a;
 }
 
-// fp32 estimates of the two radii; false when the direction is one where the estimate is not trusted
-__device__ __forceinline__ bool cmem_radii_estimate(const CmemDev& D, float q_t, float q_p, float& radius_mp,
-                                                    float& radius_bs) {
-    const birp_cmem_params& P = D.P;
-    const float cos_t = q_t, cos_p = q_p;  // cos(acos q) = q
-    const float sin_t = est_sqrt((1.f - q_t) * (1.f + q_t));
-    const float sin_p = est_sqrt((1.f - q_p) * (1.f + q_p));
-    const float theta = est_acos(q_t);
-    const float sn = sin_t * sin_p;
-    const float arg_n = fmaf(cos_t, D.cos_tn, sn * D.sin_tn);
-    const float arg_s = fmaf(cos_t, D.cos_ts, -sn * D.sin_ts);
-    const float fbase = fmaf(P.a5 * (2.f * sin_t * cos_t), 1.f - __expf(-theta), est_sqrt(0.5f * (1.f + q_t)));
-    // ill-conditioned directions: 1 + cos(theta) -> 0 (both radii blow up), acos near +-1 (cusps)
-    const bool trusted = (1.f + q_t > 0.02f) && (fabsf(arg_n) < 0.9995f) && (fabsf(arg_s) < 0.9995f) && (fbase > 0.05f);
-    const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * cos_p + P.beta_c[3] * sin_p * sin_p);
-    const float f = __powf(fbase, fexp);
-    const float phi_n = est_acos(arg_n), phi_s = est_acos(arg_s);
-    const float q = D.p2c * (__expf(D.p3dn * __powf(phi_n, P.a21)) + __expf(D.p3ds * __powf(phi_s, P.a21)));
-    radius_mp = fmaf(D.p0r0, f, q);
-    const float sbase = __fdividef(2.f, 1.f + cos_t);
-    const float ry = P.bs * __powf(sbase, P.ay_bs);
-    const float rz = D.same_flare ? ry : P.bs * __powf(sbase, P.az_bs);
-    const float rzc = rz * cos_p, rys = ry * sin_p;
-    radius_bs = ry * rz * rsqrtf(fmaf(rzc, rzc, rys * rys));
-    return trusted;
+// hardware-approximation versions of cmem_cosines' outputs (one MUFU.RSQ each instead of IEEE sqrt + division)
+__device__ __forceinline__ void cmem_cosines_estimate(float x, float y, float z, float& r, float& q_t, float& q_p) {
+    const float yz2 = y * y + z * z;
+    const float s2 = x * x + yz2;
+    const float rinv = rsqrtf(s2);
+    r = s2 * rinv;
+    q_t = (x != 0.f) ? x * rinv : 1.f;
+    q_p = (y != 0.f) ? y * rsqrtf(yz2) : 1.f;
 }
 
+// fp32 estimates for the region filter, in two stages so that a sample beyond the bow shock never pays for the
+// cusp terms.  Stage 1: the bow-shock radius and the first term of the magnetopause radius, p0 r0 f.  Stage 2:
+// the cusp indentation q (two acos, two pow, two exp).  With p2 * charlie <= 0 (D.q_nonpositive, every parameter
+// set the reference can produce) q <= 0, i.e. p0 r0 f alone is an UPPER bound of the magnetopause radius.
+struct CmemEstimate {
+    float cos_t, sin_t, cos_p, sin_p;
+    float mp_upper;  // p0 r0 f
+    float bs;
+    bool trusted;    // false in the ill-conditioned directions: 1 + cos(theta) -> 0 (both radii blow up)
+};
+
+__device__ __forceinline__ CmemEstimate cmem_estimate_stage1(const CmemDev& D, float q_t, float q_p) {
+    const birp_cmem_params& P = D.P;
+    CmemEstimate e;
+    e.cos_t = q_t, e.cos_p = q_p;  // cos(acos q) = q
+    e.sin_t = est_sqrt((1.f - q_t) * (1.f + q_t));
+    e.sin_p = est_sqrt((1.f - q_p) * (1.f + q_p));
+    const float theta = est_acos(q_t);
+    const float fbase = fmaf(P.a5 * (2.f * e.sin_t * e.cos_t), 1.f - __expf(-theta), est_sqrt(0.5f * (1.f + q_t)));
+    const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * e.cos_p + P.beta_c[3] * e.sin_p * e.sin_p);
+    e.mp_upper = D.p0r0 * __powf(fbase, fexp);
+    const float sbase = __fdividef(2.f, 1.f + e.cos_t);
+    const float ry = P.bs * __powf(sbase, P.ay_bs);
+    const float rz = D.same_flare ? ry : P.bs * __powf(sbase, P.az_bs);
+    const float rzc = rz * e.cos_p, rys = ry * e.sin_p;
+    e.bs = ry * rz * rsqrtf(fmaf(rzc, rzc, rys * rys));
+    e.trusted = (1.f + q_t > 0.02f) && (fbase > 0.05f);
+    return e;
+}
+
+// the full magnetopause estimate; `trusted` is cleared next to a cusp (acos near +-1 is ill-conditioned)
+__device__ __forceinline__ float cmem_estimate_stage2(const CmemDev& D, CmemEstimate& e) {
+    const birp_cmem_params& P = D.P;
+    const float sn = e.sin_t * e.sin_p;
+    const float arg_n = fmaf(e.cos_t, D.cos_tn, sn * D.sin_tn);
+    const float arg_s = fmaf(e.cos_t, D.cos_ts, -sn * D.sin_ts);
+    e.trusted = e.trusted && (fabsf(arg_n) < 0.9995f) && (fabsf(arg_s) < 0.9995f);
+    const float phi_n = est_acos(arg_n), phi_s = est_acos(arg_s);
+    const float q = D.p2c * (__expf(D.p3dn * __powf(phi_n, P.a21)) + __expf(D.p3ds * __powf(phi_s, P.a21)));
+    return e.mp_upper + q;
+}
+
+#define BIRP_CMEM_MARGIN(v) (BIRP_CMEM_MARGIN_REL * fabsf(v) + BIRP_CMEM_MARGIN_ABS)
+
 // The filter: true with the sample in `value` when its region is certain; false when the full evaluation
-// (cmem_full) has to decide.  r, q_t, q_p are returned either way.
-__device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& r, float& q_t,
-                                                float& q_p, float& value) {
-    cmem_cosines(x, y, z, r, q_t, q_p);
-    float mp, bs;
-    const bool trusted = cmem_radii_estimate(D, q_t, q_p, mp, bs);
+// (cmem_sample_v4) has to decide.
+__device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
+    float r, q_t, q_p;
+    cmem_cosines_estimate(x, y, z, r, q_t, q_p);
+    CmemEstimate e = cmem_estimate_stage1(D, q_t, q_p);
     const float ht = BIRP_CMEM_HALF_THICKNESS;
-    const float m_mp = BIRP_CMEM_MARGIN_REL * fabsf(mp) + BIRP_CMEM_MARGIN_ABS;
-    const float m_bs = BIRP_CMEM_MARGIN_REL * fabsf(bs) + BIRP_CMEM_MARGIN_ABS;
+    const float m_bs = BIRP_CMEM_MARGIN(e.bs);
     // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
-    if (trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
+    if (D.q_nonpositive && e.trusted && r > e.bs + ht + m_bs && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper)) {
+        // certainly r > bs_hi and r > mp_hi: neither sheath nor a layer
+        value = cmem_b2(D.P, vec_len3(x, y, z));
+        return true;
+    }
+    const float mp = cmem_estimate_stage2(D, e);
+    const float m_mp = BIRP_CMEM_MARGIN(mp);
+    if (e.trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
         value = 0.f;
         return true;
     }
-    const bool above_mp = trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
-    if (above_mp && r > bs + ht + m_bs) {                 // certainly r > bs_hi: neither sheath nor layer
-        value = cmem_b2(D.P, r);
+    const bool above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
+    if (above_mp && r > e.bs + ht + m_bs) {                 // (parameter sets with q > 0)
+        value = cmem_b2(D.P, vec_len3(x, y, z));
         return true;
     }
-    if (above_mp && r < bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
-        const cm::Angle T = cm::angle_from_cosine(q_t);
-        value = cmem_b1(D.P, r, T.a, (float)T.s);
+    if (above_mp && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
+        const float r_exact = vec_len3(x, y, z);
+        const cm::Angle T = cm::angle_from_cosine((x != 0.f) ? __fdiv_rn(x, r_exact) : 1.f);
+        value = cmem_b1(D.P, r_exact, T.a, (float)T.s);
         return true;
     }
     return false;
 }
 
-__device__ __forceinline__ float cmem_full(const CmemDev& D, float r, float q_t, float q_p) {
-    float theta, sin_t, radius_mp, radius_bs;
-    cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
-    return cmem_regions(D.P, r, theta, sin_t, radius_mp, radius_bs);
-}
-
 __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
-    float r, q_t, q_p, value;
-    if (cmem_try_filter(D, x, y, z, r, q_t, q_p, value)) return value;
-    return cmem_full(D, r, q_t, q_p);
+    float value;
+    if (cmem_try_filter(D, x, y, z, value)) return value;
+    return cmem_sample_v4(D, x, y, z);
 }
 
 // CMEM evaluation mode: 0 fp32 libdevice calls, 1 CUDA fp64 library rounded once, 2 own fp64 blocks,

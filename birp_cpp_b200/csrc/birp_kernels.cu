@@ -72,6 +72,7 @@ CmemDev make_cmem_dev(const birp_cmem_params& P) {
     D.p3dn = p3dn;
     D.p3ds = p3ds;
     D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
+    D.q_nonpositive = (p2c <= 0.f) ? 1 : 0;
     return D;
 }
 
@@ -634,14 +635,22 @@ __global__ void __launch_bounds__(256) cmem_filter_selftest_kernel(const CmemDev
     if (pick == 2) x *= tiny;
     if (pick == 3) y *= tiny, z *= tiny;
     if (pick == 4) x = -fabsf(x), y *= 0.2f * tiny, z *= 0.2f * tiny;  // around the -x axis guard
-    float r, q_t, q_p;
+    float r, q_t, q_p, re, qe_t, qe_p;
     cmem_cosines(x, y, z, r, q_t, q_p);
-    float mp_e, bs_e;
-    if (!cmem_radii_estimate(D, q_t, q_p, mp_e, bs_e)) return;
+    cmem_cosines_estimate(x, y, z, re, qe_t, qe_p);
+    CmemEstimate est = cmem_estimate_stage1(D, qe_t, qe_p);
+    const bool trusted1 = est.trusted;  // what the stage-1 decision (beyond the bow shock) relies on
+    const float mp_e = cmem_estimate_stage2(D, est);
+    const float bs_e = est.bs, up_e = est.mp_upper;
+    if (!trusted1) return;
     float theta, sin_t, mp, bs;
     cmem_radii_v4(D, q_t, q_p, theta, sin_t, mp, bs);
-    const double u_mp = fabs((double)mp_e - (double)mp) / (double)(BIRP_CMEM_MARGIN_REL * fabsf(mp_e) + BIRP_CMEM_MARGIN_ABS);
-    const double u_bs = fabs((double)bs_e - (double)bs) / (double)(BIRP_CMEM_MARGIN_REL * fabsf(bs_e) + BIRP_CMEM_MARGIN_ABS);
+    // the filter compares the ESTIMATED r with the estimated radii: the error of r counts against the margin too
+    const double dr = fabs((double)re - (double)r);
+    double u_mp = est.trusted ? (fabs((double)mp_e - (double)mp) + dr) / (double)BIRP_CMEM_MARGIN(mp_e) : 0.0;
+    const double u_bs = (fabs((double)bs_e - (double)bs) + dr) / (double)BIRP_CMEM_MARGIN(bs_e);
+    // stage 1 uses p0 r0 f as an upper bound of the magnetopause radius: how far below the exact radius can it fall?
+    if (D.q_nonpositive) u_mp = fmax(u_mp, ((double)mp - (double)up_e + dr) / (double)BIRP_CMEM_MARGIN(up_e));
     // a NaN on either side would make the filter's comparisons false (full evaluation); count it as unused margin
     if (u_mp == u_mp) atomicMax(out + 0, (unsigned long long)__double_as_longlong(u_mp));
     if (u_bs == u_bs) atomicMax(out + 1, (unsigned long long)__double_as_longlong(u_bs));

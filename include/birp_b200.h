@@ -164,6 +164,16 @@ int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframe
                      int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
 int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, int nframes, int W, int H,
                      int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
+/* A sweep given as camera POSITIONS (xyz interleaved, common aim / field of view): what the reference would do
+   with one Camera per pose -- SetPosition, SetAim(aim_x, 0, 0), Render() -- in one call.  The frame records are
+   made by birp_frame_setup_batch chunk by chunk while the GPU renders the previous chunk and the copy engine
+   drains the one before; frames_out (nframes records, optional, may be NULL) receives them. */
+int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                           float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                           int flags, birp_frame* frames_out, float* images);
+int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                           float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
+                           int maxdist, int flags, birp_frame* frames_out, float* images);
 /* src/Camera.cpp:201-223 on samples[nrays][nsamples] taken on the host from a user-defined Space
    subclass (e.g. the reference tests' CubeFake, tests/Camera_test.cpp:25-29). image: nrays floats. */
 int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags,

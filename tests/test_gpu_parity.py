@@ -377,6 +377,22 @@ def test_render_constant_cube_counts_samples(gpu):
         c.free()
 
 
+def test_sweep_call_equals_frames_call(gpu, dev_cube1):
+    """birp_render_*_sweep (poses in, chunked: host setup of one chunk while the previous one renders) returns
+    the frame records and the images of the two-step path, bit for bit; 1000 frames make four chunks"""
+    poses = S.orbit_poses(1000)
+    fp = capi.frames_for_poses(poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    for tri in (True, False):
+        fr = np.zeros(len(poses), capi.FRAME_DTYPE)
+        got = capi.render_sweep(dev_cube1, poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, trilinear=tri, frames_out=fr)
+        assert_bit_exact(fr.view(np.float32), fp.view(np.float32), "frame records")
+        assert_bit_exact(got, dev_cube1.render(fp, W, H, trilinear=tri), f"tri={tri}")
+    P = capi.cmem_init()
+    got = capi.render_sweep(P, poses[:300], AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, rows=(5, 40))
+    assert_bit_exact(got, capi.render_cmem(P, fp[:300], W, H, rows=(5, 40)), "cmem sweep, row band, no frames_out")
+    assert capi.render_sweep(dev_cube1, np.zeros((0, 3), np.float32), AIM, 27.0, 16.0, W, H).shape == (0, H, W)
+
+
 # ------------------------------------------------------------------ device-side sweep setup (SURVEY 8(f)4)
 def test_device_orbit_poses_and_frame_setup(gpu, dev_cube1, cube1):
     """poses generated and turned into frame records on the device: against the host path (glibc, bit-identical
