@@ -258,7 +258,8 @@ class Cube:
     def info(self) -> dict:
         out = (C.c_int * 4)()
         _check(lib().birp_cube_info(self._h, out))
-        return {"divmode": int(out[0]), "positive": bool(out[1]), "texture": bool(out[2]), "quads": bool(out[3])}
+        return {"divmode": int(out[0]), "positive": out[1] == 1, "nonnegative": out[1] in (1, 2),
+                "texture": bool(out[2]), "quads": bool(out[3])}
 
     def sample(self, xyz, trilinear: bool) -> np.ndarray:
         xyz = _f32(xyz).reshape(-1, 3)

@@ -462,7 +462,7 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "scan_positive launch: %s", cudaGetErrorString(e));
     BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
-    v.positive = (c->h_status[0] == 0) ? 1 : 0;
+    v.positive = (c->h_status[0] == 0) ? 1 : ((c->h_status[0] & 2) == 0) ? 2 : 0;
     *c->h_status = 0;
 
     // Layered-texture copy for the two-gather corner fetch (trilinear only).  Any failure here

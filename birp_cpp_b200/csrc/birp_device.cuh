@@ -32,7 +32,8 @@ struct CubeView {
     float lox, loy, loz;  // smallest ingress whose quotient by the spacing is >= 1 (and >= 2^-100)
                           // (hot window: lo? <= ingress < l?, i.e. index in [1, n-1); everything else is cold)
     int divmode;          // cheapest div_spacing variant proven exact for all three axes (0,1) or 2
-    int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch)
+    int positive;         // 1: every voxel is finite and > 0 (std::lerp never takes its sign branch);
+                          // 2: finite and > 0 or +0 (lerp_nonneg); 0: anything else (full std::lerp)
     // layered 2D texture over the same voxels (layer = z), point-sampled; 0 when the cube exceeds
     // the layered-texture limits or the upload-time gather self-check failed
     cudaTextureObject_t tex;
@@ -229,6 +230,18 @@ __device__ __forceinline__ float cube_sample(const CubeView& c, float x, float y
     return lerp_ref(low_y, high_y, tz);
 }
 
+// std::lerp for a NON-NEGATIVE finite cube (every voxel > 0 or +0: emissivity grids of real runs are zero
+// inside the magnetosphere) and a weight t <= 1 - 2^-23, omt = RN(1 - t):
+//   a, b > 0:  a + t*(b - a), the clamp never fires (proof at cube_sample_hot);
+//   a == 0:    the sign branch of __lerp gives t*b + (1-t)*0 = RN(t*b), and so does 0 + t*(b - 0);
+//   b == 0:    the sign branch gives t*0 + (1-t)*a = RN(omt * a)   -- the one case that needs its own formula.
+// Results are again finite and >= +0, so the seven lerps of a trilinear sample compose.
+__device__ __forceinline__ float lerp_nonneg(float a, float b, float t, float omt) {
+    const float x = __fadd_rn(a, __fmul_rn(t, __fsub_rn(b, a)));
+    const float y = __fmul_rn(omt, a);
+    return b == 0.f ? y : x;
+}
+
 // Hot-path form of DataCube::GetSample for the march kernel.  Same results as cube_sample();
 // what changes is the cost:
 //  * the bounds test `0 > ingress || index + 1 >= size` is monotone in the ingress, so it is a
@@ -237,9 +250,10 @@ __device__ __forceinline__ float cube_sample(const CubeView& c, float x, float y
 //  * the division by the spacing is div_spacing<DIVMODE>;
 //  * the eight corners are read at fixed offsets (x0+1, y0+1, z0+1 are always inside the grid for
 //    an in-bounds sample); on an exact integer index the reference reads the same voxel twice
-//    (ceil == floor) -- with weight 0 that gives the same result for finite data (POSITIVE),
+//    (ceil == floor) -- with weight 0 that gives the same result for finite data (LERP 1, 2),
 //    otherwise the duplicate is selected explicitly;
-//  * for a POSITIVE cube std::lerp is `a + t*(b-a)`, three instructions (proof below).
+//  * for a positive cube (LERP 1) std::lerp is `a + t*(b-a)`, three instructions (proof below); for a
+//    non-negative one (LERP 2) lerp_nonneg; anything else (LERP 0) runs the full __lerp.
 // cube_hot_window() says whether a sample is inside the hot window (false: dead ray, NaN coordinate,
 // first cell of an axis -- the caller falls back to cube_sample()), cube_sample_hot() evaluates it.
 //
@@ -269,7 +283,7 @@ __device__ __forceinline__ bool cube_hot_window(const CubeView& c, float xi, flo
 }
 
 // (2) the sample, for ingresses inside the window
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
 __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, float yi, float zi) {
     const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
     const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);
@@ -315,7 +329,17 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
         l110 = __ldg(p + slab + row);
         l111 = __ldg(p + slab + row + 1);
     }
-    if (POSITIVE) {
+    if (LERP == 2) {
+        const float ox = __fsub_rn(1.f, tx), oy = __fsub_rn(1.f, ty), oz = __fsub_rn(1.f, tz);
+        const float low_x1 = lerp_nonneg(s000, l001, tx, ox);
+        const float low_x2 = lerp_nonneg(l010, l011, tx, ox);
+        const float high_x1 = lerp_nonneg(l100, l101, tx, ox);
+        const float high_x2 = lerp_nonneg(l110, l111, tx, ox);
+        const float low_y = lerp_nonneg(low_x1, low_x2, ty, oy);
+        const float high_y = lerp_nonneg(high_x1, high_x2, ty, oy);
+        return lerp_nonneg(low_y, high_y, tz, oz);
+    }
+    if (LERP == 1) {
         const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
         const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
         const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));

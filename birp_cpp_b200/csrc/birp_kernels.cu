@@ -183,7 +183,7 @@ __device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& 
     return cube_hot_window(c, xi, yi, zi);
 }
 
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
 __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
                                                 float ray_width, double K, int* status, bool& alive) {
     for (;;) {
@@ -198,9 +198,9 @@ __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, 
             // has one padding entry: the look-ahead of the last step reads it and discards the result.)
             bool more;
             do {
-                const float s = cube_sample_hot<TRILINEAR, DIVMODE, POSITIVE, FETCH>(c, xi, yi, zi);
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
                 float v;
-                const bool exact = scale_fast<!POSITIVE>(s, ray_width, K, v);
+                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
                 const bool hot_next = step_ingress(c, r, sdist + 4, xi, yi, zi);
                 if (exact) {
                     r.acc = __fadd_rn(r.acc, v);
@@ -228,7 +228,7 @@ __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, 
     }
 }
 
-template <bool TRILINEAR, int DIVMODE, bool POSITIVE, int FETCH>
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     bool alive = owns_pixel;
     unsigned nlive4 = 0;  // 4 x the number of samples accumulated
     if (alive)
-        nlive4 = march_steps<TRILINEAR, DIVMODE, POSITIVE, FETCH>(cc, r, s_base, s_base + 4u * first_chunk, ray_width,
+        nlive4 = march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk, ray_width,
                                                                   K, a.status, alive) - s_base;
     // marches longer than the staged table: refill it chunk by chunk (every thread of the CTA takes part)
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
-            nlive4 += march_steps<TRILINEAR, DIVMODE, POSITIVE, FETCH>(cc, r, s_base, s_base + 4u * chunk, ray_width,
+            nlive4 += march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk, ray_width,
                                                                        K, a.status, alive) - s_base;
     }
     if (owns_pixel) {
@@ -350,31 +350,34 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, bool POS, int FETCH>
+template <bool TRI, int DIV, int LERP, int FETCH>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
-    march_cube_kernel<TRI, DIV, POS, FETCH><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    march_cube_kernel<TRI, DIV, LERP, FETCH><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
 }
 
-template <int DIV, bool POS>
+template <int DIV, int LERP>
 cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, cudaStream_t stream) {
     switch (fetch) {
-        case 1: return launch_cube_variant<true, DIV, POS, 1>(a, c, blocks, stream);
-        case 2: return launch_cube_variant<true, DIV, POS, 2>(a, c, blocks, stream);
-        case 4: return launch_cube_variant<true, DIV, POS, 4>(a, c, blocks, stream);
-        default: return launch_cube_variant<true, DIV, POS, 0>(a, c, blocks, stream);
+        case 1: return launch_cube_variant<true, DIV, LERP, 1>(a, c, blocks, stream);
+        case 2: return launch_cube_variant<true, DIV, LERP, 2>(a, c, blocks, stream);
+        case 4: return launch_cube_variant<true, DIV, LERP, 4>(a, c, blocks, stream);
+        default: return launch_cube_variant<true, DIV, LERP, 0>(a, c, blocks, stream);
     }
 }
 
+// lerp: 0 full std::lerp, 1 positive cube, 2 non-negative cube
 template <int DIV>
-cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, bool pos, int fetch,
+cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, int lerp, int fetch,
                             cudaStream_t stream) {
     if (!tri) {
-        if (pos) return launch_cube_variant<false, DIV, true, 0>(a, c, blocks, stream);
-        return launch_cube_variant<false, DIV, false, 0>(a, c, blocks, stream);
+        // nearest neighbour interpolates nothing; the class only decides whether a zero product can be a sample
+        if (lerp == 1) return launch_cube_variant<false, DIV, 1, 0>(a, c, blocks, stream);
+        return launch_cube_variant<false, DIV, 0, 0>(a, c, blocks, stream);
     }
-    if (pos) return launch_cube_fetch<DIV, true>(a, c, blocks, fetch, stream);
-    return launch_cube_fetch<DIV, false>(a, c, blocks, fetch, stream);
+    if (lerp == 1) return launch_cube_fetch<DIV, 1>(a, c, blocks, fetch, stream);
+    if (lerp == 2) return launch_cube_fetch<DIV, 2>(a, c, blocks, fetch, stream);
+    return launch_cube_fetch<DIV, 0>(a, c, blocks, fetch, stream);
 }
 
 // upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
@@ -439,14 +442,17 @@ __global__ void __launch_bounds__(256) verify_quads_kernel(const float* __restri
 }
 
 // ---- upload-time analysis kernels -------------------------------------------------------
-// flag |= 1 unless every voxel is finite and > 0
+// flag |= 1 unless every voxel is finite and > 0; flag |= 2 unless every voxel is finite and > 0 or +0
 __global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restrict__ v, size_t n, int* flag) {
-    bool bad = false;
+    int bad = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float x = __ldg(v + i);
-        bad |= !(x > 0.f && x < CUDART_INF_F);
+        const bool pos = x > 0.f && x < CUDART_INF_F;
+        if (!pos) bad |= 1;
+        if (!pos && __float_as_uint(x) != 0u) bad |= 2;
     }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
 }
 
 // Exhaustive proof for one spacing: for EVERY fp32 ingress a of the hot window,
@@ -672,7 +678,7 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         return cudaErrorInvalidConfiguration;
     if (a.total_tiles <= 0) return cudaSuccess;
     const bool tri = (flags & BIRP_TRILINEAR) != 0;
-    const bool pos = cube.positive != 0 && !(flags & BIRP_GENERAL_LERP);
+    const int lerp = (flags & BIRP_GENERAL_LERP) ? 0 : cube.positive;
     int divmode = cube.divmode;
     if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
     if (flags & BIRP_DIV_IEEE) divmode = 2;
@@ -693,9 +699,9 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     }
     cudaError_t e;
     switch (divmode) {
-        case 0: e = launch_cube_div<0>(a, view, blocks, tri, pos, fetch, stream); break;
-        case 1: e = launch_cube_div<1>(a, view, blocks, tri, pos, fetch, stream); break;
-        default: e = launch_cube_div<2>(a, view, blocks, tri, pos, fetch, stream); break;
+        case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, stream); break;
+        case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, stream); break;
+        default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, stream); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e;

@@ -11,7 +11,12 @@
 #include <mutex>
 #include <thread>
 
+#include <cmath>
+#include <stdexcept>
+
+#include "../../include/birp_b200.h"
 #include "Camera.h"
+#include "Cmem.h"
 #include "DataCube.h"
 
 namespace {
@@ -100,4 +105,33 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
     }
     for (auto& th : pool) th.join();
     return results;
+}
+
+std::vector<float> RenderSweep(Space& space, const std::vector<float>& positions_xyz, float aim_x,
+                               float pixel_size_deg, float plot_fov_h, float plot_fov_w, int* width, int* height,
+                               int samples, int max_distance) {
+    // image size and fields of view exactly as Camera's constructor derives them (src/Camera.cpp:32-39)
+    const int H = (int)std::round(plot_fov_h / pixel_size_deg), W = (int)std::round(plot_fov_w / pixel_size_deg);
+    if (width) *width = W;
+    if (height) *height = H;
+    if (positions_xyz.size() % 3 != 0) throw std::invalid_argument("RenderSweep: positions must be x, y, z triples");
+    const int n = (int)(positions_xyz.size() / 3);
+    std::vector<float> images((size_t)n * H * W, 0.f);
+    if (n == 0 || W <= 0 || H <= 0) return images;
+    int rc;
+    if (auto* cube = dynamic_cast<DataCube*>(&space)) {
+        const int flags = cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST;
+        rc = birp_render_cube_sweep(cube->Resident(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H, 0, H,
+                                    samples, max_distance, flags, nullptr, images.data());
+    } else if (auto* cmem = dynamic_cast<CMEM*>(&space)) {
+        const int flags = cmem->FastMath() ? BIRP_CMEM_FAST : 0;
+        rc = birp_render_cmem_sweep(&cmem->Params(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H, 0, H,
+                                    samples, max_distance, flags, nullptr, images.data());
+    } else {
+        throw std::invalid_argument("RenderSweep: the Space must be a DataCube or a CMEM");
+    }
+    if (rc == BIRP_ERR_SINGULAR) throw std::runtime_error("Determinant is 0");
+    if (rc == BIRP_ERR_RANGE) throw std::out_of_range("vector::_M_range_check");
+    if (rc != BIRP_OK) throw std::runtime_error(birp_last_error());
+    return images;
 }

@@ -149,7 +149,8 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
                             const float spacing[3], void* stream, birp_cube** out);
 void birp_cube_free(birp_cube* cube);
 /* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
-   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0,
+   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0, 2 when
+   finite and > 0 or +0 (each class has its own exact form of std::lerp), 0 otherwise,
    info[2] = 1 when the layered-texture copy exists and passed its gather self-check,
    info[3] = 1 when the quad copy (16-byte corner fetch) exists and passed its self-check */
 int birp_cube_info(const birp_cube* cube, int info[4]);

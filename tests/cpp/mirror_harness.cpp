@@ -208,6 +208,25 @@ int mir_render_batch(const char* in_dir, const char* out_dir, float px_deg, floa
     }
 }
 
+// RenderSweep: n positions -> n images (kind: 0 DataCube, 1 CMEM); returns 0 / error kind
+int mir_render_sweep(void* p, int kind, const float* positions, int n, float aim_x, float px_deg, float fov_h,
+                     float fov_w, float* images, int* out_wh) {
+    try {
+        Space* s = as_space(p, kind);
+        std::vector<float> pos(positions, positions + 3 * (size_t)n);
+        int w = 0, h = 0;
+        std::vector<float> img = RenderSweep(*s, pos, aim_x, px_deg, fov_h, fov_w, &w, &h);
+        if (out_wh) {
+            out_wh[0] = w;
+            out_wh[1] = h;
+        }
+        if (images) std::copy(img.begin(), img.end(), images);
+    } catch (const std::exception& e) {
+        return fail(e);
+    }
+    return 0;
+}
+
 // Helper's public matrix routines (host only)
 int mir_helper_inverse3(const float* m9, float* out9) {
     try {

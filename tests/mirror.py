@@ -52,6 +52,8 @@ def lib():
         L.mir_render_batch.restype = C.c_int
         L.mir_render_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int,
                                        C.c_int, _vp]
+        L.mir_render_sweep.restype = C.c_int
+        L.mir_render_sweep.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _vp, _vp]
         L.mir_helper_inverse3.restype = C.c_int
         L.mir_helper_inverse3.argtypes = [_vp, _vp]
         _lib = L
@@ -165,6 +167,18 @@ def render(space, pos, aim_x, px_deg, fov_h, fov_w, nsamples=0, maxdist=0, times
     img = np.zeros((int(wh[1]), int(wh[0])), np.float32)
     if lib().mir_render(space.h, space.kind, px_deg, fov_h, fov_w, _p(p), aim_x, nsamples, maxdist, times, _p(img),
                         _p(wh), str(dat).encode() if dat else None, str(fits).encode() if fits else None):
+        _raise()
+    return img
+
+
+def render_sweep(space, positions, aim_x, px_deg, fov_h, fov_w):
+    """RenderSweep: n positions -> [n][H][W] images"""
+    pos = _f32(positions).reshape(-1, 3)
+    wh = np.zeros(2, np.int32)
+    if lib().mir_render_sweep(space.h, space.kind, _p(pos), 0, aim_x, px_deg, fov_h, fov_w, None, _p(wh)):
+        _raise()
+    img = np.zeros((len(pos), int(wh[1]), int(wh[0])), np.float32)
+    if lib().mir_render_sweep(space.h, space.kind, _p(pos), len(pos), aim_x, px_deg, fov_h, fov_w, _p(img), _p(wh)):
         _raise()
     return img
 

@@ -192,17 +192,27 @@ def test_cube_with_zero_regions_stays_bit_exact(gpu):
     x = org[0] + sp[0] * np.arange(64)
     r = np.sqrt(x[None, None, :] ** 2 + x[None, :, None] ** 2 + x[:, None, None] ** 2)
     zyx[r < 12.0] = 0.0
-    zyx[40:44, :, :] = -0.0  # and a slab of negative zeros
+    zyx[np.random.default_rng(8).random(zyx.shape) < 0.08] = 0.0  # and isolated zero voxels: every corner pattern
     c = capi.Cube(zyx, org, sp)
     try:
-        assert not c.info()["positive"]
+        assert not c.info()["positive"] and c.info()["nonnegative"]
         poses = np.array([S.DEFAULT_POS, (20.0, -15.0, 3.0), (0.5, 0.25, 1.0)], np.float32)
         fp, fo = frames_pair(poses, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
         for tri in (False, True):
             want = O.orc_render_cube(zyx, org, sp, tri, fo, W, H)
-            for fl in (_FETCH if tri else [0]):
+            for fl in (_FETCH + [capi.GENERAL_LERP] if tri else [0]):
                 assert_bit_exact(c.render(fp, W, H, trilinear=tri, extra_flags=fl), want, f"tri={tri} flags={fl}")
             assert want.max() > 0
+    finally:
+        c.free()
+    # a slab of NEGATIVE zeros takes the cube out of the non-negative class: full std::lerp, same parity
+    zyx[40:44, :, :] = -0.0
+    c = capi.Cube(zyx, org, sp)
+    try:
+        assert not c.info()["nonnegative"]
+        for tri in (False, True):
+            want = O.orc_render_cube(zyx, org, sp, tri, fo, W, H)
+            assert_bit_exact(c.render(fp, W, H, trilinear=tri), want, f"negative zeros, tri={tri}")
     finally:
         c.free()
 

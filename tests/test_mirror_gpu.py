@@ -45,6 +45,29 @@ def test_camera_datacube_matches_reference_classes(gpu, cube1, tri):
 
 
 @needs_ref
+def test_render_sweep_equals_one_reference_camera_per_position(gpu, cube1):
+    """RenderSweep (C++ helper over birp_render_*_sweep) against the unmodified reference classes driven with
+    one Camera per position: bit-identical images for the DataCube, tolerance for CMEM"""
+    zyx, org, sp = cube1
+    positions = np.concatenate([S.orbit_poses(6), [S.DEFAULT_POS, (30.0, -25.0, 28.0)]]).astype(np.float32)
+    for tri in (True, False):
+        ref, mir = O.RefCube(zyx, org, sp, tri), M.Cube(zyx, org, sp, tri)
+        got = M.render_sweep(mir, positions, AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+        assert got.shape == (len(positions), S.SXI_H, S.SXI_W)
+        for k, pos in enumerate(positions):
+            assert_bit_exact(got[k], O.ref_render(ref, pos, AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W), f"pose {k}")
+        mir.free()
+    ref, mir = O.RefCmem(), M.Cmem()
+    got = M.render_sweep(mir, positions[:3], AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+    for k in range(3):
+        want = O.ref_render(ref, positions[k], AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+        assert assert_image_parity(got[k], want, f"cmem pose {k}") >= 0.99
+    mir.free()
+    with pytest.raises(Exception):  # a user-defined Space cannot be swept
+        M.render_sweep(M.Fake(1.0), positions[:1], AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+
+
+@needs_ref
 def test_camera_nondefault_march(gpu, cube1):
     zyx, org, sp = cube1
     ref, mir = O.RefCube(zyx, org, sp, True), M.Cube(zyx, org, sp, True)
