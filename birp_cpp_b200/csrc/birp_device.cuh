@@ -528,7 +528,10 @@ __device__ __forceinline__ void cmem_cosines(float x, float y, float z, float& r
 __device__ __forceinline__ float cmem_b1(const birp_cmem_params& P, float r, float theta, float sin_t) {
     const float h = __fdiv_rn(theta, 2.f);
     const float h4 = __fmul_rn(__fmul_rn(__fmul_rn(h, h), h), h);
-    const float e = (float)cm::exp_d((double)__fmul_rn(-P.B, h4));
+    // expf(-B h^4): CMEM::Init overwrites B with |b| * 1e-9 (src/Cmem.cpp:310), so the argument is ~ -1e-8 and the
+    // correctly rounded result is 1.0f whenever |argument| < 2^-26 (e^x is then within a quarter ulp of 1)
+    const float ea = __fmul_rn(-P.B, h4);
+    const float e = (fabsf(ea) < 1.4901161e-08f) ? 1.0f : (float)cm::exp_d((double)ea);
     const float pw = pow32(__fdiv_rn(r, 10.f), __fsub_rn(-P.alpha, __fmul_rn(P.beta, __fmul_rn(sin_t, sin_t))));
     return __fmul_rn(__fmul_rn(P.A1, e), pw);
 }
@@ -669,7 +672,8 @@ __device__ __forceinline__ void cmem_cosines_estimate(float x, float y, float z,
 // the cusp indentation q (two acos, two pow, two exp).  With p2 * charlie <= 0 (D.q_nonpositive, every parameter
 // set the reference can produce) q <= 0, i.e. p0 r0 f alone is an UPPER bound of the magnetopause radius.
 struct CmemEstimate {
-    float cos_t, sin_t, cos_p, sin_p;
+    float cos_t, sin_t, cos_p;
+    float sin2_p;    // sin(phi)^2 = 1 - q_p^2 (stage 1 needs no sin(phi) itself)
     float mp_upper;  // p0 r0 f
     float bs;
     bool trusted;    // false in the ill-conditioned directions: 1 + cos(theta) -> 0 (both radii blow up)
@@ -680,16 +684,21 @@ __device__ __forceinline__ CmemEstimate cmem_estimate_stage1(const CmemDev& D, f
     CmemEstimate e;
     e.cos_t = q_t, e.cos_p = q_p;  // cos(acos q) = q
     e.sin_t = est_sqrt((1.f - q_t) * (1.f + q_t));
-    e.sin_p = est_sqrt((1.f - q_p) * (1.f + q_p));
+    e.sin2_p = (1.f - q_p) * (1.f + q_p);
     const float theta = est_acos(q_t);
     const float fbase = fmaf(P.a5 * (2.f * e.sin_t * e.cos_t), 1.f - __expf(-theta), est_sqrt(0.5f * (1.f + q_t)));
-    const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * e.cos_p + P.beta_c[3] * e.sin_p * e.sin_p);
+    const float fexp = P.p1 * (P.beta_c[0] + P.beta_c[1] * e.cos_p + P.beta_c[3] * e.sin2_p);
     e.mp_upper = D.p0r0 * __powf(fbase, fexp);
-    const float sbase = __fdividef(2.f, 1.f + e.cos_t);
-    const float ry = P.bs * __powf(sbase, P.ay_bs);
-    const float rz = D.same_flare ? ry : P.bs * __powf(sbase, P.az_bs);
-    const float rzc = rz * e.cos_p, rys = ry * e.sin_p;
-    e.bs = ry * rz * rsqrtf(fmaf(rzc, rzc, rys * rys));
+    // (2 / (1 + cos theta))^a = 2^(a (1 - log2(1 + cos theta)))
+    const float lb = 1.f - __log2f(1.f + e.cos_t);
+    const float ry = P.bs * exp2f(P.ay_bs * lb);
+    if (D.same_flare) {
+        e.bs = ry;  // ry = rz: ry rz / sqrt(ry^2 (cos^2 + sin^2)) = ry
+    } else {
+        const float rz = P.bs * exp2f(P.az_bs * lb);
+        const float rzc = rz * e.cos_p;
+        e.bs = ry * rz * rsqrtf(fmaf(rzc, rzc, ry * ry * e.sin2_p));
+    }
     e.trusted = (1.f + q_t > 0.02f) && (fbase > 0.05f);
     return e;
 }
@@ -697,7 +706,7 @@ __device__ __forceinline__ CmemEstimate cmem_estimate_stage1(const CmemDev& D, f
 // the full magnetopause estimate; `trusted` is cleared next to a cusp (acos near +-1 is ill-conditioned)
 __device__ __forceinline__ float cmem_estimate_stage2(const CmemDev& D, CmemEstimate& e) {
     const birp_cmem_params& P = D.P;
-    const float sn = e.sin_t * e.sin_p;
+    const float sn = e.sin_t * est_sqrt(e.sin2_p);
     const float arg_n = fmaf(e.cos_t, D.cos_tn, sn * D.sin_tn);
     const float arg_s = fmaf(e.cos_t, D.cos_ts, -sn * D.sin_ts);
     e.trusted = e.trusted && (fabsf(arg_n) < 0.9995f) && (fabsf(arg_s) < 0.9995f);

@@ -487,6 +487,31 @@ def test_config3_256cube_1024_image(gpu, n):
         c.free()
 
 
+def test_config4_512cube_image_in_row_bands(gpu):
+    """BASELINE.json configs[3]: the 512^3 cube (512 MiB; 2 GiB as quads), a 1024x1024 image cut into the eight row
+    bands the 8-GPU run gives its ranks.  Two bands against the oracle bit for bit, and the eight bands rendered
+    one by one tile the single-call image exactly (the decomposition changes nothing)"""
+    zyx, org, sp = S.make_cube(512, 512, 512)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        assert c.info()["quads"] and c.info()["positive"]
+        fp, fo = frames_pair(np.array([S.DEFAULT_POS], np.float32), 36.0, 36.0, 1024, 1024)
+        full = c.render(fp, 1024, 1024, trilinear=True)
+        tiled = np.zeros_like(full)
+        for b in range(8):
+            c.render(fp, 1024, 1024, trilinear=True, rows=(128 * b, 128 * (b + 1)), out=tiled)
+        assert_bit_exact(tiled, full, "eight row bands vs one call")
+        for rows in ((0, 24), (500, 524)):
+            want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, rows=rows, nthreads=16)
+            assert_bit_exact(full[:, rows[0]:rows[1]], want[:, rows[0]:rows[1]], f"rows {rows}")
+        near = c.render(fp, 1024, 1024, trilinear=False, rows=(500, 524))
+        want = O.orc_render_cube(zyx, org, sp, False, fo, 1024, 1024, rows=(500, 524), nthreads=16)
+        assert_bit_exact(near[:, 500:524], want[:, 500:524], "nearest neighbour band")
+        assert full.min() > 0
+    finally:
+        c.free()
+
+
 # ------------------------------------------------------------------ CMEM
 KA_DEFAULT = [((8, 4, 4), 0.0), ((4, 12, 10), 4.46853346e-06), ((3, 1.5, 1.2), 0.0), ((8, 10, 10), 8.15947317e-07),
               ((8, -10, -10), 8.15947317e-07), ((8, 10, -10), 8.15947317e-07)]
