@@ -57,6 +57,25 @@ def test_loader_blank_lines_between_slices(tmp_path, small_dat):
     assert_bit_exact(mir.export(), ref.export())
 
 
+@needs_ref
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_loader_worker_threads_do_not_change_the_result(tmp_path, monkeypatch, threads):
+    """the value section is converted on worker threads over line-aligned pieces; whatever the number of pieces
+    (more pieces than lines included), the reference's line-by-line state machine sees the same lines"""
+    zyx, org, sp = S.make_cube(37, 23, 19, lo=(-3.0, -1.5, -2.0), hi=(3.0, 1.5, 2.0))
+    path = tmp_path / "syn_37x23x19.dat"
+    S.write_dat(path, zyx, org, sp, per_line=7)
+    text = path.read_text().splitlines()
+    # ragged extras the reference tolerates: a blank line in the middle of the values, no newline at the very end
+    text.insert(len(text) // 2, "")
+    path.write_text("\n".join(text))
+    monkeypatch.setenv("BIRP_LOAD_THREADS", threads)
+    ref, mir = O.RefCube(path=path), M.Cube(path=path)
+    assert list(mir.info()[0]) == list(ref.info()[0])
+    assert_bit_exact(mir.info()[1], ref.info()[1], "origin / spacing")
+    assert_bit_exact(mir.export(), ref.export(), "slices")
+
+
 def test_loader_errors(tmp_path):
     with pytest.raises(ValueError):
         M.Cube(path=tmp_path / "missing.dat")
