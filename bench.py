@@ -81,15 +81,15 @@ def workload_config(wl, name, world):
 
 
 def measured_traffic(name, world, nframes_total):
-    """per-launch DRAM bytes of the dominant kernel, from the committed ncu capture (profiles/traffic.json);
-    only valid for the exact configuration that was profiled"""
+    """per-launch DRAM bytes (and executed warp instructions) of the dominant kernel, from the committed ncu
+    capture (profiles/traffic.json); only valid for the exact configuration that was profiled"""
     p = ROOT / "profiles" / "traffic.json"
     if not p.exists():
-        return None, None
+        return None, None, None
     t = json.loads(p.read_text()).get(name)
     if not t or t.get("n_gpus") != world or t.get("frames") != nframes_total:
-        return None, None
-    return t["bytes"], t["profile"]
+        return None, None, None
+    return t["bytes"], t["profile"], t.get("warp_instructions")
 
 
 def peaks():
@@ -583,7 +583,16 @@ def run_b200(args, wl, name):
         alg_bytes = valid_mine * bytes_per_sample + nmine * my_rows * W * 4
         achieved = alg_bytes / (float(kern_ms.mean()) / 1e3) / 1e9
 
-        traffic, traffic_src = measured_traffic(name, world, frames_total)
+        traffic, traffic_src, warp_inst = measured_traffic(name, world, frames_total)
+        clk = clocks.summary()
+        issue = None
+        if warp_inst and clk.get("sm_mhz"):
+            # what actually bounds the kernel: one warp instruction per scheduler per clock, 4 schedulers x 148 SMs
+            slots = 148 * 4 * float(clk["sm_mhz"]) * 1e6 * (float(kern_ms.mean()) / 1e3)
+            issue = {"warp_instructions_per_launch": int(warp_inst), "issue_slots_per_launch": slots,
+                     "frac": warp_inst / slots, "source": traffic_src,
+                     "note": "executed warp instructions (ncu, same launch configuration) / (592 schedulers x SM clock x "
+                             "kernel time): the fraction of the chip's issue slots the kernel fills"}
         l2_gather = None
         gp = ROOT / "profiles" / "r1d_gather_roofline.json"
         if gp.exists():
@@ -655,7 +664,7 @@ def run_b200(args, wl, name):
             "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
-                         "gather_microbench_GBs": l2_gather,
+                         "gather_microbench_GBs": l2_gather, "issue_slots": issue,
                          "note": "achieved = algorithmic bytes (32 B per live trilinear sample + 4 B per pixel) / "
                                  "kernel time; the kernel's real DRAM traffic is ~0.06 % of that (the cube is served "
                                  "from L1/L2), it is bound by instruction issue (86 % issue-active at 78 instructions "
