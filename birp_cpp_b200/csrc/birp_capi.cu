@@ -116,6 +116,8 @@ struct DeviceCtx {
     int* d_flags = nullptr;   // 4 ints of scratch for the upload-time analysis kernels
     // spacing bits + limit bits -> cheapest exact div_spacing mode (0, 1, 2), proven on this device
     std::map<std::pair<unsigned, unsigned>, int> divmode_cache;
+    // CMEM parameter record (raw bytes) -> may the region filter be used?  (self-test at first use, see cmem_flags)
+    std::map<std::string, bool> cmem_filter_ok;
     int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
     std::mutex mu;
 };
@@ -207,6 +209,44 @@ int read_status(DeviceCtx* c, cudaStream_t stream) {
                              "NaN sample coordinate inside the cube bounds test "
                              "(the reference throws std::out_of_range here)");
     }
+    return BIRP_OK;
+}
+
+int run_cmem_filter_selftest(DeviceCtx* c, const birp_cmem_params& params, long n, double out[3]) {
+    int rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
+    if (rc) return rc;
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_scratch);
+    BIRP_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), c->compute));
+    cudaError_t e = birp::launch_cmem_filter_selftest(params, n, d_out, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    unsigned long long h[3];
+    BIRP_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    std::memcpy(&out[0], &h[0], sizeof(double));
+    std::memcpy(&out[1], &h[1], sizeof(double));
+    out[2] = (double)h[2] / (double)n;
+    return BIRP_OK;
+}
+
+// The region filter of the CMEM kernel is exact as long as its fp32 radius estimates stay within their margin.
+// That is measured over 10^8 directions for the parameter sets of the tests; for ANY parameter set the same
+// self-test runs here once, at first use (4M directions, a few ms, cached per device): if the estimates use
+// more than a quarter of the margin the filter is switched off for that set (BIRP_CMEM_NO_FILTER, same results,
+// slower) -- the CMEM counterpart of the division / texture / quad self-checks at cube upload.
+int cmem_flags(DeviceCtx* c, const birp_cmem_params& params, int flags, int* out_flags) {
+    *out_flags = flags;
+    if (flags & (BIRP_CMEM_FAST | BIRP_CMEM_LIBM64 | BIRP_CMEM_NO_FILTER)) return BIRP_OK;
+    const std::string key(reinterpret_cast<const char*>(&params), sizeof(params));
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->cmem_filter_ok.find(key);
+    if (it == c->cmem_filter_ok.end()) {
+        double u[3];
+        int rc = run_cmem_filter_selftest(c, params, 1L << 22, u);
+        if (rc) return rc;
+        const bool ok = u[0] <= 0.25 && u[1] <= 0.25;  // (NaNs compare false: no filter)
+        it = c->cmem_filter_ok.emplace(key, ok).first;
+    }
+    if (!it->second) *out_flags |= BIRP_CMEM_NO_FILTER;
     return BIRP_OK;
 }
 
@@ -664,6 +704,8 @@ int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, i
     rc = get_ctx(&c);
     if (rc) return rc;
     const birp_cmem_params P = *params;
+    rc = cmem_flags(c, P, flags, &flags);
+    if (rc) return rc;
     return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
                        [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
                            cudaStream_t s) {
@@ -725,6 +767,8 @@ int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, i
     rc = get_ctx(&c);
     if (rc) return rc;
     const birp_cmem_params P = *params;
+    rc = cmem_flags(c, P, flags, &flags);
+    if (rc) return rc;
     return render_host(c, sw.frames_out, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
                        [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
                            cudaStream_t s) {
@@ -803,6 +847,8 @@ int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, i
     DeviceCtx* c;
     int rc = get_ctx(&c);
     if (rc) return rc;
+    rc = cmem_flags(c, *params, flags, &flags);
+    if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)n * 4);
     if (rc) return rc;
@@ -879,6 +925,8 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
     g.tile_w_log2 = c->tile_w_log2;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
+    rc = cmem_flags(c, *params, flags, &flags);  // (first use of a parameter set: a self-test on the library's stream)
+    if (rc) return rc;
     cudaError_t e = birp::launch_render_cmem(*params, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -959,19 +1007,7 @@ int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out
     int rc = get_ctx(&c);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
-    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
-    if (rc) return rc;
-    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_scratch);
-    BIRP_CUDA(cudaMemsetAsync(d_out, 0, 3 * sizeof(unsigned long long), c->compute));
-    cudaError_t e = birp::launch_cmem_filter_selftest(*params, n, d_out, c->compute);
-    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-    unsigned long long h[3];
-    BIRP_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->compute));
-    BIRP_CUDA(cudaStreamSynchronize(c->compute));
-    std::memcpy(&out[0], &h[0], sizeof(double));
-    std::memcpy(&out[1], &h[1], sizeof(double));
-    out[2] = (double)h[2] / (double)n;
-    return BIRP_OK;
+    return run_cmem_filter_selftest(c, *params, n, out);
 }
 
 unsigned long long birp_launch_count(void) { return birp::launch_count(); }

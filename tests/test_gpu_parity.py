@@ -541,7 +541,8 @@ def test_cmem_filter_margin(gpu, kw):
     assert out["trusted_fraction"] > 0.9
 
 
-@pytest.mark.parametrize("kw", CMEM_KW)
+@pytest.mark.parametrize("kw", CMEM_KW + [dict(dipole=0.5, p0=2.0, bs=20.0, A1=1e-5, ay_bs=1.5, az_bs=0.4),
+                                          dict(dipole=-0.4, p3=1, bs=6.0, alpha=0.5, beta=3.0)])
 def test_cmem_filter_is_invisible(gpu, kw):
     """filtered and unfiltered evaluation return the same bits: random positions, and 4000 rays sampled 2500
     times each so that every boundary is crossed at a resolution of 0.015 RE"""
