@@ -277,6 +277,7 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     size_t chunk = (size_t(16) << 20) / frame_px;  // 16 Mi pixels = 64 MiB per buffer
     // at least four chunks for a batch of many small frames, so that the D2H copy of one chunk (and the host
     // set-up of the next, for a sweep) overlaps the render of another
+    // (four: eight pieces of a 10 000-frame sweep were measured slower, 283.9 k against 288.8 k frames/s end to end)
     if ((size_t)nframes >= 256 && chunk > ((size_t)nframes + 3) / 4) chunk = ((size_t)nframes + 3) / 4;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)nframes) chunk = nframes;
