@@ -95,6 +95,7 @@ int set_error(int code, const char* fmt, ...) {
 struct RayTable {
     float* d_dist = nullptr;
     float ray_width = 0.f;
+    bool monotone = false;  // dist[] never decreases, or never increases (no NaN): RenderGeom::monotone_table
 };
 
 // Per-device state.  Created lazily on first use from the thread that owns the device.
@@ -165,6 +166,13 @@ int get_ray_table(DeviceCtx* c, int nsamples, int maxdist, cudaStream_t stream, 
     std::vector<float> h(nsamples);
     RayTable t;
     birp::host_ray_table(nsamples, maxdist, h.data(), &t.ray_width);
+    bool up = true, down = true;
+    for (int i = 0; i < nsamples; ++i) {
+        if (h[i] != h[i]) up = down = false;
+        if (i > 0 && !(h[i] >= h[i - 1])) up = false;
+        if (i > 0 && !(h[i] <= h[i - 1])) down = false;
+    }
+    t.monotone = up || down;
     BIRP_CUDA(cudaMalloc(&t.d_dist, sizeof(float) * nsamples));
     // synchronous copy from pageable memory: the table is ready for any stream afterwards
     BIRP_CUDA(cudaMemcpy(t.d_dist, h.data(), sizeof(float) * nsamples, cudaMemcpyHostToDevice));
@@ -323,6 +331,7 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             }
         }
         birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
+        g.monotone_table = table.monotone;
         g.tile_w_log2 = c->tile_w_log2;
         cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
         if (e != cudaSuccess)
@@ -889,6 +898,7 @@ int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_f
         if (rc) return rc;
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    g.monotone_table = table.monotone;
     g.tile_w_log2 = c->tile_w_log2;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
@@ -923,6 +933,7 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
         if (rc) return rc;
     }
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
+    g.monotone_table = table.monotone;
     g.tile_w_log2 = c->tile_w_log2;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;

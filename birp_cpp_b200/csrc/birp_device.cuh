@@ -42,6 +42,10 @@ struct CubeView {
     // (neighbours clamped at the last row / column, which no in-bounds sample reads): the four
     // corners of one z layer are ONE aligned 16-byte load.
     const float4* __restrict__ quad;
+    // quad + nx * ny, the z + 1 layer of the same cell: set by the march kernel itself (both bases are then
+    // plain registers and each corner address is one IMAD.WIDE)
+    const float4* __restrict__ quad_up;
+    int quad_bytes;  // 16, opaque to the compiler (likewise set by the kernel)
 };
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
@@ -135,8 +139,9 @@ __device__ __forceinline__ bool scale_fast(float s, float ray_width, double K, f
     const float p = __fmul_rn(s, ray_width);
     const double d = __dmul_rn((double)p, K);
     y = __double2float_rn(d);
-    const unsigned frac = (unsigned)__double2loint(d) & 0x1fffffffu;
-    const bool near_mid = (frac - (0x10000000u - 32u)) < 64u;
+    // (frac - (2^28 - 32)) mod 2^29 < 64 with frac = the 29 dropped bits: times 8, the modulus is the word size and
+    // the mask disappears (one multiply-add and one compare)
+    const bool near_mid = ((unsigned)__double2loint(d) * 8u - ((0x10000000u - 32u) << 3)) < 512u;
     bool exact = (y >= BIRP_SCALE_SAFE_LO) && (y < BIRP_SCALE_SAFE_HI);
     if (MAYBE_ZERO) exact = exact || (p == 0.f);  // (+-0) * C1 / C2 / C3 = +-0 = y
     return exact && !near_mid;
@@ -313,9 +318,9 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
         l110 = __ldg(p + row);
         l111 = __ldg(p + row + 1);
     } else if (FETCH == 4) {
-        const float4* __restrict__ q = c.quad + cell;
-        const float4 lo = __ldg(q);
-        const float4 hi = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(q) + c.slab16));
+        // address = uniform base + cell * 16, the 16 held in a register: one IMAD.WIDE per layer
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(c.quad) + (long long)cell * c.quad_bytes));
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(c.quad_up) + (long long)cell * c.quad_bytes));
         s000 = lo.x, l001 = lo.y, l010 = lo.z, l011 = lo.w;
         l100 = hi.x, l101 = hi.y, l110 = hi.z, l111 = hi.w;
     } else {

@@ -12,6 +12,9 @@ struct RenderGeom {
     int row_begin, row_end;  // rows [row_begin,row_end) of every frame are rendered
     int nsamples;
     float ray_width;
+    // the ray table never decreases (or never increases) from one step to the next: the cube kernel may then
+    // locate the end of a ray's hot run by bisection instead of testing every step (march_steps_span)
+    bool monotone_table = false;
     // angular size of one pixel step in x / y (any common unit) and an optional forced tile
     // width (log2, -1 = choose from the angles); only used to shape the per-warp pixel tile
     float pixel_angle_x = 0.f, pixel_angle_y = 0.f;

@@ -183,6 +183,16 @@ __device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& 
     return cube_hot_window(c, xi, yi, zi);
 }
 
+// the ingresses alone (SPAN kernels: the window was settled for the whole run)
+__device__ __forceinline__ void step_ingress_only(const CubeView& c, const RayState& r, unsigned sdist, float& xi,
+                                                  float& yi, float& zi) {
+    float tk;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
+    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
+    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
+    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
+}
+
 template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
 __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
                                                 float ray_width, double K, int* status, bool& alive) {
@@ -228,7 +238,68 @@ __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, 
     }
 }
 
+// The same march with the window test taken OUT of the step (SPAN kernels, the default).
+//
+// The ray table is monotone (checked on the host when the table is made: RayTable::monotone), and every
+// operation between a table entry and an ingress -- RN(d * t), RN(. + p), RN(. - o) -- is a correctly
+// rounded, hence monotone, function of t.  So each ingress is a monotone function of the step index, each
+// axis is inside its window [lo, l) over a contiguous range of steps, and so is the conjunction of the three:
+// the hot samples of a ray form ONE run of consecutive steps.  Once a step is found hot, the end of its run
+// is located by bisection with the very same window test (step_ingress; about log2(nsamples) evaluations per
+// ray instead of one per step), and the steps up to there are marched without any test: six compares and
+// their predicate chain leave the loop body.  Results are those of march_steps bit for bit -- the window test
+// only ever decided WHICH code evaluates a sample, and both codes return the reference's value.
 template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
+__device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
+                                                     float ray_width, double K, int* status, bool& alive) {
+    for (;;) {
+        asm volatile("" : "+r"(sdist));  // (keeps the outer loop separate from the hot one, see march_steps)
+        if (sdist == send) return sdist;
+        float xi, yi, zi;
+        if (step_ingress(c, r, sdist, xi, yi, zi)) {
+            // end of the hot run that starts here: every step in [sdist, lo) is hot, `hi` is cold or the end
+            unsigned lo = sdist + 4, hi = send;
+            while (lo < hi) {
+                const unsigned mid = lo + (((hi - lo) >> 3) << 2);
+                float ux, uy, uz;
+                if (step_ingress(c, r, mid, ux, uy, uz)) lo = mid + 4;
+                else hi = mid;
+            }
+            const unsigned hend = lo;
+            // (rotated like march_steps: the body evaluates the sample at `sdist` and the ingresses of the next)
+            bool more;
+            do {
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
+                float v;
+                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
+                step_ingress_only(c, r, sdist + 4, xi, yi, zi);
+                if (exact) {
+                    r.acc = __fadd_rn(r.acc, v);
+                    sdist += 4;
+                }
+                more = exact && (sdist != hend);
+            } while (more);
+            if (sdist == send) return sdist;
+        }
+        float tk;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
+        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
+        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
+        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
+        bool nan_index = false;
+        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+        if (nan_index) atomicOr(status, kStatusNanIndex);
+        s = scale_sample(s, ray_width);
+        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
+            alive = false;
+            return sdist;
+        }
+        r.acc = __fadd_rn(r.acc, s);
+        sdist += 4;
+    }
+}
+
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool SPAN>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
@@ -248,7 +319,15 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     pin_uniform(cc.sx), pin_uniform(cc.sy), pin_uniform(cc.sz);
     pin_uniform(ray_width);
     pin_uniform(K);
-    pin_uniform(cc.nx), pin_uniform(cc.ny), pin_uniform(cc.slab16);
+    pin_uniform(cc.nx), pin_uniform(cc.ny);
+    if (FETCH == 4) {
+        long long q0 = (long long)cc.quad, q1 = q0 + cc.slab16;
+        pin_uniform(q0), pin_uniform(q1);
+        cc.quad = reinterpret_cast<const float4*>(q0);
+        cc.quad_up = reinterpret_cast<const float4*>(q1);
+        cc.quad_bytes = 16;
+        asm volatile("" : "+r"(cc.quad_bytes));
+    }
 
     int f = 0, i = 0, j = 0;
     const bool owns_pixel = lane_ray(a, f, i, j);
@@ -267,8 +346,10 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     bool alive = owns_pixel;
     unsigned nlive4 = 0;  // 4 x the number of samples accumulated
     if (alive)
-        nlive4 = march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk, ray_width,
-                                                                  K, a.status, alive) - s_base;
+        nlive4 = (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk,
+                                                                              ray_width, K, a.status, alive)
+                       : march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk,
+                                                                         ray_width, K, a.status, alive)) - s_base;
     // marches longer than the staged table: refill it chunk by chunk (every thread of the CTA takes part)
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
@@ -276,8 +357,10 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
-            nlive4 += march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk, ray_width,
-                                                                       K, a.status, alive) - s_base;
+            nlive4 += (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk,
+                                                                                   ray_width, K, a.status, alive)
+                            : march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk,
+                                                                              ray_width, K, a.status, alive)) - s_base;
     }
     if (owns_pixel) {
         *pix = r.acc;
@@ -350,34 +433,44 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, int LERP, int FETCH>
+template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
-    march_cube_kernel<TRI, DIV, LERP, FETCH><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    march_cube_kernel<TRI, DIV, LERP, FETCH, SPAN><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
 }
 
+// `span`: the window test is taken out of the step (march_steps_span).  Built for the default corner fetch
+// (quads) and for nearest neighbour; the other fetch forms -- diagnostics, or a cube whose quad copy did not
+// fit -- keep the per-step test.
 template <int DIV, int LERP>
-cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, cudaStream_t stream) {
+cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, bool span,
+                              cudaStream_t stream) {
     switch (fetch) {
-        case 1: return launch_cube_variant<true, DIV, LERP, 1>(a, c, blocks, stream);
-        case 2: return launch_cube_variant<true, DIV, LERP, 2>(a, c, blocks, stream);
-        case 4: return launch_cube_variant<true, DIV, LERP, 4>(a, c, blocks, stream);
-        default: return launch_cube_variant<true, DIV, LERP, 0>(a, c, blocks, stream);
+        case 1: return launch_cube_variant<true, DIV, LERP, 1, false>(a, c, blocks, stream);
+        case 2: return launch_cube_variant<true, DIV, LERP, 2, false>(a, c, blocks, stream);
+        case 4:
+            if (span) return launch_cube_variant<true, DIV, LERP, 4, true>(a, c, blocks, stream);
+            return launch_cube_variant<true, DIV, LERP, 4, false>(a, c, blocks, stream);
+        default: return launch_cube_variant<true, DIV, LERP, 0, false>(a, c, blocks, stream);
     }
 }
 
 // lerp: 0 full std::lerp, 1 positive cube, 2 non-negative cube
 template <int DIV>
 cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, int lerp, int fetch,
-                            cudaStream_t stream) {
+                            bool span, cudaStream_t stream) {
     if (!tri) {
         // nearest neighbour interpolates nothing; the class only decides whether a zero product can be a sample
-        if (lerp == 1) return launch_cube_variant<false, DIV, 1, 0>(a, c, blocks, stream);
-        return launch_cube_variant<false, DIV, 0, 0>(a, c, blocks, stream);
+        if (lerp == 1) {
+            if (span) return launch_cube_variant<false, DIV, 1, 0, true>(a, c, blocks, stream);
+            return launch_cube_variant<false, DIV, 1, 0, false>(a, c, blocks, stream);
+        }
+        if (span) return launch_cube_variant<false, DIV, 0, 0, true>(a, c, blocks, stream);
+        return launch_cube_variant<false, DIV, 0, 0, false>(a, c, blocks, stream);
     }
-    if (lerp == 1) return launch_cube_fetch<DIV, 1>(a, c, blocks, fetch, stream);
-    if (lerp == 2) return launch_cube_fetch<DIV, 2>(a, c, blocks, fetch, stream);
-    return launch_cube_fetch<DIV, 0>(a, c, blocks, fetch, stream);
+    if (lerp == 1) return launch_cube_fetch<DIV, 1>(a, c, blocks, fetch, span, stream);
+    if (lerp == 2) return launch_cube_fetch<DIV, 2>(a, c, blocks, fetch, span, stream);
+    return launch_cube_fetch<DIV, 0>(a, c, blocks, fetch, span, stream);
 }
 
 // upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
@@ -697,11 +790,13 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         view.loy = view.lox;
         view.loz = view.lox;
     }
+    // the run-end search needs a monotone ray table (RenderGeom::monotone_table, checked where the table is made)
+    const bool span = g.monotone_table && !(flags & BIRP_WINDOW_PER_STEP);
     cudaError_t e;
     switch (divmode) {
-        case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, stream); break;
-        case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, stream); break;
-        default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, stream); break;
+        case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, span, stream); break;
+        case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, span, stream); break;
+        default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, span, stream); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e;

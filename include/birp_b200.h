@@ -67,9 +67,12 @@ enum {
     BIRP_CMEM_LIBM64 = 1024, /* CMEM only: the fp64-then-round evaluation through the CUDA fp64 math library
                                 instead of the library's own fp64 blocks (same results but for ~1e-8 of the
                                 calls; slower; kept as the cross-check of those blocks) */
-    BIRP_CMEM_NO_FILTER = 2048 /* CMEM only: evaluate both radii exactly for every sample instead of deciding
+    BIRP_CMEM_NO_FILTER = 2048, /* CMEM only: evaluate both radii exactly for every sample instead of deciding
                                   the region of samples far from a boundary with fp32 estimates (identical
                                   results; kept as the cross-check of the filter) */
+    BIRP_WINDOW_PER_STEP = 4096 /* DataCube only: test the cube bounds window at every step of the march instead
+                                   of locating the end of each ray's in-bounds run once by bisection over the
+                                   (monotone) ray table (identical results; kept as the cross-check) */
 };
 
 /* Opaque, device-resident emissivity grid (replaces DataCube::slices, include/DataCube.h:42). */

@@ -83,9 +83,9 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
     assert want[0].min() > 0 and want[2].max() == 0  # inside / outside the cube
 
 
-# corner fetch (default: two quad loads; tld4 + quad load (BIRP_FETCH=3 only); tld4 + 4 loads; two tld4; 8 loads)
-# x division x lerp flavour
-_FETCH = [0, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
+# corner fetch (default: two quad loads, end of the in-bounds run located once per ray; the same with the window
+# test in every step; tld4 + 4 loads; two tld4; 8 loads) x division x lerp flavour
+_FETCH = [0, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
 _DIV = [0, capi.DIV_TWO_STEP, capi.DIV_IEEE]
 _LERP = [0, capi.GENERAL_LERP]
 
