@@ -19,7 +19,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
 DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY, CMEM_LIBM64, CMEM_NO_FILTER = 8, 16, 32, 64, 128, 256, 512, 1024, 2048
-WINDOW_PER_STEP = 4096
+WINDOW_PER_STEP, NO_OCTS = 4096, 8192
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -69,6 +69,7 @@ SIGNATURES = {
     "birp_cube_upload_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _vp, C.POINTER(_vp)]),
     "birp_cube_free": (None, [_vp]),
     "birp_cube_info": (C.c_int, [_vp, _i32p]),
+    "birp_cube_has_oct_records": (C.c_int, [_vp, _i32p]),
     "birp_render_cube": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cube_sweep": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 + [_vp, _vp]),
@@ -259,8 +260,10 @@ class Cube:
     def info(self) -> dict:
         out = (C.c_int * 4)()
         _check(lib().birp_cube_info(self._h, out))
+        oct_ = (C.c_int * 1)()
+        _check(lib().birp_cube_has_oct_records(self._h, oct_))
         return {"divmode": int(out[0]), "positive": out[1] == 1, "nonnegative": out[1] in (1, 2),
-                "texture": bool(out[2]), "quads": bool(out[3])}
+                "texture": bool(out[2]), "quads": bool(out[3]), "octs": bool(oct_[0])}
 
     def sample(self, xyz, trilinear: bool) -> np.ndarray:
         xyz = _f32(xyz).reshape(-1, 3)

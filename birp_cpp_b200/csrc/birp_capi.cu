@@ -23,6 +23,7 @@ struct birp_cube {
     size_t voxels;
     cudaArray_t tex_array = nullptr;  // layered copy for the gather path (optional)
     float4* d_quad = nullptr;         // quad copy for the 16-byte corner fetch (optional)
+    float* d_oct = nullptr;           // oct copy for the 32-byte corner fetch (optional)
 };
 
 // smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
@@ -585,6 +586,30 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
             cube->d_quad = nullptr;
         }
     }
+    // Oct copy for the 32-byte corner fetch (the default of the trilinear kernel): 8x the grid.  Optional like
+    // the quads: when memory is short or the self-check fails the kernels use the quad copy.
+    v.oct = nullptr;
+    if (v.nx >= 2 && v.ny >= 2 && v.nz >= 2 && !getenv("BIRP_DISABLE_OCTS")) {
+        const size_t bytes = cube->voxels * 8 * sizeof(float);
+        size_t free_b = 0, total_b = 0;
+        cudaError_t oe = cudaMemGetInfo(&free_b, &total_b);
+        if (oe == cudaSuccess && free_b / 2 >= bytes) oe = cudaMalloc(&cube->d_oct, bytes);
+        else if (oe == cudaSuccess) oe = cudaErrorMemoryAllocation;
+        if (oe == cudaSuccess) {
+            cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute);
+            oe = birp::launch_pack_octs(v, cube->d_oct, c->d_flags, c->compute);
+            if (oe == cudaSuccess)
+                oe = cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute);
+            if (oe == cudaSuccess) oe = cudaStreamSynchronize(c->compute);
+            if (oe == cudaSuccess && c->h_status[0] == 0) v.oct = cube->d_oct;
+            *c->h_status = 0;
+        }
+        if (!v.oct) {
+            cudaGetLastError();
+            if (cube->d_oct) cudaFree(cube->d_oct);
+            cube->d_oct = nullptr;
+        }
+    }
     v.lox = first_cell_limit(sp[0]);
     v.loy = first_cell_limit(sp[1]);
     v.loz = first_cell_limit(sp[2]);
@@ -674,10 +699,17 @@ int birp_cube_info(const birp_cube* cube, int info[4]) {
     return BIRP_OK;
 }
 
+int birp_cube_has_oct_records(const birp_cube* cube, int* present) {
+    if (!cube || !present) return set_error(BIRP_ERR_ARG, "null pointer");
+    *present = cube->view.oct != nullptr;
+    return BIRP_OK;
+}
+
 static void destroy_cube(birp_cube* cube) {
     if (cube->view.tex) cudaDestroyTextureObject(cube->view.tex);
     if (cube->tex_array) cudaFreeArray(cube->tex_array);
     if (cube->d_quad) cudaFree(cube->d_quad);
+    if (cube->d_oct) cudaFree(cube->d_oct);
     cudaFree(cube->d_data);
     delete cube;
 }

@@ -46,7 +46,20 @@ struct CubeView {
     // plain registers and each corner address is one IMAD.WIDE)
     const float4* __restrict__ quad_up;
     int quad_bytes;  // 16, opaque to the compiler (likewise set by the kernel)
+    // "oct" copy of the grid, or nullptr: 32-byte records, oct[(z*ny + y)*nx + x] = the quad of layer z followed by
+    // the quad of layer z + 1 (clamped at the last layer like the quads at the last row / column): all eight
+    // corners of a cell are ONE aligned 32-byte load (LDG.256), i.e. one L1 request per sample instead of two.
+    // 8x the grid in device memory.
+    const float* __restrict__ oct;
 };
+
+// one 32-byte load through the read-only path (sm_100: LDG.E.256)
+__device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, float& a2, float& a3, float& b0, float& b1,
+                                         float& b2, float& b3) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+        : "l"(p));
+}
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
 // raw fp32 texels of the bilinear footprint, unfiltered (no 9-bit weights are involved -- the
@@ -266,8 +279,10 @@ __device__ __forceinline__ float lerp_nonneg(float a, float b, float t, float om
 //   0  eight global loads from the linear grid
 //   1  two texture gathers (tld4) on the layered copy
 //   2  lower z layer: one tld4; upper z layer: four global loads
-//   4  two 16-byte loads from the quad copy (default: fewest instructions -- one address, two loads --
-//      and fewest cache lines per warp request; measured fastest, profiles/README.md)
+//   4  two 16-byte loads from the quad copy (one address computation each, fewer cache lines per warp request
+//      than 4-byte loads)
+//   5  one 32-byte load (LDG.256) from the oct copy (default: one L1 request per sample instead of two, three
+//      instructions fewer; measured fastest, profiles/README.md)
 // (A form 3, tld4 for the lower layer + one quad load for the upper, was measured 9 % slower than 4.)
 // With the 4-byte forms the texture unit and the load/store unit each saturate their return path
 // into the register file first (profiles/r1d, r1e, r1g), hence the mixed form 2.
@@ -317,6 +332,9 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
         l101 = __ldg(p + 1);
         l110 = __ldg(p + row);
         l111 = __ldg(p + row + 1);
+    } else if (FETCH == 5) {
+        load_oct(reinterpret_cast<const char*>(c.oct) + (long long)cell * 32, s000, l001, l010, l011, l100, l101, l110,
+                 l111);
     } else if (FETCH == 4) {
         // address = uniform base + cell * 16, the 16 held in a register: one IMAD.WIDE per layer
         const float4 lo = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(c.quad) + (long long)cell * c.quad_bytes));

@@ -53,6 +53,8 @@ cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float
 cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaStream_t stream);
 // build the quad copy of the grid and compare every entry with the linear copy (*d_bad |= 1 on a mismatch)
 cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, cudaStream_t stream);
+// the same for the oct copy (32-byte records: both z layers of a cell)
+cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 

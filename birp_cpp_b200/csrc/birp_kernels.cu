@@ -127,7 +127,11 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
 // base address, 7 lerps, the fp64 scale, the fp32 accumulate.  Everything a sample outside
 // the window needs (dead ray, NaN coordinate) is on the cold side of one branch.
 #ifndef BIRP_CUBE_MIN_BLOCKS
-#define BIRP_CUBE_MIN_BLOCKS 6  // resident CTAs per SM the register allocation must allow (48 of 64 warps)
+// resident CTAs per SM the register allocation must allow: 8 = all 64 warps at 32 registers per thread.  The hot
+// loops of every variant fit into 32 registers without local-memory traffic (one instruction more than at 40
+// registers / 6 CTAs), and since v9 the kernel waits for L1 data more than for issue slots, so the extra warps pay:
+// orbit sweep 31.5 instead of 32.3 ms with quads, 29.2 instead of 30.3 ms with oct records.
+#define BIRP_CUBE_MIN_BLOCKS 8
 #endif
 
 struct RayState {
@@ -303,6 +307,9 @@ template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool SPAN>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
+    // (Sizing the buffer to the march -- 0.8 KB of dynamic shared memory for 200 samples, i.e. a 16 KB instead of
+    // a 100 KB shared-memory carve-out at 8 CTAs per SM and that much more L1 -- was measured: the trilinear
+    // kernel got 1.7 % SLOWER (29.68 vs 29.19 ms), nearest neighbour 1.4 % faster; the static table stays.)
     __shared__ float s_dist[kSmemDist + 1];  // + the look-ahead padding entry
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
     const int first_chunk = min(kSmemDist, a.nsamples);
@@ -327,6 +334,11 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         cc.quad_up = reinterpret_cast<const float4*>(q1);
         cc.quad_bytes = 16;
         asm volatile("" : "+r"(cc.quad_bytes));
+    }
+    if (FETCH == 5) {
+        long long q0 = (long long)cc.oct;
+        pin_uniform(q0);
+        cc.oct = reinterpret_cast<const float*>(q0);
     }
 
     int f = 0, i = 0, j = 0;
@@ -448,6 +460,7 @@ cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned bl
     switch (fetch) {
         case 1: return launch_cube_variant<true, DIV, LERP, 1, false>(a, c, blocks, stream);
         case 2: return launch_cube_variant<true, DIV, LERP, 2, false>(a, c, blocks, stream);
+        case 5: return launch_cube_variant<true, DIV, LERP, 5, true>(a, c, blocks, stream);
         case 4:
             if (span) return launch_cube_variant<true, DIV, LERP, 4, true>(a, c, blocks, stream);
             return launch_cube_variant<true, DIV, LERP, 4, false>(a, c, blocks, stream);
@@ -515,6 +528,46 @@ __global__ void __launch_bounds__(256) pack_quads_kernel(const float* __restrict
         const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
         quad[t] = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
     }
+}
+
+// oct copy: oct[t] = {quad of layer z, quad of layer z + 1 (clamped at the last layer)}, 32 bytes per cell
+__global__ void __launch_bounds__(256) pack_octs_kernel(const float* __restrict__ v, int nx, int ny, int nz,
+                                                        float4* __restrict__ oct) {
+    const size_t n = (size_t)nx * ny * nz;
+    const size_t slab = (size_t)nx * ny;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int y = (int)((t / nx) % ny);
+        const int z = (int)(t / slab);
+        const int dx = (x + 1 < nx) ? 1 : 0;
+        const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+        const size_t u = t + ((z + 1 < nz) ? slab : 0);
+        oct[2 * t] = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
+        oct[2 * t + 1] = make_float4(__ldg(v + u), __ldg(v + u + dx), __ldg(v + u + dy), __ldg(v + u + dy + dx));
+    }
+}
+
+// upload-time self-check of the oct copy, every entry, bit for bit, through the load the march uses
+__global__ void __launch_bounds__(256) verify_octs_kernel(const float* __restrict__ v, int nx, int ny, int nz,
+                                                          const float* __restrict__ oct, int* bad) {
+    const size_t n = (size_t)nx * ny * nz;
+    const size_t slab = (size_t)nx * ny;
+    bool ok = true;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int y = (int)((t / nx) % ny);
+        const int z = (int)(t / slab);
+        const int dx = (x + 1 < nx) ? 1 : 0;
+        const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+        const size_t u = t + ((z + 1 < nz) ? slab : 0);
+        float a0, a1, a2, a3, b0, b1, b2, b3;
+        load_oct(oct + 8 * t, a0, a1, a2, a3, b0, b1, b2, b3);
+        ok &= __float_as_uint(a0) == __float_as_uint(v[t]) && __float_as_uint(a1) == __float_as_uint(v[t + dx]) &&
+              __float_as_uint(a2) == __float_as_uint(v[t + dy]) && __float_as_uint(a3) == __float_as_uint(v[t + dy + dx]) &&
+              __float_as_uint(b0) == __float_as_uint(v[u]) && __float_as_uint(b1) == __float_as_uint(v[u + dx]) &&
+              __float_as_uint(b2) == __float_as_uint(v[u + dy]) && __float_as_uint(b3) == __float_as_uint(v[u + dy + dx]);
+    }
+    if (!ok) atomicOr(bad, 1);
 }
 
 // upload-time self-check of the quad copy, every entry, bit for bit, through the load the march uses
@@ -778,9 +831,14 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     // corner fetch of the trilinear kernel (cube_sample_hot): what the cube has, minus what the flags forbid
     const bool has_tex = cube.tex != 0 && !(flags & BIRP_NO_TEXTURE);
     const bool has_quad = cube.quad != nullptr && !(flags & BIRP_NO_QUADS);
+    // the run-end search needs a monotone ray table (RenderGeom::monotone_table, checked where the table is made)
+    const bool span = g.monotone_table && !(flags & BIRP_WINDOW_PER_STEP);
+    // (the oct kernel exists in the span form only)
+    const bool has_oct = cube.oct != nullptr && span && !(flags & (BIRP_NO_OCTS | BIRP_NO_QUADS | BIRP_QUADS_ONLY));
     int fetch = 0;
     if (tri) {
         if (has_tex && (flags & BIRP_TEXTURE_ONLY)) fetch = 1;
+        else if (has_oct) fetch = 5;
         else if (has_quad) fetch = 4;
         else if (has_tex) fetch = 2;
     }
@@ -790,8 +848,6 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         view.loy = view.lox;
         view.loz = view.lox;
     }
-    // the run-end search needs a monotone ray table (RenderGeom::monotone_table, checked where the table is made)
-    const bool span = g.monotone_table && !(flags & BIRP_WINDOW_PER_STEP);
     cudaError_t e;
     switch (divmode) {
         case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, span, stream); break;
@@ -813,6 +869,15 @@ cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     verify_quads_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_quad, d_bad);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cudaStream_t stream) {
+    pack_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, reinterpret_cast<float4*>(d_oct));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    verify_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_oct, d_bad);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }

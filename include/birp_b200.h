@@ -57,19 +57,23 @@ enum {
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
     BIRP_GENERAL_LERP = 32,  /* full std::lerp semantics even for an all-positive cube */
-    /* corner fetch of the trilinear kernel; default: one 16-byte load per z layer from the quad
-       copy of the grid */
+    /* corner fetch of the trilinear kernel; default: one 32-byte load per sample from the oct copy of
+       the grid (see BIRP_NO_OCTS), else one 16-byte load per z layer from the quad copy */
     BIRP_NO_TEXTURE = 64,    /* no texture gathers */
     BIRP_TEXTURE_ONLY = 128, /* all eight corners with two texture gathers */
     BIRP_NO_QUADS = 256,     /* do not use the quad copy (lower layer: one texture gather, upper layer:
                                 four global loads; with BIRP_NO_TEXTURE: eight global loads) */
-    BIRP_QUADS_ONLY = 512,   /* (the default when the quad copy exists; kept for explicit A/B runs) */
+    BIRP_QUADS_ONLY = 512,   /* the quad copy (two 16-byte loads) even when the oct copy exists */
     BIRP_CMEM_LIBM64 = 1024, /* CMEM only: the fp64-then-round evaluation through the CUDA fp64 math library
                                 instead of the library's own fp64 blocks (same results but for ~1e-8 of the
                                 calls; slower; kept as the cross-check of those blocks) */
     BIRP_CMEM_NO_FILTER = 2048, /* CMEM only: evaluate both radii exactly for every sample instead of deciding
                                   the region of samples far from a boundary with fp32 estimates (identical
                                   results; kept as the cross-check of the filter) */
+    BIRP_NO_OCTS = 8192,        /* DataCube, trilinear: do not use the oct copy of the grid (the default corner fetch:
+                                   ONE 32-byte load per sample from a copy that stores both z layers of every cell
+                                   together, 8x the grid in device memory); with this flag, two 16-byte loads from
+                                   the quad copy */
     BIRP_WINDOW_PER_STEP = 4096 /* DataCube only: test the cube bounds window at every step of the march instead
                                    of locating the end of each ray's in-bounds run once by bisection over the
                                    (monotone) ray table (identical results; kept as the cross-check) */
@@ -157,6 +161,8 @@ void birp_cube_free(birp_cube* cube);
    info[2] = 1 when the layered-texture copy exists and passed its gather self-check,
    info[3] = 1 when the quad copy (16-byte corner fetch) exists and passed its self-check */
 int birp_cube_info(const birp_cube* cube, int info[4]);
+/* *present = 1 when the oct copy (32-byte corner fetch) exists and passed its self-check */
+int birp_cube_has_oct_records(const birp_cube* cube, int* present);
 
 /* ------------------------------------------------------------------ the hot path, host buffers
  * frames: nframes records (host).  images: nframes*H*W floats (host), row j = image y, top row

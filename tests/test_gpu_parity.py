@@ -83,9 +83,9 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
     assert want[0].min() > 0 and want[2].max() == 0  # inside / outside the cube
 
 
-# corner fetch (default: two quad loads, end of the in-bounds run located once per ray; the same with the window
-# test in every step; tld4 + 4 loads; two tld4; 8 loads) x division x lerp flavour
-_FETCH = [0, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
+# corner fetch (default: one 32-byte oct load, end of the in-bounds run located once per ray; two quad loads, same
+# march; two quad loads with the window test in every step; tld4 + 4 loads; two tld4; 8 loads) x division x lerp flavour
+_FETCH = [0, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
 _DIV = [0, capi.DIV_TWO_STEP, capi.DIV_IEEE]
 _LERP = [0, capi.GENERAL_LERP]
 
@@ -108,6 +108,7 @@ def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
     assert a["positive"] and not b["positive"]
     assert a["texture"] and b["texture"], "layered-texture copy missing or failed its gather self-check"
     assert a["quads"] and b["quads"], "quad copy missing or failed its self-check"
+    assert a["octs"] and b["octs"], "oct copy missing or failed its self-check"
     assert a["divmode"] in (0, 1, 2) and a["divmode"] == b["divmode"]
     print("division variant proven exact for spacing 0.5:", a["divmode"])
     # awkward spacings: whatever variant is chosen, the renders must stay bit-exact
@@ -217,6 +218,33 @@ def test_cube_with_zero_regions_stays_bit_exact(gpu):
         c.free()
 
 
+def test_oct_record_fetch_on_a_small_grid(gpu):
+    """the default corner fetch (one 32-byte load from the oct copy, every record verified against the linear grid at
+    upload) on a small non-negative grid seen from inside: cameras in the first and in the last cells of every
+    axis, where the records' clamped neighbours sit; the quad and the 4-byte forms must agree with it"""
+    rng = np.random.default_rng(5)
+    zyx = rng.uniform(1e-7, 1e-5, size=(24, 26, 28)).astype(np.float32)
+    zyx[rng.random(zyx.shape) < 0.1] = 0.0
+    org = np.array([-2.0, 1.0, 0.5], np.float32)
+    sp = np.array([0.3137255, 0.25, 0.4], np.float32)
+    poses = np.array([(org[0] + fx * sp[0], org[1] + fy * sp[1], org[2] + fz * sp[2])
+                      for fx, fy, fz in ((0.5, 0.5, 0.5), (26.5, 24.5, 22.5), (13.0, 0.99999994, 11.0), (5.3, 12.2, 22.9))],
+                     np.float32)
+    c = capi.Cube(zyx, org, sp)
+    try:
+        assert c.info()["octs"] and c.info()["quads"] and c.info()["nonnegative"] and not c.info()["positive"]
+        for aim in (3.0, -30.0):
+            fq = capi.frames_for_poses(poses, aim, 60.0, 60.0, 40, 40)
+            fr = O.orc_frames(poses, aim, 60.0, 60.0, 40, 40)
+            want = O.orc_render_cube(zyx, org, sp, True, fr, 40, 40, nsamples=600, maxdist=12)
+            for fl in _FETCH + [capi.GENERAL_LERP]:
+                got = c.render(fq, 40, 40, nsamples=600, maxdist=12, trilinear=True, extra_flags=fl)
+                assert_bit_exact(got, want, f"small grid, aim={aim} flags={fl}")
+            assert want.max() > 0
+    finally:
+        c.free()
+
+
 def test_cube_beyond_texture_limits_uses_global_loads(gpu):
     """more z slices than a layered texture can hold (2048): no texture copy, the global-load kernel runs"""
     rng = np.random.default_rng(21)
@@ -225,11 +253,11 @@ def test_cube_beyond_texture_limits_uses_global_loads(gpu):
     sp = np.array([0.5, 0.5, 0.01], np.float32)
     c = capi.Cube(zyx, org, sp)
     try:
-        assert not c.info()["texture"] and c.info()["positive"] and c.info()["quads"]
+        assert not c.info()["texture"] and c.info()["positive"] and c.info()["quads"] and c.info()["octs"]
         fp, fo = frames_pair(np.array([(0.2, 0.3, 5.0), (0.5, 0.1, -3.0)], np.float32), 36.0, 36.0, 24, 24)
         want = O.orc_render_cube(zyx, org, sp, True, fo, 24, 24, nsamples=400, maxdist=30)
         assert want.max() > 0
-        for fl in (0, capi.NO_QUADS):  # two 16-byte quad loads / eight global loads
+        for fl in (0, capi.NO_OCTS, capi.NO_QUADS):  # one oct load / two quad loads / eight global loads
             got = c.render(fp, 24, 24, nsamples=400, maxdist=30, trilinear=True, extra_flags=fl)
             assert_bit_exact(got, want, f"flags={fl}")
     finally:
