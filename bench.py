@@ -667,8 +667,9 @@ def run_b200(args, wl, name):
                          "gather_microbench_GBs": l2_gather, "issue_slots": issue,
                          "note": "achieved = algorithmic bytes (32 B per live trilinear sample + 4 B per pixel) / "
                                  "kernel time; the kernel's real DRAM traffic is ~0.06 % of that (the cube is served "
-                                 "from L1/L2), it is bound by instruction issue (86 % issue-active at 78 instructions "
-                                 "per warp-sample) with the L1TEX return path behind (74 %): profiles/r1q_march_orbit_v8.md",
+                                 "from L1/L2), it is bound by instruction issue (88 % issue-active at 69 executed "
+                                 "instructions per warp-sample, all 64 warps resident) with the L1TEX path behind "
+                                 "(74 %): profiles/r1z_march_orbit_v9.md",
                          "kernel": ("march_cube_kernel<trilinear>" if trilinear else "march_cube_kernel<nearest>") if field == "cube" else "march_kernel<CmemField>",
                          "kernel_ms": float(kern_ms.mean()), "algorithmic_bytes_per_launch": int(alg_bytes),
                          "live_samples_per_launch": int(valid_mine)},
