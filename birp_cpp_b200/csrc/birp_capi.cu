@@ -26,50 +26,9 @@ struct birp_cube {
     float* d_oct = nullptr;           // oct copy for the 32-byte corner fetch (optional)
 };
 
-// smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
-// index = ingress / spacing in fp32 (src/DataCube.cpp:205-218).  The test is monotone in the
-// ingress, so a bisection over the fp32 bit patterns finds the exact threshold.
-static float bounds_limit(float spacing, int n) {
-    auto rejected = [&](unsigned bits) {
-        float xi;
-        std::memcpy(&xi, &bits, sizeof(xi));
-        const volatile float index = xi / spacing;
-        const volatile float plus1 = index + 1;
-        return plus1 >= (float)n;
-    };
-    unsigned lo = 0, hi = 0x7f800000u;  // +0 .. +inf (always rejected)
-    if (rejected(lo)) return 0.f;
-    while (hi - lo > 1) {
-        const unsigned mid = lo + (hi - lo) / 2;
-        if (rejected(mid)) hi = mid;
-        else lo = mid;
-    }
-    float out;
-    std::memcpy(&out, &hi, sizeof(out));
-    return out;
-}
-
-// smallest ingress whose quotient by the spacing is >= 1 (monotone, same bisection): below it a
-// sample sits in the first cell of the axis, where the interpolation weight can exceed 1 - 2^-23
-// and the hot path's clamp-free lerp is not proven (birp_device.cuh).  Never below 2^-100, the
-// lower end of the range div_spacing is verified on.
-static float first_cell_limit(float spacing) {
-    auto reached = [&](unsigned bits) {
-        float xi;
-        std::memcpy(&xi, &bits, sizeof(xi));
-        const volatile float index = xi / spacing;
-        return index >= 1.0f;
-    };
-    unsigned lo = 0, hi = 0x7f800000u;  // +0 (never: 0 / s = 0) .. +inf (always)
-    while (hi - lo > 1) {
-        const unsigned mid = lo + (hi - lo) / 2;
-        if (reached(mid)) hi = mid;
-        else lo = mid;
-    }
-    float out;
-    std::memcpy(&out, &hi, sizeof(out));
-    return out < BIRP_TINY_INGRESS ? BIRP_TINY_INGRESS : out;
-}
+static_assert(birp::kTinyIngress == BIRP_TINY_INGRESS, "birp_host.h and birp_device.cuh disagree on 2^-100");
+using birp::host_bounds_limit;
+using birp::host_first_cell_limit;
 
 namespace {
 
@@ -488,7 +447,7 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
     for (int a = 0; a < 3; ++a) {
         const volatile float r = 1.0f / sp[a];
         rcp[a] = r;
-        lim[a] = bounds_limit(sp[a], n[a]);
+        lim[a] = host_bounds_limit(sp[a], n[a]);
         unsigned sbits, lbits;
         std::memcpy(&sbits, &sp[a], 4);
         std::memcpy(&lbits, &lim[a], 4);
@@ -610,9 +569,9 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
             cube->d_oct = nullptr;
         }
     }
-    v.lox = first_cell_limit(sp[0]);
-    v.loy = first_cell_limit(sp[1]);
-    v.loz = first_cell_limit(sp[2]);
+    v.lox = host_first_cell_limit(sp[0]);
+    v.loy = host_first_cell_limit(sp[1]);
+    v.loz = host_first_cell_limit(sp[2]);
     v.rx = rcp[0];
     v.ry = rcp[1];
     v.rz = rcp[2];

@@ -56,9 +56,14 @@ struct CubeView {
 // one 32-byte load through the read-only path (sm_100: LDG.E.256)
 __device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, float& a2, float& a3, float& b0, float& b1,
                                          float& b2, float& b3) {
+#ifdef __CUDACC__
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
         : "l"(p));
+#else
+    const float* f = static_cast<const float*>(p);
+    a0 = f[0], a1 = f[1], a2 = f[2], a3 = f[3], b0 = f[4], b1 = f[5], b2 = f[6], b3 = f[7];
+#endif
 }
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
@@ -69,9 +74,13 @@ __device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, fl
 // Order: {T[y0+1][x0], T[y0+1][x0+1], T[y0][x0+1], T[y0][x0]}.
 __device__ __forceinline__ void gather4(cudaTextureObject_t tex, int layer, float u, float v, float& t01,
                                         float& t11, float& t10, float& t00) {
+#ifdef __CUDACC__
     asm("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %8}];"
         : "=f"(t01), "=f"(t11), "=f"(t10), "=f"(t00)
         : "l"(tex), "r"(layer), "f"(u), "f"(v), "f"(0.f));
+#else  // host build of this header (tests/cpp/device_on_host.cpp): the provider of that build
+    birp_host_gather4(tex, layer, u, v, t01, t11, t10, t00);
+#endif
 }
 
 
@@ -389,6 +398,172 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
 }
 
 // ---------------------------------------------------------------------------------
+// The march of one ray through the cube (called by march_cube_kernel, birp_kernels.cu; compiled for the host
+// as well by tests/cpp/device_on_host.cpp, where the whole control flow below runs against the oracle).
+// ---------------------------------------------------------------------------------
+constexpr int kSmemDist = 2048;  // ray-table entries kept in shared memory by the cube kernel (+ 1 of padding)
+
+// bits in the device status word
+constexpr int kStatusNanIndex = 1;  // BIRP_ERR_RANGE
+constexpr int kStatusSingular = 2;  // BIRP_ERR_SINGULAR (device frame setup)
+
+// entry of the staged ray table at 32-bit shared-window address `sdist` (one LDS; the host build reads its own
+// copy of the table at that byte offset)
+__device__ __forceinline__ float table_entry(unsigned sdist) {
+#ifdef __CUDACC__
+    float tk;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
+    return tk;
+#else
+    return birp_host_table_entry(sdist);
+#endif
+}
+
+struct RayState {
+    float dx, dy, dz;  // unit direction
+    float px, py, pz;  // camera position
+    float acc;         // pixel value so far
+};
+
+// March the steps whose distances sit in shared memory at byte addresses [sdist, send) (32-bit
+// shared-window addresses, advanced by 4 per step: one LDS + one IADD, no per-step index
+// arithmetic and no separate step counter).  Returns the address of the first step NOT
+// accumulated (send when the ray is still alive); `alive` is cleared when the ray ended.
+//
+// Control flow: the inner loop is the hot path only -- a sample inside the hot window whose
+// single-multiply scale is proven exact.  Anything else (ray leaving the cube, first cell of an
+// axis, NaN, a scale product next to a rounding midpoint, ...) BREAKS out of it; the lane then
+// waits at the loop exit for the rest of its warp, evaluates that one sample with the literal
+// transcription (cube_sample + scale_sample) and, if the ray lives on, re-enters the hot loop.
+// So the hot loop carries no reconvergence bookkeeping and no cold code; almost every break is a
+// ray ending, and a lane that re-enters alone (about 1 warp in 1000) costs its warp at most one
+// extra pass.
+// ingresses of the sample whose distance sits at shared address `sdist`, and whether it is hot
+__device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& r, unsigned sdist, float& xi, float& yi,
+                                             float& zi) {
+    const float tk = table_entry(sdist);
+    // Helper::MatrixScalarMultiply then "+ position" (src/Camera.cpp:183-189): two roundings,
+    // then DataCube::GetSample's `x - coords_x[0]` (src/DataCube.cpp:205)
+    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
+    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
+    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
+    return cube_hot_window(c, xi, yi, zi);
+}
+
+// the ingresses alone (SPAN kernels: the window was settled for the whole run)
+__device__ __forceinline__ void step_ingress_only(const CubeView& c, const RayState& r, unsigned sdist, float& xi,
+                                                  float& yi, float& zi) {
+    const float tk = table_entry(sdist);
+    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
+    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
+    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
+}
+
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
+__device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
+                                                float ray_width, double K, int* status, bool& alive) {
+    for (;;) {
+        // (an opaque statement of the OUTER loop only: keeps the compiler from merging the two loops
+        // into one, which would put the cold code and its reconvergence barrier back into every step)
+        asm volatile("" : "+r"(sdist));
+        if (sdist == send) return sdist;
+        float xi, yi, zi;
+        if (step_ingress(c, r, sdist, xi, yi, zi)) {
+            // Hot loop, rotated by hand: the body evaluates the sample at `sdist` (known to be in the
+            // window) AND the window test of the next one, so a step has a single branch.  (The table
+            // has one padding entry: the look-ahead of the last step reads it and discards the result.)
+            bool more;
+            do {
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
+                float v;
+                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
+                const bool hot_next = step_ingress(c, r, sdist + 4, xi, yi, zi);
+                if (exact) {
+                    r.acc = __fadd_rn(r.acc, v);
+                    sdist += 4;
+                }
+                more = exact && hot_next && (sdist != send);
+            } while (more);
+            if (sdist == send) return sdist;
+        }
+        const float tk = table_entry(sdist);
+        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
+        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
+        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
+        bool nan_index = false;
+        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+        if (nan_index) atomicOr(status, kStatusNanIndex);
+        s = scale_sample(s, ray_width);
+        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
+            alive = false;
+            return sdist;
+        }
+        r.acc = __fadd_rn(r.acc, s);
+        sdist += 4;
+    }
+}
+
+// The same march with the window test taken OUT of the step (SPAN kernels, the default).
+//
+// The ray table is monotone (checked on the host when the table is made: RayTable::monotone), and every
+// operation between a table entry and an ingress -- RN(d * t), RN(. + p), RN(. - o) -- is a correctly
+// rounded, hence monotone, function of t.  So each ingress is a monotone function of the step index, each
+// axis is inside its window [lo, l) over a contiguous range of steps, and so is the conjunction of the three:
+// the hot samples of a ray form ONE run of consecutive steps.  Once a step is found hot, the end of its run
+// is located by bisection with the very same window test (step_ingress; about log2(nsamples) evaluations per
+// ray instead of one per step), and the steps up to there are marched without any test: six compares and
+// their predicate chain leave the loop body.  Results are those of march_steps bit for bit -- the window test
+// only ever decided WHICH code evaluates a sample, and both codes return the reference's value.
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
+__device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
+                                                     float ray_width, double K, int* status, bool& alive) {
+    for (;;) {
+        asm volatile("" : "+r"(sdist));  // (keeps the outer loop separate from the hot one, see march_steps)
+        if (sdist == send) return sdist;
+        float xi, yi, zi;
+        if (step_ingress(c, r, sdist, xi, yi, zi)) {
+            // end of the hot run that starts here: every step in [sdist, lo) is hot, `hi` is cold or the end
+            unsigned lo = sdist + 4, hi = send;
+            while (lo < hi) {
+                const unsigned mid = lo + (((hi - lo) >> 3) << 2);
+                float ux, uy, uz;
+                if (step_ingress(c, r, mid, ux, uy, uz)) lo = mid + 4;
+                else hi = mid;
+            }
+            const unsigned hend = lo;
+            // (rotated like march_steps: the body evaluates the sample at `sdist` and the ingresses of the next)
+            bool more;
+            do {
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
+                float v;
+                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
+                step_ingress_only(c, r, sdist + 4, xi, yi, zi);
+                if (exact) {
+                    r.acc = __fadd_rn(r.acc, v);
+                    sdist += 4;
+                }
+                more = exact && (sdist != hend);
+            } while (more);
+            if (sdist == send) return sdist;
+        }
+        const float tk = table_entry(sdist);
+        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
+        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
+        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
+        bool nan_index = false;
+        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
+        if (nan_index) atomicOr(status, kStatusNanIndex);
+        s = scale_sample(s, ray_width);
+        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
+            alive = false;
+            return sdist;
+        }
+        r.acc = __fadd_rn(r.acc, s);
+        sdist += 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // CMEM::GetSample, src/Cmem.cpp:117-186, with ShueCoords :224-246, LinScaled :188-222
 // and ShueModel :280-288.
 //
@@ -445,6 +620,24 @@ struct CmemDev {
     int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
     int q_nonpositive;                     // p2 * charlie <= 0: the cusp term of LinScaled can only lower the radius
 };
+
+// Sample-independent CMEM terms, with the host libm the reference itself calls.
+inline CmemDev make_cmem_dev(const birp_cmem_params& P) {
+    CmemDev D;
+    D.P = P;
+    D.cos_tn = cosf(P.theta_n);
+    D.sin_tn = sinf(P.theta_n);
+    D.cos_ts = cosf(P.theta_s);
+    D.sin_ts = sinf(P.theta_s);
+    const volatile float p0r0 = P.p0 * P.r0_lin, p2c = P.p2 * P.charlie, p3dn = P.p3 * P.dn, p3ds = P.p3 * P.ds;
+    D.p0r0 = p0r0;
+    D.p2c = p2c;
+    D.p3dn = p3dn;
+    D.p3ds = p3ds;
+    D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
+    D.q_nonpositive = (p2c <= 0.f) ? 1 : 0;
+    return D;
+}
 
 template <bool PRECISE>
 __device__ __forceinline__ float cmem_sample(const CmemDev& D, float x, float y, float z) {
@@ -660,9 +853,13 @@ __device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float
 
 // hardware approximations for the estimate (MUFU.SQRT / MUFU.RCP, ~2^-22 relative)
 __device__ __forceinline__ float est_sqrt(float x) {
+#ifdef __CUDACC__
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#else
+    return sqrtf(x);
+#endif
 }
 // acos(x), |error| < 1e-7: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) (a0 + a1 x + ... + a7 x^7) on [0, 1]
 // (|eps| <= 2e-8), mirrored for x < 0

@@ -84,6 +84,51 @@ int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_d
     return status.load();
 }
 
+// smallest ingress >= 0 that the reference's bounds test `index + 1 >= size` rejects, where
+// index = ingress / spacing in fp32 (src/DataCube.cpp:205-218).  The test is monotone in the
+// ingress, so a bisection over the fp32 bit patterns finds the exact threshold.
+float host_bounds_limit(float spacing, int n) {
+    auto rejected = [&](unsigned bits) {
+        float xi;
+        std::memcpy(&xi, &bits, sizeof(xi));
+        const volatile float index = xi / spacing;
+        const volatile float plus1 = index + 1;
+        return plus1 >= (float)n;
+    };
+    unsigned lo = 0, hi = 0x7f800000u;  // +0 .. +inf (always rejected)
+    if (rejected(lo)) return 0.f;
+    while (hi - lo > 1) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (rejected(mid)) hi = mid;
+        else lo = mid;
+    }
+    float out;
+    std::memcpy(&out, &hi, sizeof(out));
+    return out;
+}
+
+// smallest ingress whose quotient by the spacing is >= 1 (monotone, same bisection): below it a
+// sample sits in the first cell of the axis, where the interpolation weight can exceed 1 - 2^-23
+// and the hot path's clamp-free lerp is not proven (birp_device.cuh).  Never below 2^-100, the
+// lower end of the range div_spacing is verified on.
+float host_first_cell_limit(float spacing) {
+    auto reached = [&](unsigned bits) {
+        float xi;
+        std::memcpy(&xi, &bits, sizeof(xi));
+        const volatile float index = xi / spacing;
+        return index >= 1.0f;
+    };
+    unsigned lo = 0, hi = 0x7f800000u;  // +0 (never: 0 / s = 0) .. +inf (always)
+    while (hi - lo > 1) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (reached(mid)) hi = mid;
+        else lo = mid;
+    }
+    float out;
+    std::memcpy(&out, &hi, sizeof(out));
+    return out < kTinyIngress ? kTinyIngress : out;
+}
+
 void host_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out) {
     float d0 = 0.f, d1 = 0.f;
     for (int i = 0; i < nsamples; ++i) {

@@ -23,10 +23,6 @@ struct RenderGeom {
     long long out_frame_offset = 0, out_frame_stride = 1;
 };
 
-// bits in the device status word
-constexpr int kStatusNanIndex = 1;  // BIRP_ERR_RANGE
-constexpr int kStatusSingular = 2;  // BIRP_ERR_SINGULAR (device frame setup)
-
 cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames, const RenderGeom& g,
                                const float* d_dist, int flags, float* d_images,
                                unsigned long long* d_valid, int* d_status, cudaStream_t stream);

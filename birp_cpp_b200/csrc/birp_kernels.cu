@@ -27,7 +27,6 @@ namespace {
 std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kSmemDist = 2048;  // ray-table entries kept in shared memory by the cube kernel
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
 struct MarchArgs {
@@ -57,24 +56,6 @@ struct CmemField {
         return cmem_sample_mode<MODE>(D, x, y, z);
     }
 };
-
-// Sample-independent CMEM terms, with the host libm the reference itself calls.
-CmemDev make_cmem_dev(const birp_cmem_params& P) {
-    CmemDev D;
-    D.P = P;
-    D.cos_tn = cosf(P.theta_n);
-    D.sin_tn = sinf(P.theta_n);
-    D.cos_ts = cosf(P.theta_s);
-    D.sin_ts = sinf(P.theta_s);
-    const volatile float p0r0 = P.p0 * P.r0_lin, p2c = P.p2 * P.charlie, p3dn = P.p3 * P.dn, p3ds = P.p3 * P.ds;
-    D.p0r0 = p0r0;
-    D.p2c = p2c;
-    D.p3dn = p3dn;
-    D.p3ds = p3ds;
-    D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
-    D.q_nonpositive = (p2c <= 0.f) ? 1 : 0;
-    return D;
-}
 
 // Which ray this lane owns; false when the lane falls outside the image / row band.
 __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int& j) {
@@ -134,25 +115,6 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
 #define BIRP_CUBE_MIN_BLOCKS 8
 #endif
 
-struct RayState {
-    float dx, dy, dz;  // unit direction
-    float px, py, pz;  // camera position
-    float acc;         // pixel value so far
-};
-
-// March the steps whose distances sit in shared memory at byte addresses [sdist, send) (32-bit
-// shared-window addresses, advanced by 4 per step: one LDS + one IADD, no per-step index
-// arithmetic and no separate step counter).  Returns the address of the first step NOT
-// accumulated (send when the ray is still alive); `alive` is cleared when the ray ended.
-//
-// Control flow: the inner loop is the hot path only -- a sample inside the hot window whose
-// single-multiply scale is proven exact.  Anything else (ray leaving the cube, first cell of an
-// axis, NaN, a scale product next to a rounding midpoint, ...) BREAKS out of it; the lane then
-// waits at the loop exit for the rest of its warp, evaluates that one sample with the literal
-// transcription (cube_sample + scale_sample) and, if the ray lives on, re-enters the hot loop.
-// So the hot loop carries no reconvergence bookkeeping and no cold code; almost every break is a
-// ray ending, and a lane that re-enters alone (about 1 warp in 1000) costs its warp at most one
-// extra pass.
 // Make a warp-uniform kernel parameter opaque to ptxas AND keep it in a uniform register: the OR-reduction
 // of 32 identical words is the word itself, the result of redux.sync lives in the uniform register
 // file, and ptxas cannot rematerialise it from the constant bank inside the march loop (left to
@@ -172,135 +134,6 @@ __device__ __forceinline__ void pin_uniform(double& v) {
     long long b = __double_as_longlong(v);
     pin_uniform(b);
     v = __longlong_as_double(b);
-}
-
-// ingresses of the sample whose distance sits at shared address `sdist`, and whether it is hot
-__device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& r, unsigned sdist, float& xi, float& yi,
-                                             float& zi) {
-    float tk;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
-    // Helper::MatrixScalarMultiply then "+ position" (src/Camera.cpp:183-189): two roundings,
-    // then DataCube::GetSample's `x - coords_x[0]` (src/DataCube.cpp:205)
-    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
-    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
-    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
-    return cube_hot_window(c, xi, yi, zi);
-}
-
-// the ingresses alone (SPAN kernels: the window was settled for the whole run)
-__device__ __forceinline__ void step_ingress_only(const CubeView& c, const RayState& r, unsigned sdist, float& xi,
-                                                  float& yi, float& zi) {
-    float tk;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
-    xi = __fsub_rn(__fadd_rn(__fmul_rn(r.dx, tk), r.px), c.ox);
-    yi = __fsub_rn(__fadd_rn(__fmul_rn(r.dy, tk), r.py), c.oy);
-    zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
-}
-
-template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
-__device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
-                                                float ray_width, double K, int* status, bool& alive) {
-    for (;;) {
-        // (an opaque statement of the OUTER loop only: keeps the compiler from merging the two loops
-        // into one, which would put the cold code and its reconvergence barrier back into every step)
-        asm volatile("" : "+r"(sdist));
-        if (sdist == send) return sdist;
-        float xi, yi, zi;
-        if (step_ingress(c, r, sdist, xi, yi, zi)) {
-            // Hot loop, rotated by hand: the body evaluates the sample at `sdist` (known to be in the
-            // window) AND the window test of the next one, so a step has a single branch.  (The table
-            // has one padding entry: the look-ahead of the last step reads it and discards the result.)
-            bool more;
-            do {
-                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
-                float v;
-                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
-                const bool hot_next = step_ingress(c, r, sdist + 4, xi, yi, zi);
-                if (exact) {
-                    r.acc = __fadd_rn(r.acc, v);
-                    sdist += 4;
-                }
-                more = exact && hot_next && (sdist != send);
-            } while (more);
-            if (sdist == send) return sdist;
-        }
-        float tk;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
-        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
-        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
-        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
-        bool nan_index = false;
-        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-        if (nan_index) atomicOr(status, kStatusNanIndex);
-        s = scale_sample(s, ray_width);
-        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
-            alive = false;
-            return sdist;
-        }
-        r.acc = __fadd_rn(r.acc, s);
-        sdist += 4;
-    }
-}
-
-// The same march with the window test taken OUT of the step (SPAN kernels, the default).
-//
-// The ray table is monotone (checked on the host when the table is made: RayTable::monotone), and every
-// operation between a table entry and an ingress -- RN(d * t), RN(. + p), RN(. - o) -- is a correctly
-// rounded, hence monotone, function of t.  So each ingress is a monotone function of the step index, each
-// axis is inside its window [lo, l) over a contiguous range of steps, and so is the conjunction of the three:
-// the hot samples of a ray form ONE run of consecutive steps.  Once a step is found hot, the end of its run
-// is located by bisection with the very same window test (step_ingress; about log2(nsamples) evaluations per
-// ray instead of one per step), and the steps up to there are marched without any test: six compares and
-// their predicate chain leave the loop body.  Results are those of march_steps bit for bit -- the window test
-// only ever decided WHICH code evaluates a sample, and both codes return the reference's value.
-template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
-__device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
-                                                     float ray_width, double K, int* status, bool& alive) {
-    for (;;) {
-        asm volatile("" : "+r"(sdist));  // (keeps the outer loop separate from the hot one, see march_steps)
-        if (sdist == send) return sdist;
-        float xi, yi, zi;
-        if (step_ingress(c, r, sdist, xi, yi, zi)) {
-            // end of the hot run that starts here: every step in [sdist, lo) is hot, `hi` is cold or the end
-            unsigned lo = sdist + 4, hi = send;
-            while (lo < hi) {
-                const unsigned mid = lo + (((hi - lo) >> 3) << 2);
-                float ux, uy, uz;
-                if (step_ingress(c, r, mid, ux, uy, uz)) lo = mid + 4;
-                else hi = mid;
-            }
-            const unsigned hend = lo;
-            // (rotated like march_steps: the body evaluates the sample at `sdist` and the ingresses of the next)
-            bool more;
-            do {
-                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
-                float v;
-                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
-                step_ingress_only(c, r, sdist + 4, xi, yi, zi);
-                if (exact) {
-                    r.acc = __fadd_rn(r.acc, v);
-                    sdist += 4;
-                }
-                more = exact && (sdist != hend);
-            } while (more);
-            if (sdist == send) return sdist;
-        }
-        float tk;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(tk) : "r"(sdist));
-        const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
-        const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
-        const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
-        bool nan_index = false;
-        float s = cube_sample<TRILINEAR>(c, x, y, z, nan_index);
-        if (nan_index) atomicOr(status, kStatusNanIndex);
-        s = scale_sample(s, ray_width);
-        if (s < 0.f) {  // src/Camera.cpp:207-210: the rest of the ray is ignored
-            alive = false;
-            return sdist;
-        }
-        r.acc = __fadd_rn(r.acc, s);
-        sdist += 4;
-    }
 }
 
 template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool SPAN>

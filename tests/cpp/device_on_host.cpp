@@ -1,0 +1,378 @@
+// TEST INFRASTRUCTURE: the device code of the march kernels (birp_cpp_b200/csrc/birp_device.cuh) compiled for the
+// HOST by g++ through tests/cpp/cuda_on_host.h, behind a small C interface for tests/test_device_on_host.py.
+//
+// What runs here is the source the GPU runs: cube_sample / cube_sample_hot (every lerp class, division mode and
+// corner fetch), scale_fast / scale_sample, march_steps and march_steps_span (the hot loop with its cold exits,
+// the bisection for the end of a ray's hot run), pixel_direction, and the CMEM samplers with their fp64 blocks.
+// What is restated here, because it lives in the __global__ kernels (birp_kernels.cu: march_cube_kernel,
+// pack_quads_kernel, pack_octs_kernel, scan_positive_kernel) or in the upload code (birp_capi.cu: finish_cube), is
+// the glue around it: the per-ray prologue, the staging of the ray table in chunks of kSmemDist entries, the
+// copies of the grid, the classification of the voxels.  The window limits come from the product's own host
+// functions (birp_hostmath.cpp, linked from libbirp_b200.so).
+//
+// This is a checker of device SOURCE on the CPU; it is not a product path (nothing in birp_cpp_b200/ uses it).
+#include "cuda_on_host.h"
+
+#include <thread>
+#include <vector>
+
+#include "../../birp_cpp_b200/csrc/birp_device.cuh"
+#include "../../birp_cpp_b200/csrc/birp_host.h"
+
+namespace {
+
+thread_local const float* t_table = nullptr;
+
+struct HostTex {
+    const float* v;
+    int nx, ny;
+};
+
+struct HostCube {
+    birp::CubeView view;
+    std::vector<float> grid, quad, oct;
+    HostTex tex;
+};
+
+}  // namespace
+
+float birp_host_table_entry(unsigned sdist) {
+    float t;
+    std::memcpy(&t, reinterpret_cast<const char*>(t_table) + sdist, sizeof(t));
+    return t;
+}
+
+// tld4 on the layered texture: the four texels around the footprint centre (u, v) = (x0 + 1, y0 + 1) of layer `layer`
+void birp_host_gather4(cudaTextureObject_t tex, int layer, float u, float v, float& t01, float& t11, float& t10,
+                       float& t00) {
+    const HostTex* t = reinterpret_cast<const HostTex*>(tex);
+    const int x0 = (int)u - 1, y0 = (int)v - 1;
+    const float* p = t->v + ((size_t)layer * t->ny + y0) * t->nx + x0;
+    t00 = p[0];
+    t10 = p[1];
+    t01 = p[t->nx];
+    t11 = p[t->nx + 1];
+}
+
+namespace {
+
+using birp::CubeView;
+using birp::RayState;
+
+// march_cube_kernel's body for one ray (birp_kernels.cu), with the table staged chunk by chunk
+template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
+void march_ray(const CubeView& c, const birp_frame& fr, int i, int j, int W, int H,
+               const std::vector<std::vector<float>>& staged, const std::vector<int>& chunk_len, float ray_width,
+               int accumulate, float* pix, unsigned long long* valid, int* status) {
+    RayState r;
+    birp::pixel_direction(fr, i, j, (float)W, (float)H, r.dx, r.dy, r.dz);
+    r.px = fr.pos[0];
+    r.py = fr.pos[1];
+    r.pz = fr.pos[2];
+    r.acc = accumulate ? *pix : 0.f;
+    bool alive = true;
+    unsigned nlive4 = 0;
+    const double K = BIRP_SCALE_K;
+    for (size_t k = 0; k < staged.size() && alive; ++k) {
+        t_table = staged[k].data();
+        const unsigned send = 4u * (unsigned)chunk_len[k];
+        nlive4 += SPAN ? birp::march_steps_span<TRI, DIV, LERP, FETCH>(c, r, 0u, send, ray_width, K, status, alive)
+                       : birp::march_steps<TRI, DIV, LERP, FETCH>(c, r, 0u, send, ray_width, K, status, alive);
+    }
+    *pix = r.acc;
+    *valid += nlive4 >> 2;
+}
+
+struct RenderJob {
+    const HostCube* cube;
+    const birp_frame* frames;
+    int nframes, W, H, nsamples, maxdist, accumulate;
+    float* images;
+    unsigned long long valid = 0;
+    int status = 0;
+};
+
+template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
+void render_variant(RenderJob& job) {
+    CubeView c = job.cube->view;
+    if (!TRI) c.lox = c.loy = c.loz = BIRP_TINY_INGRESS;  // launch_render_cube: nearest keeps the first cells hot
+    std::vector<float> dist(job.nsamples);
+    float ray_width = 0.f;
+    birp::host_ray_table(job.nsamples, job.maxdist, dist.data(), &ray_width);
+    // the shared-memory table as the CTA sees it in each chunk: kSmemDist entries + the look-ahead padding entry;
+    // a shorter last chunk leaves the tail of the previous one in place
+    std::vector<std::vector<float>> staged;
+    std::vector<int> chunk_len;
+    std::vector<float> cur(birp::kSmemDist + 1, 0.f);
+    for (int base = 0; base < job.nsamples; base += birp::kSmemDist) {
+        const int n = std::min(birp::kSmemDist, job.nsamples - base);
+        std::copy(dist.begin() + base, dist.begin() + base + n, cur.begin());
+        staged.push_back(cur);
+        chunk_len.push_back(n);
+    }
+    const int nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<unsigned long long> valid(nthreads, 0);
+    std::vector<int> status(nthreads, 0);
+    std::vector<std::thread> pool;
+    const long rows_total = (long)job.nframes * job.H;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            for (long row = t; row < rows_total; row += nthreads) {
+                const int f = (int)(row / job.H), j = (int)(row % job.H);
+                for (int i = 0; i < job.W; ++i)
+                    march_ray<TRI, DIV, LERP, FETCH, SPAN>(c, job.frames[f], i, j, job.W, job.H, staged, chunk_len, ray_width,
+                                                           job.accumulate,
+                                                           job.images + ((size_t)f * job.H + j) * job.W + i, &valid[t],
+                                                           &status[t]);
+            }
+        });
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < nthreads; ++t) job.valid += valid[t], job.status |= status[t];
+}
+
+template <bool TRI, int DIV, int LERP, int FETCH>
+void render_span(RenderJob& job, int span) {
+    if (span) render_variant<TRI, DIV, LERP, FETCH, true>(job);
+    else render_variant<TRI, DIV, LERP, FETCH, false>(job);
+}
+
+template <bool TRI, int DIV, int LERP>
+bool render_fetch(RenderJob& job, int fetch, int span) {
+    if (!TRI) return render_span<false, DIV, LERP, 0>(job, span), true;
+    switch (fetch) {
+        case 0: render_span<TRI, DIV, LERP, 0>(job, span); return true;
+        case 1: render_span<TRI, DIV, LERP, 1>(job, span); return true;
+        case 2: render_span<TRI, DIV, LERP, 2>(job, span); return true;
+        case 4: render_span<TRI, DIV, LERP, 4>(job, span); return true;
+        case 5: render_span<TRI, DIV, LERP, 5>(job, span); return true;
+    }
+    return false;
+}
+
+template <bool TRI, int DIV>
+bool render_lerp(RenderJob& job, int lerp, int fetch, int span) {
+    switch (lerp) {
+        case 0: return render_fetch<TRI, DIV, 0>(job, fetch, span);
+        case 1: return render_fetch<TRI, DIV, 1>(job, fetch, span);
+        case 2: return render_fetch<TRI, DIV, 2>(job, fetch, span);
+    }
+    return false;
+}
+
+template <bool TRI>
+bool render_div(RenderJob& job, int div, int lerp, int fetch, int span) {
+    switch (div) {
+        case 0: return render_lerp<TRI, 0>(job, lerp, fetch, span);
+        case 1: return render_lerp<TRI, 1>(job, lerp, fetch, span);
+        case 2: return render_lerp<TRI, 2>(job, lerp, fetch, span);
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+// The device view of a cube as birp_capi.cu (finish_cube) and the pack / scan kernels build it.  `divmode` is the
+// caller's choice: on the GPU it comes from the exhaustive device-side comparison with IEEE division, which
+// doh_verify_div repeats here on a stride of the ingresses.
+void* doh_cube_create(const float* zyx, int nx, int ny, int nz, const float origin[3], const float spacing[3],
+                      int divmode) {
+    HostCube* h = new HostCube();
+    const size_t n = (size_t)nx * ny * nz, slab = (size_t)nx * ny;
+    h->grid.assign(zyx, zyx + n);
+    CubeView& v = h->view;
+    std::memset(&v, 0, sizeof(v));
+    v.v = h->grid.data();
+    v.nx = nx, v.ny = ny, v.nz = nz;
+    v.slab = nx * ny;
+    v.slab16 = 16LL * nx * ny;
+    v.fnx = (float)nx, v.fny = (float)ny, v.fnz = (float)nz;
+    v.ox = origin[0], v.oy = origin[1], v.oz = origin[2];
+    v.sx = spacing[0], v.sy = spacing[1], v.sz = spacing[2];
+    const volatile float rx = 1.0f / spacing[0], ry = 1.0f / spacing[1], rz = 1.0f / spacing[2];
+    v.rx = rx, v.ry = ry, v.rz = rz;
+    v.lx = birp::host_bounds_limit(spacing[0], nx);
+    v.ly = birp::host_bounds_limit(spacing[1], ny);
+    v.lz = birp::host_bounds_limit(spacing[2], nz);
+    v.lox = birp::host_first_cell_limit(spacing[0]);
+    v.loy = birp::host_first_cell_limit(spacing[1]);
+    v.loz = birp::host_first_cell_limit(spacing[2]);
+    v.divmode = divmode;
+    int bad = 0;  // scan_positive_kernel
+    for (size_t t = 0; t < n; ++t) {
+        const float x = zyx[t];
+        const bool pos = x > 0.f && x < CUDART_INF_F;
+        uint32_t bits;
+        std::memcpy(&bits, &x, 4);
+        if (!pos) bad |= 1;
+        if (!pos && bits != 0u) bad |= 2;
+    }
+    v.positive = (bad == 0) ? 1 : ((bad & 2) == 0) ? 2 : 0;
+    h->tex = HostTex{h->grid.data(), nx, ny};
+    v.tex = reinterpret_cast<cudaTextureObject_t>(&h->tex);
+    if (nx >= 2 && ny >= 2 && nz >= 2) {
+        h->quad.resize(4 * n);  // pack_quads_kernel
+        h->oct.resize(8 * n);   // pack_octs_kernel
+        for (size_t t = 0; t < n; ++t) {
+            const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / slab);
+            const int dx = (x + 1 < nx) ? 1 : 0;
+            const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+            const size_t u = t + ((z + 1 < nz) ? slab : 0);
+            const float lo[4] = {zyx[t], zyx[t + dx], zyx[t + dy], zyx[t + dy + dx]};
+            const float hi[4] = {zyx[u], zyx[u + dx], zyx[u + dy], zyx[u + dy + dx]};
+            std::memcpy(&h->quad[4 * t], lo, sizeof(lo));
+            std::memcpy(&h->oct[8 * t], lo, sizeof(lo));
+            std::memcpy(&h->oct[8 * t + 4], hi, sizeof(hi));
+        }
+        v.quad = reinterpret_cast<const float4*>(h->quad.data());
+        v.quad_up = v.quad + slab;  // (march_cube_kernel sets these three itself)
+        v.quad_bytes = 16;
+        v.oct = h->oct.data();
+    }
+    return h;
+}
+
+void doh_cube_free(void* cube) { delete static_cast<HostCube*>(cube); }
+
+// 1 all voxels finite and > 0, 2 finite and > 0 or +0, 0 otherwise
+int doh_cube_class(const void* cube) { return static_cast<const HostCube*>(cube)->view.positive; }
+
+void doh_cube_window(const void* cube, float lo[3], float hi[3]) {
+    const CubeView& v = static_cast<const HostCube*>(cube)->view;
+    lo[0] = v.lox, lo[1] = v.loy, lo[2] = v.loz;
+    hi[0] = v.lx, hi[1] = v.ly, hi[2] = v.lz;
+}
+
+// verify_div_kernel on every `stride`-th fp32 ingress of the hot window of one axis: bad[m] = 1 when
+// div_spacing<m> ever differs from IEEE division
+void doh_verify_div(float s, int n, unsigned stride, int bad[2]) {
+    const volatile float rv = 1.0f / s;
+    const float r = rv;
+    const float limit = birp::host_bounds_limit(s, n);
+    uint32_t first, last;
+    const float tiny = BIRP_TINY_INGRESS;
+    std::memcpy(&first, &tiny, 4);
+    std::memcpy(&last, &limit, 4);
+    bad[0] = bad[1] = 0;
+    for (uint64_t u = first; u < last; u += stride) {
+        const uint32_t b = (uint32_t)u;
+        float a;
+        std::memcpy(&a, &b, 4);
+        const float want = a / s;
+        if (birp::div_spacing<0>(a, s, r) != want) bad[0] = 1;
+        if (birp::div_spacing<1>(a, s, r) != want) bad[1] = 1;
+    }
+}
+
+// DataCube::GetSample on points: literal device transcription (cube_sample) and, where the point lies in the hot
+// window, the hot form (cube_sample_hot<lerp class, divmode, fetch>); hot_mask[p] says which points were hot.
+// lerp < 0: the class of the cube.
+int doh_sample_cube(const void* cube, int trilinear, int lerp, int fetch, const float* xyz, long n, float* literal,
+                    float* hot, unsigned char* hot_mask) {
+    const HostCube* h = static_cast<const HostCube*>(cube);
+    CubeView c = h->view;
+    if (!trilinear) c.lox = c.loy = c.loz = BIRP_TINY_INGRESS;
+    if (lerp < 0) lerp = c.positive;
+    int status = 0;
+    for (long p = 0; p < n; ++p) {
+        const float x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+        bool nan_index = false;
+        literal[p] = trilinear ? birp::cube_sample<true>(c, x, y, z, nan_index) : birp::cube_sample<false>(c, x, y, z, nan_index);
+        if (nan_index) status |= birp::kStatusNanIndex;
+        const float xi = x - c.ox, yi = y - c.oy, zi = z - c.oz;
+        const bool is_hot = birp::cube_hot_window(c, xi, yi, zi);
+        hot_mask[p] = is_hot;
+        hot[p] = 0.f;
+        if (!is_hot) continue;
+#define DOH_HOT(TRI, DIV, LERP, FETCH) hot[p] = birp::cube_sample_hot<TRI, DIV, LERP, FETCH>(c, xi, yi, zi)
+#define DOH_HOT_FETCH(TRI, DIV, LERP)              \
+    switch (TRI ? fetch : 0) {                     \
+        case 1: DOH_HOT(TRI, DIV, LERP, 1); break; \
+        case 2: DOH_HOT(TRI, DIV, LERP, 2); break; \
+        case 4: DOH_HOT(TRI, DIV, LERP, 4); break; \
+        case 5: DOH_HOT(TRI, DIV, LERP, 5); break; \
+        default: DOH_HOT(TRI, DIV, LERP, 0); break; \
+    }
+#define DOH_HOT_LERP(TRI, DIV)                        \
+    switch (lerp) {                                   \
+        case 1: DOH_HOT_FETCH(TRI, DIV, 1); break;    \
+        case 2: DOH_HOT_FETCH(TRI, DIV, 2); break;    \
+        default: DOH_HOT_FETCH(TRI, DIV, 0); break;   \
+    }
+#define DOH_HOT_DIV(TRI)                         \
+    switch (c.divmode) {                         \
+        case 0: DOH_HOT_LERP(TRI, 0); break;     \
+        case 1: DOH_HOT_LERP(TRI, 1); break;     \
+        default: DOH_HOT_LERP(TRI, 2); break;    \
+    }
+        if (trilinear) { DOH_HOT_DIV(true) } else { DOH_HOT_DIV(false) }
+    }
+    return status;
+}
+
+// march_cube_kernel over whole frames.  lerp / divmode < 0: the cube's.  Returns -1 for an unknown variant, else
+// the status word (kStatusNanIndex when the reference would throw).
+int doh_render_cube(const void* cube, int trilinear, int lerp, int divmode, int fetch, int span, const birp_frame* frames,
+                    int nframes, int W, int H, int nsamples, int maxdist, int accumulate, float* images,
+                    unsigned long long* valid) {
+    const HostCube* h = static_cast<const HostCube*>(cube);
+    RenderJob job{h, frames, nframes, W, H, nsamples, maxdist, accumulate, images};
+    if (lerp < 0) lerp = h->view.positive;
+    if (divmode < 0) divmode = h->view.divmode;
+    if (!trilinear && lerp == 2) lerp = 0;  // launch_cube_div: nearest has the classes 1 and 0 only
+    const bool ok = trilinear ? render_div<true>(job, divmode, lerp, fetch, span) : render_div<false>(job, divmode, lerp, 0, span);
+    if (!ok) return -1;
+    if (valid) *valid = job.valid;
+    return job.status;
+}
+
+// the exactness flag of the hot loop's scale: for each s, y = scale_fast's value, exact = its claim, chain = the
+// literal three-step fp64 chain of the reference (scale_sample_chain), full = scale_sample (what the cold path uses)
+void doh_scale(const float* s, long n, float ray_width, int maybe_zero, float* y, unsigned char* exact, float* chain,
+               float* full) {
+    for (long p = 0; p < n; ++p) {
+        float v;
+        const bool e = maybe_zero ? birp::scale_fast<true>(s[p], ray_width, BIRP_SCALE_K, v)
+                                  : birp::scale_fast<false>(s[p], ray_width, BIRP_SCALE_K, v);
+        y[p] = v;
+        exact[p] = e;
+        chain[p] = birp::scale_sample_chain(s[p] * ray_width);
+        full[p] = birp::scale_sample(s[p], ray_width);
+    }
+}
+
+// the seven-lerp building blocks on raw operands: std::lerp transcription, positive form, non-negative form
+void doh_lerps(const float* a, const float* b, const float* t, long n, float* ref, float* positive, float* nonneg) {
+    for (long p = 0; p < n; ++p) {
+        ref[p] = birp::lerp_ref(a[p], b[p], t[p]);
+        positive[p] = a[p] + t[p] * (b[p] - a[p]);
+        nonneg[p] = birp::lerp_nonneg(a[p], b[p], t[p], 1.f - t[p]);
+    }
+}
+
+// CMEM::GetSample on points: mode 0 fp32 libm calls, 1 fp64 libm rounded once, 2 the library's own fp64 blocks,
+// 3 the same behind the region filter (the default of the kernels)
+void doh_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, int mode, float* out) {
+    const birp::CmemDev D = birp::make_cmem_dev(*params);
+    for (long p = 0; p < n; ++p) {
+        const float x = xyz[3 * p], y = xyz[3 * p + 1], z = xyz[3 * p + 2];
+        switch (mode) {
+            case 0: out[p] = birp::cmem_sample_mode<0>(D, x, y, z); break;
+            case 1: out[p] = birp::cmem_sample_mode<1>(D, x, y, z); break;
+            case 2: out[p] = birp::cmem_sample_mode<2>(D, x, y, z); break;
+            default: out[p] = birp::cmem_sample_mode<3>(D, x, y, z); break;
+        }
+    }
+}
+
+// which samples the region filter decides on its own (1) and which go to the full evaluation (0)
+void doh_cmem_filter_decides(const birp_cmem_params* params, const float* xyz, long n, unsigned char* decided) {
+    const birp::CmemDev D = birp::make_cmem_dev(*params);
+    for (long p = 0; p < n; ++p) {
+        float value;
+        decided[p] = birp::cmem_try_filter(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], value);
+    }
+}
+
+}  // extern "C"
