@@ -148,7 +148,11 @@ int birp_cmem_init(int has_v, const int v[3], int has_b, const int b[3], float d
 
 /* ------------------------------------------------------------------ cube residency */
 /* zyx: nz*ny*nx floats, x fastest (slices[z][y][x], include/DataCube.h:42).
-   origin = coords_{x,y,z}[0], spacing = DataCube::spacing (src/DataCube.cpp:140-191). */
+   origin = coords_{x,y,z}[0], spacing = DataCube::spacing (src/DataCube.cpp:140-191).
+   Besides the linear grid the upload builds three verified copies for the trilinear corner fetch -- oct records
+   (8x the grid), quads (4x), a layered texture (1x) -- each only when it fits into half of the free device
+   memory and passes its self-check; BIRP_DISABLE_OCTS / BIRP_DISABLE_QUADS / BIRP_DISABLE_TEXTURE in the
+   environment skip a copy (the kernels fall back to the next fetch form, results are identical). */
 int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origin[3],
                      const float spacing[3], birp_cube** out);
 /* same, the grid already in device memory (e.g. after an NCCL broadcast); copied */
