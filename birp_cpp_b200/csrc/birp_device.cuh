@@ -425,19 +425,6 @@ struct RayState {
     float acc;         // pixel value so far
 };
 
-// March the steps whose distances sit in shared memory at byte addresses [sdist, send) (32-bit
-// shared-window addresses, advanced by 4 per step: one LDS + one IADD, no per-step index
-// arithmetic and no separate step counter).  Returns the address of the first step NOT
-// accumulated (send when the ray is still alive); `alive` is cleared when the ray ended.
-//
-// Control flow: the inner loop is the hot path only -- a sample inside the hot window whose
-// single-multiply scale is proven exact.  Anything else (ray leaving the cube, first cell of an
-// axis, NaN, a scale product next to a rounding midpoint, ...) BREAKS out of it; the lane then
-// waits at the loop exit for the rest of its warp, evaluates that one sample with the literal
-// transcription (cube_sample + scale_sample) and, if the ray lives on, re-enters the hot loop.
-// So the hot loop carries no reconvergence bookkeeping and no cold code; almost every break is a
-// ray ending, and a lane that re-enters alone (about 1 warp in 1000) costs its warp at most one
-// extra pass.
 // ingresses of the sample whose distance sits at shared address `sdist`, and whether it is hot
 __device__ __forceinline__ bool step_ingress(const CubeView& c, const RayState& r, unsigned sdist, float& xi, float& yi,
                                              float& zi) {
@@ -459,6 +446,19 @@ __device__ __forceinline__ void step_ingress_only(const CubeView& c, const RaySt
     zi = __fsub_rn(__fadd_rn(__fmul_rn(r.dz, tk), r.pz), c.oz);
 }
 
+// March the steps whose distances sit in shared memory at byte addresses [sdist, send) (32-bit
+// shared-window addresses, advanced by 4 per step: one LDS + one IADD, no per-step index
+// arithmetic and no separate step counter).  Returns the address of the first step NOT
+// accumulated (send when the ray is still alive); `alive` is cleared when the ray ended.
+//
+// Control flow: the inner loop is the hot path only -- a sample inside the hot window whose
+// single-multiply scale is proven exact.  Anything else (ray leaving the cube, first cell of an
+// axis, NaN, a scale product next to a rounding midpoint, ...) BREAKS out of it; the lane then
+// waits at the loop exit for the rest of its warp, evaluates that one sample with the literal
+// transcription (cube_sample + scale_sample) and, if the ray lives on, re-enters the hot loop.
+// So the hot loop carries no reconvergence bookkeeping and no cold code; almost every break is a
+// ray ending, and a lane that re-enters alone (about 1 warp in 1000) costs its warp at most one
+// extra pass.
 template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
 __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
                                                 float ray_width, double K, int* status, bool& alive) {

@@ -7,7 +7,12 @@
 //   accumulate_kernel     K4: scale + terminate + accumulate of host-sampled values
 //                         (reference src/Camera.cpp:201-223), for user-defined Space classes.
 //   sample_*_kernel, ray_directions_kernel: Space::GetSample on points; the ray generator alone.
-//   verify_div_kernel, verify_gather_kernel, scan_positive_kernel: upload-time proofs / analysis.
+//   verify_div_kernel, verify_gather_kernel, scan_positive_kernel: upload-time proofs / analysis;
+//   pack_octs_kernel / pack_quads_kernel (+ verify_*): the copies of the grid for the corner fetch.
+//
+// What a single ray does -- samplers, lerps, scale, the march loops (march_steps, march_steps_span) -- lives in
+// birp_device.cuh, which also compiles for the host (tests/cpp/device_on_host.cpp checks it against the oracle
+// on the CPU); this file holds the __global__ kernels and their launches.
 //
 // Work decomposition of the march kernels: one warp owns a 4x8 / 8x4 pixel tile of one frame, one
 // lane per ray.  The 32 rays of a tile stay within a few voxels of one another along the whole
