@@ -630,6 +630,18 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.sx = spacing[0];
     v.sy = spacing[1];
     v.sz = spacing[2];
+    // value range of the grid, for BIRP_LEAN_MARCH (host uploads of at most 2^24 voxels; only read for a cube the
+    // device scan classifies as positive, so NaNs -- which these comparisons skip -- cannot matter)
+    v.vmin = v.vmax = 0.f;
+    if (!src_on_device && voxels <= (size_t(1) << 24)) {
+        float lo = src[0], hi = src[0];
+        for (size_t i = 1; i < voxels; ++i) {
+            lo = src[i] < lo ? src[i] : lo;
+            hi = src[i] > hi ? src[i] : hi;
+        }
+        v.vmin = lo;
+        v.vmax = hi;
+    }
     rc = finish_cube(c, cube);
     if (rc) {
         destroy_cube(cube);

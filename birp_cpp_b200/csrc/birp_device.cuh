@@ -51,6 +51,9 @@ struct CubeView {
     // corners of a cell are ONE aligned 32-byte load (LDG.256), i.e. one L1 request per sample instead of two.
     // 8x the grid in device memory.
     const float* __restrict__ oct;
+    // smallest / largest voxel of a cube uploaded from the host (0, 0: unknown); every sample interpolated from a
+    // positive cube lies between them (BIRP_LEAN_MARCH; host-side use only)
+    float vmin, vmax;
 };
 
 // one 32-byte load through the read-only path (sm_100: LDG.E.256)
@@ -156,7 +159,10 @@ __device__ __forceinline__ float scale_sample(float s, float ray_width) {
 #define BIRP_SCALE_K (BIRP_SCALE_C1 / BIRP_SCALE_C2 / BIRP_SCALE_C3)
 #define BIRP_SCALE_SAFE_LO 7.52316384526264e-37f  /* 2^-120 */
 #define BIRP_SCALE_SAFE_HI 1.329227995784916e+36f /* 2^120 */
-template <bool MAYBE_ZERO>
+// RANGE_SAFE: the caller has shown on the host that every sample the hot path can produce scales into
+// [2^-120, 2^120) (launch_render_cube: a positive cube's samples lie in [vmin, vmax], the scale is monotone), so
+// the range test is dropped and only the midpoint test remains.
+template <bool MAYBE_ZERO, bool RANGE_SAFE = false>
 __device__ __forceinline__ bool scale_fast(float s, float ray_width, double K, float& y) {
     const float p = __fmul_rn(s, ray_width);
     const double d = __dmul_rn((double)p, K);
@@ -164,6 +170,7 @@ __device__ __forceinline__ bool scale_fast(float s, float ray_width, double K, f
     // (frac - (2^28 - 32)) mod 2^29 < 64 with frac = the 29 dropped bits: times 8, the modulus is the word size and
     // the mask disappears (one multiply-add and one compare)
     const bool near_mid = ((unsigned)__double2loint(d) * 8u - ((0x10000000u - 32u) << 3)) < 512u;
+    if (RANGE_SAFE) return !near_mid;
     bool exact = (y >= BIRP_SCALE_SAFE_LO) && (y < BIRP_SCALE_SAFE_HI);
     if (MAYBE_ZERO) exact = exact || (p == 0.f);  // (+-0) * C1 / C2 / C3 = +-0 = y
     return exact && !near_mid;
@@ -312,7 +319,10 @@ __device__ __forceinline__ bool cube_hot_window(const CubeView& c, float xi, flo
 }
 
 // (2) the sample, for ingresses inside the window
-template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
+// FIDX (grids of at most 2^24 voxels, trilinear): the cell index is computed in fp32 -- floor of the three
+// indices (FRND), two FFMA, ONE float->int conversion -- instead of three conversions each way and two IMAD.
+// Every intermediate is an integer below 2^24, so the fp32 arithmetic is exact and the cell is the same.
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool FIDX = false>
 __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, float yi, float zi) {
     const float fx = div_spacing<DIVMODE>(xi, c.sx, c.rx);
     const float fy = div_spacing<DIVMODE>(yi, c.sy, c.ry);
@@ -320,12 +330,20 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
     const int row = c.nx;
     const int slab = c.slab;
     // indices are in [1, n-1): truncation == floor == the reference's (int) cast
-    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-    const int cell = (z0 * c.ny + y0) * row + x0;
-    if (!TRILINEAR) return __ldg(c.v + cell);
-    // One float->int conversion per axis (XU pipe) and the int->float back on the ALU pipe;
-    // the fractions are exact.
-    const float gx = (float)x0, gy = (float)y0, gz = (float)z0;
+    int x0, y0, z0, cell;
+    float gx, gy, gz;
+    if (FIDX && TRILINEAR) {
+        gx = truncf(fx), gy = truncf(fy), gz = truncf(fz);
+        cell = (int)__fmaf_rn(__fmaf_rn(gz, c.fny, gy), c.fnx, gx);
+        x0 = y0 = z0 = 0;  // (only the texture forms use them)
+    } else {
+        x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+        cell = (z0 * c.ny + y0) * row + x0;
+        if (!TRILINEAR) return __ldg(c.v + cell);
+        // One float->int conversion per axis (XU pipe) and the int->float back on the ALU pipe;
+        // the fractions are exact.
+        gx = (float)x0, gy = (float)y0, gz = (float)z0;
+    }
     const float tx = __fsub_rn(fx, gx);
     const float ty = __fsub_rn(fy, gy);
     const float tz = __fsub_rn(fz, gz);
@@ -514,7 +532,10 @@ __device__ __forceinline__ unsigned march_steps(const CubeView& c, RayState& r, 
 // ray instead of one per step), and the steps up to there are marched without any test: six compares and
 // their predicate chain leave the loop body.  Results are those of march_steps bit for bit -- the window test
 // only ever decided WHICH code evaluates a sample, and both codes return the reference's value.
-template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH>
+// LEAN (BIRP_LEAN_MARCH, positive cubes of at most 2^24 voxels whose value range was checked on the host): the
+// hot loop uses the fp32 cell index and the scale without its range test (cube_sample_hot<FIDX>,
+// scale_fast<RANGE_SAFE>): four instructions fewer per sample.
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool LEAN = false>
 __device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState& r, unsigned sdist, const unsigned send,
                                                      float ray_width, double K, int* status, bool& alive) {
     for (;;) {
@@ -534,9 +555,9 @@ __device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState
             // (rotated like march_steps: the body evaluates the sample at `sdist` and the ingresses of the next)
             bool more;
             do {
-                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH>(c, xi, yi, zi);
+                const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH, LEAN>(c, xi, yi, zi);
                 float v;
-                const bool exact = scale_fast<LERP != 1>(s, ray_width, K, v);
+                const bool exact = scale_fast<LERP != 1, LEAN>(s, ray_width, K, v);
                 step_ingress_only(c, r, sdist + 4, xi, yi, zi);
                 if (exact) {
                     r.acc = __fadd_rn(r.acc, v);

@@ -141,7 +141,8 @@ __device__ __forceinline__ void pin_uniform(double& v) {
     v = __longlong_as_double(b);
 }
 
-template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, bool SPAN>
+// SPAN: 0 the window test in every step (march_steps), 1 run end by bisection (march_steps_span), 2 the same, lean
+template <bool TRILINEAR, int DIVMODE, int LERP, int FETCH, int SPAN>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cube_kernel(const MarchArgs a, const CubeView c) {
     // The ray table is staged through shared memory in chunks of kSmemDist distances (one chunk
     // for any march up to 2048 samples), so a step costs one LDS instead of a global load.
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         cc.quad_bytes = 16;
         asm volatile("" : "+r"(cc.quad_bytes));
     }
+    if (SPAN == 2) pin_uniform(cc.fnx), pin_uniform(cc.fny);
     if (FETCH == 5) {
         long long q0 = (long long)cc.oct;
         pin_uniform(q0);
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     bool alive = owns_pixel;
     unsigned nlive4 = 0;  // 4 x the number of samples accumulated
     if (alive)
-        nlive4 = (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk,
-                                                                              ray_width, K, a.status, alive)
+        nlive4 = (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH, SPAN == 2>(cc, r, s_base, s_base + 4u * first_chunk,
+                                                                                         ray_width, K, a.status, alive)
                        : march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * first_chunk,
                                                                          ray_width, K, a.status, alive)) - s_base;
     // marches longer than the staged table: refill it chunk by chunk (every thread of the CTA takes part)
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
-            nlive4 += (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk,
-                                                                                   ray_width, K, a.status, alive)
+            nlive4 += (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH, SPAN == 2>(cc, r, s_base, s_base + 4u * chunk,
+                                                                                              ray_width, K, a.status, alive)
                             : march_steps<TRILINEAR, DIVMODE, LERP, FETCH>(cc, r, s_base, s_base + 4u * chunk,
                                                                               ray_width, K, a.status, alive)) - s_base;
     }
@@ -283,7 +285,7 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     return cudaGetLastError();
 }
 
-template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
+template <bool TRI, int DIV, int LERP, int FETCH, int SPAN>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
     march_cube_kernel<TRI, DIV, LERP, FETCH, SPAN><<<blocks, kBlockThreads, 0, stream>>>(a, c);
     return cudaGetLastError();
@@ -293,35 +295,37 @@ cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned 
 // (quads) and for nearest neighbour; the other fetch forms -- diagnostics, or a cube whose quad copy did not
 // fit -- keep the per-step test.
 template <int DIV, int LERP>
-cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, bool span,
+cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned blocks, int fetch, bool span, bool lean,
                               cudaStream_t stream) {
     switch (fetch) {
-        case 1: return launch_cube_variant<true, DIV, LERP, 1, false>(a, c, blocks, stream);
-        case 2: return launch_cube_variant<true, DIV, LERP, 2, false>(a, c, blocks, stream);
-        case 5: return launch_cube_variant<true, DIV, LERP, 5, true>(a, c, blocks, stream);
+        case 1: return launch_cube_variant<true, DIV, LERP, 1, 0>(a, c, blocks, stream);
+        case 2: return launch_cube_variant<true, DIV, LERP, 2, 0>(a, c, blocks, stream);
+        case 5:
+            if (lean && LERP == 1) return launch_cube_variant<true, DIV, 1, 5, 2>(a, c, blocks, stream);
+            return launch_cube_variant<true, DIV, LERP, 5, 1>(a, c, blocks, stream);
         case 4:
-            if (span) return launch_cube_variant<true, DIV, LERP, 4, true>(a, c, blocks, stream);
-            return launch_cube_variant<true, DIV, LERP, 4, false>(a, c, blocks, stream);
-        default: return launch_cube_variant<true, DIV, LERP, 0, false>(a, c, blocks, stream);
+            if (span) return launch_cube_variant<true, DIV, LERP, 4, 1>(a, c, blocks, stream);
+            return launch_cube_variant<true, DIV, LERP, 4, 0>(a, c, blocks, stream);
+        default: return launch_cube_variant<true, DIV, LERP, 0, 0>(a, c, blocks, stream);
     }
 }
 
 // lerp: 0 full std::lerp, 1 positive cube, 2 non-negative cube
 template <int DIV>
 cudaError_t launch_cube_div(const MarchArgs& a, const CubeView& c, unsigned blocks, bool tri, int lerp, int fetch,
-                            bool span, cudaStream_t stream) {
+                            bool span, bool lean, cudaStream_t stream) {
     if (!tri) {
         // nearest neighbour interpolates nothing; the class only decides whether a zero product can be a sample
         if (lerp == 1) {
-            if (span) return launch_cube_variant<false, DIV, 1, 0, true>(a, c, blocks, stream);
-            return launch_cube_variant<false, DIV, 1, 0, false>(a, c, blocks, stream);
+            if (span) return launch_cube_variant<false, DIV, 1, 0, 1>(a, c, blocks, stream);
+            return launch_cube_variant<false, DIV, 1, 0, 0>(a, c, blocks, stream);
         }
-        if (span) return launch_cube_variant<false, DIV, 0, 0, true>(a, c, blocks, stream);
-        return launch_cube_variant<false, DIV, 0, 0, false>(a, c, blocks, stream);
+        if (span) return launch_cube_variant<false, DIV, 0, 0, 1>(a, c, blocks, stream);
+        return launch_cube_variant<false, DIV, 0, 0, 0>(a, c, blocks, stream);
     }
-    if (lerp == 1) return launch_cube_fetch<DIV, 1>(a, c, blocks, fetch, span, stream);
-    if (lerp == 2) return launch_cube_fetch<DIV, 2>(a, c, blocks, fetch, span, stream);
-    return launch_cube_fetch<DIV, 0>(a, c, blocks, fetch, span, stream);
+    if (lerp == 1) return launch_cube_fetch<DIV, 1>(a, c, blocks, fetch, span, lean, stream);
+    if (lerp == 2) return launch_cube_fetch<DIV, 2>(a, c, blocks, fetch, span, false, stream);
+    return launch_cube_fetch<DIV, 0>(a, c, blocks, fetch, span, false, stream);
 }
 
 // upload-time self-check of the texture path: gathered texels == linear voxels at `n` cells
@@ -686,11 +690,21 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         view.loy = view.lox;
         view.loz = view.lox;
     }
+    // BIRP_LEAN_MARCH: fp32 cell index (grids of at most 2^24 voxels) and no range test in the scale -- allowed when
+    // every sample of the positive cube, which lies in [vmin, vmax], scales into [2^-120, 2^120) (the scale is a
+    // monotone function of the sample for a positive ray width)
+    bool lean = false;
+    if ((flags & BIRP_LEAN_MARCH) && fetch == 5 && lerp == 1 && (long long)cube.nx * cube.ny * cube.nz <= (1LL << 24) &&
+        cube.vmin > 0.f && cube.vmax >= cube.vmin && a.ray_width > 0.f) {
+        const volatile float plo = cube.vmin * a.ray_width, phi = cube.vmax * a.ray_width;
+        const float ylo = (float)((double)plo * BIRP_SCALE_K), yhi = (float)((double)phi * BIRP_SCALE_K);
+        lean = ylo >= BIRP_SCALE_SAFE_LO && yhi < BIRP_SCALE_SAFE_HI;
+    }
     cudaError_t e;
     switch (divmode) {
-        case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, span, stream); break;
-        case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, span, stream); break;
-        default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, span, stream); break;
+        case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
+        case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
+        default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e;

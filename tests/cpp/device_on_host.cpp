@@ -60,7 +60,7 @@ using birp::CubeView;
 using birp::RayState;
 
 // march_cube_kernel's body for one ray (birp_kernels.cu), with the table staged chunk by chunk
-template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
+template <bool TRI, int DIV, int LERP, int FETCH, int SPAN>
 void march_ray(const CubeView& c, const birp_frame& fr, int i, int j, int W, int H,
                const std::vector<std::vector<float>>& staged, const std::vector<int>& chunk_len, float ray_width,
                int accumulate, float* pix, unsigned long long* valid, int* status) {
@@ -76,7 +76,7 @@ void march_ray(const CubeView& c, const birp_frame& fr, int i, int j, int W, int
     for (size_t k = 0; k < staged.size() && alive; ++k) {
         t_table = staged[k].data();
         const unsigned send = 4u * (unsigned)chunk_len[k];
-        nlive4 += SPAN ? birp::march_steps_span<TRI, DIV, LERP, FETCH>(c, r, 0u, send, ray_width, K, status, alive)
+        nlive4 += SPAN ? birp::march_steps_span<TRI, DIV, LERP, FETCH, SPAN == 2>(c, r, 0u, send, ray_width, K, status, alive)
                        : birp::march_steps<TRI, DIV, LERP, FETCH>(c, r, 0u, send, ray_width, K, status, alive);
     }
     *pix = r.acc;
@@ -92,7 +92,7 @@ struct RenderJob {
     int status = 0;
 };
 
-template <bool TRI, int DIV, int LERP, int FETCH, bool SPAN>
+template <bool TRI, int DIV, int LERP, int FETCH, int SPAN>
 void render_variant(RenderJob& job) {
     CubeView c = job.cube->view;
     if (!TRI) c.lox = c.loy = c.loz = BIRP_TINY_INGRESS;  // launch_render_cube: nearest keeps the first cells hot
@@ -132,8 +132,11 @@ void render_variant(RenderJob& job) {
 
 template <bool TRI, int DIV, int LERP, int FETCH>
 void render_span(RenderJob& job, int span) {
-    if (span) render_variant<TRI, DIV, LERP, FETCH, true>(job);
-    else render_variant<TRI, DIV, LERP, FETCH, false>(job);
+    // span 2 = the lean march (BIRP_LEAN_MARCH): built, like the kernel, for positive cubes and oct records only;
+    // the caller is responsible for launch_render_cube's conditions (grid size, value range)
+    if (span == 2 && TRI && LERP == 1 && FETCH == 5) render_variant<TRI, DIV, LERP, FETCH, (TRI && LERP == 1 && FETCH == 5) ? 2 : 1>(job);
+    else if (span) render_variant<TRI, DIV, LERP, FETCH, 1>(job);
+    else render_variant<TRI, DIV, LERP, FETCH, 0>(job);
 }
 
 template <bool TRI, int DIV, int LERP>

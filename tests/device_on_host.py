@@ -94,7 +94,8 @@ class HostCube:
 
     def render(self, frames, W, H, trilinear=True, lerp=-1, divmode=-1, fetch=5, span=True, nsamples=200, maxdist=44,
                accumulate_into=None):
-        """march_cube_kernel on the host; frames: birp_frame records (structured array or (n, 16) floats)"""
+        """march_cube_kernel on the host; frames: birp_frame records (structured array or (n, 16) floats);
+        span: False / 0 the window test in every step, True / 1 run end by bisection, 2 the lean form of it"""
         fr = np.ascontiguousarray(frames).view(np.float32).reshape(-1, 16)
         img = np.zeros((len(fr), H, W), np.float32) if accumulate_into is None else _f32(accumulate_into).copy()
         valid = C.c_ulonglong(0)

@@ -198,6 +198,33 @@ def test_march_on_host_first_cells_zero_regions_long_tables():
     c.free()
 
 
+def test_lean_march_on_host_equals_oracle(cube1):
+    """BIRP_LEAN_MARCH (opt-in): fp32 cell index and no range test in the scale, on a positive cube whose values scale
+    well inside the normal fp32 range -- same images bit for bit, on the reference test cube's shape and on a grid with
+    an awkward spacing seen from inside"""
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    c = D.HostCube(zyx, org, sp, divmode=0)
+    assert c.lerp_class == 1 and zyx.size <= 1 << 24
+    want = O.orc_render_cube(zyx, org, sp, True, fo, W, H)
+    got, _, st = c.render(fp, W, H, fetch=5, span=2)
+    assert st == 0
+    assert_bit_exact(got, want, "lean march, config1 cube")
+    c.free()
+    zyx, org, sp = small_grid()
+    poses = np.array([(org[0] + fx * sp[0], org[1] + fy * sp[1], org[2] + fz * sp[2])
+                      for fx, fy, fz in ((0.5, 0.5, 0.5), (26.5, 24.5, 22.5), (13.0, 0.99999994, 11.0), (5.3, 12.2, 22.9))],
+                     np.float32)
+    c = D.HostCube(zyx, org, sp, divmode=1)
+    fq = capi.frames_for_poses(poses, -30.0, 60.0, 60.0, 20, 20)
+    fr = O.orc_frames(poses, -30.0, 60.0, 60.0, 20, 20)
+    for nsamples in (600, 4500):
+        want = O.orc_render_cube(zyx, org, sp, True, fr, 20, 20, nsamples=nsamples, maxdist=12)
+        got, _, _ = c.render(fq, 20, 20, fetch=5, span=2, nsamples=nsamples, maxdist=12)
+        assert_bit_exact(got, want, f"lean march, small grid, n={nsamples}")
+    c.free()
+
+
 def test_march_on_host_nan_pose_sets_the_range_status():
     """a NaN camera position passes the reference's bounds test (comparisons with NaN are false) and throws from
     .at(): the device code reports it through the status word"""

@@ -1,0 +1,108 @@
+"""A/B timing of march-kernel variants WITHOUT torch (seconds instead of tens of seconds of start-up): the orbit
+workload through birp_render_cube_device on the default stream, CUDA events from libcudart via ctypes.
+
+  python tools/ab_quick.py [--flags 0,16384] [--frames 10000] [--steps 4] [--dry]
+
+Prints one JSON line: per flag combination the best and mean kernel time, frames/s, and whether its images are
+bit-identical to those of the first combination.  No L2 flush between launches (the oct copy of the 256^3 cube is
+537 MB, four times the L2).  Development tool, not the bench.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import glob
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+def cudart():
+    cands = glob.glob(str(Path(np.__file__).resolve().parents[1] / "nvidia" / "cuda_runtime" / "lib" / "libcudart.so*"))
+    cands += glob.glob("/usr/local/cuda/targets/x86_64-linux/lib/libcudart.so.*") + ["libcudart.so.12", "libcudart.so"]
+    for c in cands:
+        try:
+            rt = C.CDLL(c)
+        except OSError:
+            continue
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        rt.cudaEventCreate.argtypes = [C.POINTER(C.c_void_p)]
+        rt.cudaEventRecord.argtypes = [C.c_void_p, C.c_void_p]
+        rt.cudaEventSynchronize.argtypes = [C.c_void_p]
+        rt.cudaEventElapsedTime.argtypes = [C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        return rt, c
+    raise OSError("no libcudart found")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--flags", default="0,16384")
+    ap.add_argument("--frames", type=int, default=10000)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--cube", type=int, default=256)
+    ap.add_argument("--dry", action="store_true", help="everything that needs no GPU, then stop")
+    args = ap.parse_args()
+    t0 = time.perf_counter()
+    from birp_cpp_b200 import capi, synthetic as S
+
+    rt, rt_path = cudart()
+    capi.lib()
+    W, H = S.SXI_W, S.SXI_H
+    n = args.cube
+    zyx, org, sp = S.make_cube(n, n, n)
+    poses = S.orbit_poses(args.frames)
+    frames = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    flags = [int(x) for x in args.flags.split(",")]
+    out = {"workload": "orbit", "frames": len(poses), "cube": n, "cudart": rt_path,
+           "host_setup_s": round(time.perf_counter() - t0, 2)}
+    if args.dry:
+        print(json.dumps(out))
+        return
+
+    def ck(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: cudaError {rc}")
+
+    capi.set_device(0)
+    cube = capi.Cube(zyx, org, sp)
+    out["info"] = cube.info()
+    d_frames = capi.DeviceBuffer(len(poses) * 16)
+    d_img = capi.DeviceBuffer(len(poses) * H * W)
+    fr = np.ascontiguousarray(frames).view(np.float32).reshape(-1, 16)
+    ck(rt.cudaMemcpy(d_frames.ptr, fr.ctypes.data, fr.nbytes, 1), "H2D frames")
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    ck(rt.cudaEventCreate(C.byref(e0)), "event")
+    ck(rt.cudaEventCreate(C.byref(e1)), "event")
+    ref = None
+    img = np.empty((len(poses), H, W), np.float32)
+    for fl in flags:
+        ms = []
+        for it in range(args.steps + 1):
+            ck(rt.cudaEventRecord(e0, None), "record")
+            capi.render_cube_device(cube, d_frames.ptr, len(poses), W, H, d_img.ptr, trilinear=True, stream=0,
+                                    extra_flags=fl)
+            ck(rt.cudaEventRecord(e1, None), "record")
+            ck(rt.cudaEventSynchronize(e1), "sync")
+            t = C.c_float(0)
+            ck(rt.cudaEventElapsedTime(C.byref(t), e0, e1), "elapsed")
+            if it >= 1:
+                ms.append(t.value)
+        capi.check_device_status(0)
+        ck(rt.cudaMemcpy(img.ctypes.data, d_img.ptr, img.nbytes, 2), "D2H images")
+        same = True if ref is None else bool(np.array_equal(img.view(np.uint32), ref.view(np.uint32)))
+        if ref is None:
+            ref = img.copy()
+        out[f"flags_{fl}"] = {"ms_min": round(min(ms), 4), "ms_mean": round(float(np.mean(ms)), 4),
+                              "frames_per_s": round(len(poses) / (min(ms) * 1e-3), 1), "same_as_first": same,
+                              "nonzero_pixels": int(np.count_nonzero(img))}
+    out["total_s"] = round(time.perf_counter() - t0, 2)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
