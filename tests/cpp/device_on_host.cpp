@@ -369,6 +369,47 @@ void doh_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, i
     }
 }
 
+// march_kernel<CmemField<mode>> over whole frames (birp_kernels.cu; the loop is restated, the sampler and the scale
+// are the device source)
+void doh_render_cmem(const birp_cmem_params* params, int mode, const birp_frame* frames, int nframes, int W, int H,
+                     int nsamples, int maxdist, float* images) {
+    const birp::CmemDev D = birp::make_cmem_dev(*params);
+    std::vector<float> dist(nsamples);
+    float ray_width = 0.f;
+    birp::host_ray_table(nsamples, maxdist, dist.data(), &ray_width);
+    const int nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    const long rows_total = (long)nframes * H;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            for (long row = t; row < rows_total; row += nthreads) {
+                const int f = (int)(row / H), j = (int)(row % H);
+                const birp_frame& fr = frames[f];
+                for (int i = 0; i < W; ++i) {
+                    float dx, dy, dz;
+                    birp::pixel_direction(fr, i, j, (float)W, (float)H, dx, dy, dz);
+                    float acc = 0.f;
+                    for (int k = 0; k < nsamples; ++k) {
+                        const float tk = dist[k];
+                        const float x = dx * tk + fr.pos[0], y = dy * tk + fr.pos[1], z = dz * tk + fr.pos[2];
+                        float s;
+                        switch (mode) {
+                            case 0: s = birp::cmem_sample_mode<0>(D, x, y, z); break;
+                            case 1: s = birp::cmem_sample_mode<1>(D, x, y, z); break;
+                            case 2: s = birp::cmem_sample_mode<2>(D, x, y, z); break;
+                            default: s = birp::cmem_sample_mode<3>(D, x, y, z); break;
+                        }
+                        s = birp::scale_sample(s, ray_width);
+                        if (s < 0.f) break;
+                        acc += s;
+                    }
+                    images[((size_t)f * H + j) * W + i] = acc;
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 // which samples the region filter decides on its own (1) and which go to the full evaluation (0)
 void doh_cmem_filter_decides(const birp_cmem_params* params, const float* xyz, long n, unsigned char* decided) {
     const birp::CmemDev D = birp::make_cmem_dev(*params);

@@ -34,6 +34,7 @@ def lib():
         L.doh_lerps.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
         L.doh_sample_cmem.argtypes = [_vp, _vp, C.c_long, C.c_int, _vp]
         L.doh_cmem_filter_decides.argtypes = [_vp, _vp, C.c_long, _vp]
+        L.doh_render_cmem.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
         _lib = L
     return _lib
 
@@ -140,3 +141,12 @@ def cmem_filter_decides(params, xyz):
     params = np.ascontiguousarray(params)
     lib().doh_cmem_filter_decides(_p(params), _p(xyz), len(xyz), _p(out))
     return out.astype(bool)
+
+
+def render_cmem(params, frames, W, H, mode=3, nsamples=200, maxdist=44):
+    """march_kernel<CmemField<mode>> on the host"""
+    fr = np.ascontiguousarray(frames).view(np.float32).reshape(-1, 16)
+    img = np.zeros((len(fr), H, W), np.float32)
+    params = np.ascontiguousarray(params)
+    lib().doh_render_cmem(_p(params), int(mode), _p(fr), len(fr), W, H, nsamples, maxdist, _p(img))
+    return img

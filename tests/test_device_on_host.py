@@ -13,7 +13,7 @@ import pytest
 import device_on_host as D
 import oracle as O
 from birp_cpp_b200 import capi, synthetic as S
-from conftest import assert_bit_exact
+from conftest import assert_bit_exact, assert_image_parity
 
 W, H = 36, 24
 AIM = S.DEFAULT_AIM_X
@@ -281,3 +281,17 @@ def test_cmem_device_source_vs_oracle_and_filter_is_invisible(kw):
     ok = err <= 1e-5 * np.maximum(np.abs(want), 1e-3 * scale)
     assert ok.mean() >= 0.9995
     assert np.all(err <= 1e-2 * np.maximum(np.abs(want), 1e-3 * scale))
+
+
+@pytest.mark.parametrize("name,kw", [("default", {}), ("test2", O.CMEM_TEST2)])
+def test_cmem_frames_on_host_vs_oracle(name, kw):
+    """whole CMEM frames from the device sampler (own fp64 blocks behind the region filter) against the oracle at the
+    SURVEY 8(d) tolerance (1e-5 per pixel, 1e-4 flux, >= 95 % of pixels), and filter on = filter off bit for bit"""
+    poses = np.array([S.DEFAULT_POS, (30.0, -25.0, 28.0), (1.5, -3.0, 2.0)], np.float32)
+    fp, fo = frames_pair(poses, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    want = O.orc_render_cmem(O.orc_cmem_init(**kw), fo, W, H)
+    P = capi.cmem_init(**kw)
+    got = D.render_cmem(P, fp, W, H, mode=3)
+    frac = assert_image_parity(got, want, f"CMEM {name}")
+    assert frac >= 0.999
+    assert_bit_exact(D.render_cmem(P, fp, W, H, mode=2), got, "filter off")
