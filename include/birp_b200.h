@@ -76,8 +76,8 @@ enum {
                                    the quad copy */
     BIRP_LEAN_MARCH = 16384,    /* DataCube, trilinear, opt-in (not yet measured against the default): for a positive cube
                                    of at most 2^24 voxels uploaded from host memory, compute the cell index in fp32
-                                   and drop the scale's range test where the cube's smallest and largest voxel make
-                                   it redundant (identical results, four instructions fewer per sample) */
+                                   and drop the tests of the scale shortcut where the cube's smallest and largest
+                                   voxel make them redundant (identical results, five instructions fewer per sample) */
     BIRP_WINDOW_PER_STEP = 4096 /* DataCube only: test the cube bounds window at every step of the march instead
                                    of locating the end of each ray's in-bounds run once by bisection over the
                                    (monotone) ray table (identical results; kept as the cross-check) */

@@ -345,6 +345,54 @@ void doh_scale(const float* s, long n, float ray_width, int maybe_zero, float* y
     }
 }
 
+// The scale shortcut over EVERY fp32 product (all 2^32 bit patterns of p = sample * ray_width, here sample = p and
+// ray_width = 1): count[0] = products the hot loop accepts (scale_fast says exact), count[1] = accepted products
+// whose value differs from the reference's three-step chain (must be 0), count[2] = accepted products that are
+// negative or NaN after the chain (must be 0: those end the ray or poison the pixel, which only the cold path
+// handles), count[3] = finite products in [2^-120, 2^120) that the flag sends to the cold path (the near-midpoint
+// ones), count[4] = products whose chain value lies in [2^-120, 2^120) and differs from the single multiply,
+// whatever the flag says (0 means: inside that range the single multiply IS the chain, for every input -- what
+// scale_fast<.., RANGE_SAFE> relies on).  `stride` > 1 checks every stride-th pattern.
+void doh_scale_exhaustive(int maybe_zero, unsigned stride, int nthreads, unsigned long long count[5]) {
+    if (nthreads < 1) nthreads = 1;
+    std::vector<std::vector<unsigned long long>> part(nthreads, std::vector<unsigned long long>(5, 0));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            auto& c = part[t];
+            for (uint64_t u = (uint64_t)t * stride; u < (1ull << 32); u += (uint64_t)nthreads * stride) {
+                const uint32_t b = (uint32_t)u;
+                float p;
+                std::memcpy(&p, &b, 4);
+                float y;
+                const bool e = maybe_zero ? birp::scale_fast<true>(p, 1.0f, BIRP_SCALE_K, y)
+                                          : birp::scale_fast<false>(p, 1.0f, BIRP_SCALE_K, y);
+                const float chain = birp::scale_sample_chain(p);
+                if (chain >= BIRP_SCALE_SAFE_LO && chain < BIRP_SCALE_SAFE_HI) {
+                    uint32_t by, bc;
+                    std::memcpy(&by, &y, 4);
+                    std::memcpy(&bc, &chain, 4);
+                    if (by != bc) ++c[4];
+                }
+                if (e) {
+                    ++c[0];
+                    uint32_t by, bc;
+                    std::memcpy(&by, &y, 4);
+                    std::memcpy(&bc, &chain, 4);
+                    if (by != bc) ++c[1];
+                    if (!(chain >= 0.f)) ++c[2];
+                } else if (chain >= BIRP_SCALE_SAFE_LO && chain < BIRP_SCALE_SAFE_HI) {
+                    ++c[3];
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+    for (int k = 0; k < 5; ++k) {
+        count[k] = 0;
+        for (int t = 0; t < nthreads; ++t) count[k] += part[t][k];
+    }
+}
+
 // the seven-lerp building blocks on raw operands: std::lerp transcription, positive form, non-negative form
 void doh_lerps(const float* a, const float* b, const float* t, long n, float* ref, float* positive, float* nonneg) {
     for (long p = 0; p < n; ++p) {

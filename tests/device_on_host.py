@@ -32,6 +32,7 @@ def lib():
                                       C.c_int, C.c_int, C.c_int, _vp, _vp]
         L.doh_scale.argtypes = [_vp, C.c_long, C.c_float, C.c_int, _vp, _vp, _vp, _vp]
         L.doh_lerps.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
+        L.doh_scale_exhaustive.argtypes = [C.c_int, C.c_uint, C.c_int, _vp]
         L.doh_sample_cmem.argtypes = [_vp, _vp, C.c_long, C.c_int, _vp]
         L.doh_cmem_filter_decides.argtypes = [_vp, _vp, C.c_long, _vp]
         L.doh_render_cmem.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
@@ -116,6 +117,16 @@ def scale(s, ray_width, maybe_zero=False):
     exact = np.zeros(n, np.uint8)
     lib().doh_scale(_p(s), n, float(ray_width), int(maybe_zero), _p(y), _p(exact), _p(chain), _p(full))
     return y, exact.astype(bool), chain, full
+
+
+def scale_exhaustive(maybe_zero=False, stride=1, nthreads=0):
+    """scale_fast against the reference's chain over every stride-th fp32 product:
+    (accepted, accepted but different, accepted but negative / NaN, in range but sent to the cold path,
+    in range and different whatever the flag says)"""
+    import os
+    out = (C.c_ulonglong * 5)()
+    lib().doh_scale_exhaustive(int(maybe_zero), int(stride), int(nthreads or len(os.sched_getaffinity(0))), out)
+    return tuple(int(x) for x in out)
 
 
 def lerps(a, b, t):

@@ -131,6 +131,19 @@ def test_scale_fast_flags_products_near_a_rounding_midpoint():
     assert (~exact).sum() < 50  # about 1 in 2^23 is flagged
 
 
+@pytest.mark.parametrize("maybe_zero", [False, True])
+def test_scale_single_multiply_is_the_chain_for_every_product(maybe_zero):
+    """ALL 2^32 fp32 products through scale_fast and through the reference's three-step fp64 chain: whatever the hot
+    loop accepts equals the chain and is never negative or NaN; and inside [2^-120, 2^120) the single multiply equals
+    the chain for EVERY product (for this K the midpoint window is never hit) -- the statement the lean march's
+    test-free scale (scale_fast<.., RANGE_SAFE>) rests on"""
+    accepted, differ, bad_sign, flagged, differ_in_range = D.scale_exhaustive(maybe_zero)
+    assert accepted > 1.9e9
+    assert differ == 0 and bad_sign == 0
+    assert differ_in_range == 0
+    assert flagged == 0
+
+
 def test_clamp_free_lerps_equal_std_lerp_on_their_domains():
     rng = np.random.default_rng(23)
     n = 500000
