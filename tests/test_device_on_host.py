@@ -211,6 +211,56 @@ def test_march_on_host_first_cells_zero_regions_long_tables():
     c.free()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_march_on_host_random_grids_and_marches(seed):
+    """seeded random stress of the march source against the oracle: grids from 2 to 13 voxels per axis (with
+    two voxels the hot window is empty), spacings over three decades, positive / zero-riddled / signed / NaN / inf /
+    near-underflow / near-overflow values, cameras inside, on the faces and outside, marches of 1 to 4100 samples
+    (up to three table chunks), negative and zero maxdist; every fetch form, both march forms, the cube's own lerp
+    class and the general one.  Where the reference throws (NaN index) the status word must say so."""
+    rng = np.random.default_rng(seed)
+    for trial in range(40):
+        nx, ny, nz = (int(v) for v in rng.integers(2, 14, 3))
+        kind = rng.choice(["pos", "nonneg", "gen", "nan", "inf", "tiny", "huge"])
+        zyx = (10.0 ** rng.uniform(-8, -4, (nz, ny, nx))).astype(np.float32)
+        if kind == "nonneg":
+            zyx[rng.random(zyx.shape) < 0.3] = 0
+        if kind == "gen":
+            zyx[rng.random(zyx.shape) < 0.2] *= -1
+        if kind in ("nan", "inf"):
+            zyx[rng.integers(0, nz), rng.integers(0, ny), rng.integers(0, nx)] = np.nan if kind == "nan" else np.inf
+        if kind == "tiny":
+            zyx *= np.float32(1e-38)
+        if kind == "huge":
+            zyx *= np.float32(1e36)
+        sp = (10.0 ** rng.uniform(-2, 1, 3)).astype(np.float32)
+        org = rng.uniform(-20, 20, 3).astype(np.float32)
+        ext = sp * np.array([nx - 1, ny - 1, nz - 1], np.float32)
+        poses = (org + rng.uniform(-0.2, 1.2, (3, 3)).astype(np.float32) * ext).astype(np.float32)
+        w, h = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        ns, md = int(rng.choice([1, 2, 7, 200, 333, 2049, 4100])), int(rng.choice([1, 5, 44, 300, -7, 0]))
+        fp = capi.frames_for_poses(poses, float(rng.uniform(-30, 30)), 40.0, 30.0, w, h)
+        fo = fp.view(np.float32).reshape(-1, 16)
+        c = D.HostCube(zyx, org, sp, divmode=2)
+        for tri in (True, False):
+            try:
+                want = O.orc_render_cube(zyx, org, sp, tri, fo, w, h, nsamples=ns, maxdist=md)
+            except IndexError:
+                want = None
+            for span in (0, 1):
+                for fetch in ((5, 4, 0, 2) if tri else (0,)):
+                    for lerp in (-1, 0):
+                        got, _, st = c.render(fp, w, h, trilinear=tri, fetch=fetch, span=span, lerp=lerp, nsamples=ns,
+                                              maxdist=md)
+                        what = f"seed {seed} trial {trial} {kind} tri={tri} span={span} fetch={fetch} lerp={lerp}"
+                        if want is None:
+                            assert st == 1, what
+                        else:
+                            assert st == 0, what
+                            assert_bit_exact(got, want, what)
+        c.free()
+
+
 def test_lean_march_on_host_equals_oracle(cube1):
     """BIRP_LEAN_MARCH (opt-in): fp32 cell index and no range test in the scale, on a positive cube whose values scale
     well inside the normal fp32 range -- same images bit for bit, on the reference test cube's shape and on a grid with
