@@ -602,7 +602,7 @@ def run_b200(args, wl, name):
         parity = None
         if O.have_ref():
             if nframes > 1:
-                nsamp = 16
+                nsamp = 32  # ~10 s of the single-threaded reference
                 idx = np.linspace(0, nmine - 1, nsamp).astype(int)
                 secs, ref_imgs = reference_sample(wl, my_poses[idx], 1, want_images=True)
                 cpu = {"value": nsamp / secs, "unit": "frames/s", "cores": 1, "kind": "reference",
