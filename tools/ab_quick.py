@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--frames", type=int, default=10000)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--cube", type=int, default=256)
+    ap.add_argument("--e2e", action="store_true", help="also time birp_render_cube_sweep (host poses -> pinned images)")
     ap.add_argument("--dry", action="store_true", help="everything that needs no GPU, then stop")
     args = ap.parse_args()
     t0 = time.perf_counter()
@@ -100,6 +101,22 @@ def main():
         out[f"flags_{fl}"] = {"ms_min": round(min(ms), 4), "ms_mean": round(float(np.mean(ms)), 4),
                               "frames_per_s": round(len(poses) / (min(ms) * 1e-3), 1), "same_as_first": same,
                               "nonzero_pixels": int(np.count_nonzero(img))}
+    if args.e2e:
+        # end to end through birp_render_cube_sweep: host poses in, pinned host images out (wall clock, the call
+        # synchronises before it returns)
+        pinned = capi.PinnedArray((len(poses), H, W))
+        for fl in flags:
+            secs = []
+            for it in range(args.steps + 1):
+                t1 = time.perf_counter()
+                capi.render_sweep(cube, poses, S.DEFAULT_AIM_X, S.SXI_FOV_W, S.SXI_FOV_H, W, H, trilinear=True,
+                                  extra_flags=fl, out=pinned.array)
+                if it >= 1:
+                    secs.append(time.perf_counter() - t1)
+            out[f"e2e_flags_{fl}"] = {"ms_min": round(min(secs) * 1e3, 4), "frames_per_s": round(len(poses) / min(secs), 1),
+                                      "same_as_device_render": bool(np.array_equal(pinned.array.view(np.uint32),
+                                                                                   ref.view(np.uint32)))}
+        pinned.free()
     out["total_s"] = round(time.perf_counter() - t0, 2)
     print(json.dumps(out))
 
