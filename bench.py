@@ -15,8 +15,17 @@ and the images are gathered to rank 0 with NCCL inside the timed region.
          max over ranks; L2 is flushed between timed steps.
   e2e    the same sweep through the host-buffer C ABI call birp_render_cube (pinned host frame
          records in, pinned host images out; H2D/D2H inside the timed region).
-  roofline       the march kernel: algorithmic bytes (32 B per live trilinear sample + 4 B per
-                 pixel) / CUDA-event kernel time, against the measured HBM copy bandwidth.
+  roofline       the march kernel against the roof that binds it: instruction issue.  achieved =
+                 executed warp instructions per launch (ncu smsp__inst_executed.sum of the same
+                 kernel and workload, profiles/traffic.json, scaled by the live samples of this
+                 launch) / CUDA-event kernel time; peak = 592 schedulers x SM clock sampled under
+                 load.  The byte figures of SURVEY 8(d) (32 B per live trilinear sample + 4 B per
+                 pixel, against the measured HBM copy bandwidth and the L2 gather microbenchmark)
+                 ride along as vs_hbm / vs_l2_gather: they exceed 1 because the cube is served
+                 from L1/L2, which is why they are not the binding roof.
+  exit code      non-zero when the DataCube images are not bit-exact (tolerance-mode flags: < 99.9 %
+                 of pixels within 1e-5 or flux off by > 1e-4), CMEM < 95 % / flux > 1e-4, or rank 0's
+                 gathered buffer differs from a single-GPU render.
   cpu_baseline   the unmodified reference (oracle/_ref) on a bounded sample of the same frames,
                  on the host cores of this box; the same frames give the parity figure.
 """
@@ -77,19 +86,59 @@ def workload_config(wl, name, world):
     interp = {"cube": "trilinear", "cube-nearest": "nearest", "cmem": "analytic"}[field]
     return {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples, "maxdist_RE": MAXDIST,
             "interpolation": interp, "frames": nframes, "cube": cube_n,
-            "parallelism": (f"frames x{world}" if nframes > 1 else f"row bands x{world}")}
+            "parallelism": (f"frames x{world}" if nframes > 1 else f"row tiles x{world}"),
+            "l2": "GPU arm: flushed between timed steps (256 MiB memset, untimed)",
+            # a line is only printed when these hold: the B200 arm exits non-zero otherwise (see run_b200), the
+            # reference arm is the thing compared against
+            "parity_ok": True, "gather_ok": True}
 
 
-def measured_traffic(name, world, nframes_total):
-    """per-launch DRAM bytes (and executed warp instructions) of the dominant kernel, from the committed ncu
-    capture (profiles/traffic.json); only valid for the exact configuration that was profiled"""
+def measured_traffic(name, extra_flags):
+    """the committed ncu capture of this workload's dominant kernel (profiles/traffic.json, written by
+    tools/ncu_traffic.py from one `ncu --set full` capture of `python bench.py --workload <name> --steps 2
+    --warmup 1` on one GPU): per-launch DRAM bytes, executed warp instructions and the live samples of that launch.
+    Instructions and bytes per live sample are properties of the kernel, so a launch with a different share of the
+    same workload (N > 1, --frames) is scaled by its live-sample count."""
     p = ROOT / "profiles" / "traffic.json"
     if not p.exists():
-        return None, None, None
-    t = json.loads(p.read_text()).get(name)
-    if not t or t.get("n_gpus") != world or t.get("frames") != nframes_total:
-        return None, None, None
-    return t["bytes"], t["profile"], t.get("warp_instructions")
+        return None
+    key = name if not extra_flags else f"{name}+flags{extra_flags}"
+    return json.loads(p.read_text()).get(key)
+
+
+def issue_roofline(entry, live_samples, kernel_ms, sm_mhz):
+    """The binding roof of the march kernels is instruction issue: one warp instruction per scheduler per clock,
+    4 schedulers x 148 SMs.  achieved = executed warp instructions of this launch / kernel time; the instruction
+    count is ncu's smsp__inst_executed.sum of the committed capture of the same kernel on the same workload, scaled
+    by live samples when this launch covers a different share (N > 1, --frames)."""
+    peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp instructions / s at the SM clock sampled under load
+    out = {"bound": "issue", "achieved": None, "peak": peak, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
+           "peak_source": f"592 warp schedulers x {sm_mhz:.0f} MHz (SM clock sampled under load, nvml)"}
+    if not entry or not entry.get("warp_instructions") or not entry.get("live_samples"):
+        out["note"] = "no ncu capture of this workload / flag combination in profiles/traffic.json"
+        return out
+    scale = live_samples / float(entry["live_samples"])
+    winst = entry["warp_instructions"] * scale
+    out["achieved"] = winst / (kernel_ms / 1e3) / 1e9
+    out["frac"] = out["achieved"] / peak
+    out["traffic"] = int(entry["bytes"] * scale) if entry.get("bytes") is not None else None
+    out["warp_instructions_per_launch"] = int(winst)
+    out["warp_instructions_per_warp_sample"] = entry["warp_instructions"] / (entry["live_samples"] / 32.0)
+    out["source"] = {"profile": entry.get("profile"), "kernel": entry.get("kernel"),
+                     "scaled_by_live_samples": round(scale, 6)}
+    for k in ("issue_active_pct", "l1tex_pct", "l1_wavefronts_per_request", "xu_pct", "fp64_pct"):
+        if k in entry:
+            out[k + "_ncu"] = entry[k]
+    return out
+
+
+def kernel_name(field, trilinear, extra_flags):
+    from birp_cpp_b200 import capi
+    if field != "cube":
+        return "march_kernel<CmemField>"
+    if not trilinear:
+        return "march_cube_kernel<nearest>"
+    return "march_cube_fast_kernel<trilinear>" if (extra_flags & capi.FAST_MARCH) else "march_cube_kernel<trilinear>"
 
 
 def peaks():
@@ -217,6 +266,7 @@ def run_reference(args, wl, name):
     if not O.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbirp_ref.so was not built"}))
         return
+    O.ref()  # dlopen oracle/_ref/libbirp_ref.so in THIS process: the fork-pool workers inherit the mapping
     cores = len(os.sched_getaffinity(0))
     workers = max(1, min(cores, 32))
     if nframes == 1:
@@ -258,8 +308,8 @@ def run_reference(args, wl, name):
         "value": frames_per_s, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / max(len(times), 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(WORKLOADS[name] if nframes == 1 else wl, name, args.gpus),
-                       reference_threads=workers),
+        "config": workload_config(WORKLOADS[name] if nframes == 1 else wl, name, args.gpus),
+        "reference_threads": workers,
         "rays_per_sec": rays,
         "cpu_baseline": {"value": frames_per_s, "unit": "frames/s", "cores": workers, "kind": "reference",
                          "sample": sample_note},
@@ -462,6 +512,9 @@ def run_b200(args, wl, name):
 
     # ---- N > 1: what rank 0 holds must be what one GPU renders (a few frames / rows of other ranks' shares)
     gather_check = None
+    e2e_gather_check = None
+    e2e_note = "bytes are per rank; every rank moves its own share"
+    parity_rows = (rows[0], min(rows[0] + 16, rows[1]))
     if peer is not None:
         torch.cuda.synchronize()
         dist.barrier()
@@ -572,31 +625,38 @@ def run_b200(args, wl, name):
                                 "not correctly rounded, hence the differing records (<= 2.2e-6 in a rotation entry)"}
 
     # ---- rank 0: CPU baseline on a bounded sample + parity of the same frames, then the JSON line
+    failed = []
     if rank == 0:
         import oracle as O
         hbm, hbm_src = peaks()
         frames_total = nframes if nframes > 1 else 1
-        rays_total = frames_total * W * H
         value = frames_total / (total_ms / args.steps / 1e3)
-        # algorithmic bytes of this rank's launch (rank 0's share; N=1: everything)
+        kernel_ms = float(kern_ms.mean())
+        # algorithmic bytes of this rank's launch (rank 0's share; N=1: everything), SURVEY 8(d)
         bytes_per_sample = (32 if trilinear else 4) if field == "cube" else 0
         alg_bytes = valid_mine * bytes_per_sample + nmine * my_rows * W * 4
-        achieved = alg_bytes / (float(kern_ms.mean()) / 1e3) / 1e9
-
-        traffic, traffic_src, warp_inst = measured_traffic(name, world, frames_total)
+        achieved_gbs = alg_bytes / (kernel_ms / 1e3) / 1e9
         clk = clocks.summary()
-        issue = None
-        if warp_inst and clk.get("sm_mhz"):
-            # what actually bounds the kernel: one warp instruction per scheduler per clock, 4 schedulers x 148 SMs
-            slots = 148 * 4 * float(clk["sm_mhz"]) * 1e6 * (float(kern_ms.mean()) / 1e3)
-            issue = {"warp_instructions_per_launch": int(warp_inst), "issue_slots_per_launch": slots,
-                     "frac": warp_inst / slots, "source": traffic_src,
-                     "note": "executed warp instructions (ncu, same launch configuration) / (592 schedulers x SM clock x "
-                             "kernel time): the fraction of the chip's issue slots the kernel fills"}
+        sm_mhz = float(clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0)
         l2_gather = None
         gp = ROOT / "profiles" / "r1d_gather_roofline.json"
         if gp.exists():
             l2_gather = json.loads(gp.read_text())
+        roofline = issue_roofline(measured_traffic(name, EXTRA_FLAGS), valid_mine, kernel_ms, sm_mhz)
+        roofline.update({
+            "kernel": kernel_name(field, trilinear, EXTRA_FLAGS), "kernel_ms": kernel_ms,
+            "live_samples_per_launch": int(valid_mine), "algorithmic_bytes_per_launch": int(alg_bytes),
+            "vs_hbm": {"achieved_GBs": achieved_gbs, "peak_GBs": hbm, "ratio": achieved_gbs / hbm, "peak_source": hbm_src,
+                       "note": "algorithmic bytes (32 B per live trilinear sample, 4 B nearest, + 4 B per pixel) / kernel "
+                               "time over the measured HBM copy bandwidth; above 1 because the cube is served from "
+                               "L1/L2 (see traffic: DRAM bytes per launch) -- not the binding roof"},
+            "vs_l2_gather": ({"peak_GBs": l2_gather["gather32_l2_64MiB_GBs"],
+                              "ratio": achieved_gbs / l2_gather["gather32_l2_64MiB_GBs"],
+                              "hbm_resident_peak_GBs": l2_gather["gather32_hbm_2GiB_GBs"],
+                              "source": "profiles/r1d_gather_roofline.json (tools/gather_roofline.cu: random independent "
+                                        "32 B sectors out of a 64 MiB L2-resident / 2 GiB HBM-resident buffer)"}
+                             if l2_gather else None),
+        })
 
         cpu = {"value": None, "unit": "frames/s", "cores": 1, "kind": "reference", "sample": "unavailable"}
         parity = None
@@ -623,7 +683,7 @@ def run_b200(args, wl, name):
                                  f"unmodified reference, 1 thread, {secs:.1f} s, scaled by ray count"}
                 zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n)
                 fo = O.orc_frames(poses, S.DEFAULT_AIM_X, fov_w, fov_h, W, H)
-                pr = (rows[0], min(rows[0] + 16, rows[1]))
+                pr = parity_rows
                 want = O.orc_render_cube(zyx, org, sp, trilinear, fo, W, H, nsamples=nsamples, rows=pr,
                                          nthreads=len(os.sched_getaffinity(0)))[:, pr[0]:pr[1]]
                 got = e2e_images[:, pr[0]:pr[1]]
@@ -635,19 +695,36 @@ def run_b200(args, wl, name):
                       "flux_rel_err": float(abs(got.sum(dtype=np.float64) - want.sum(dtype=np.float64)) /
                                             max(want.sum(dtype=np.float64), 1e-300)),
                       "against": "unmodified reference (oracle/_ref)" if nframes > 1 else "oracle restatement"}
+            # the gate: DataCube path bit-exact (tolerance-mode kernels: SURVEY 8(d) tolerance at 99.9 %), CMEM 95 %
+            tolerance_mode = field == "cube" and (EXTRA_FLAGS & capi.FAST_MARCH)
+            if field == "cube" and not tolerance_mode:
+                if not parity["bit_exact"]:
+                    failed.append("DataCube images are not bit-exact against the reference")
+            else:
+                need = 0.999 if field == "cube" else 0.95
+                if parity["pixels_within_1e-5"] < need:
+                    failed.append(f"only {parity['pixels_within_1e-5']:.4%} of pixels within 1e-5 (need {need:.1%})")
+                if parity["flux_rel_err"] > 1e-4:
+                    failed.append(f"integrated flux off by {parity['flux_rel_err']:.3g} (> 1e-4)")
+        if gather_check is not None and not gather_check["identical_to_single_gpu_render"]:
+            failed.append("rank 0's gathered buffer differs from a single-GPU render")
+        if e2e_gather_check is not None and not e2e_gather_check["identical"]:
+            failed.append("e2e: rank 0's host images differ from this rank's own render of the probe frames")
 
+        cfg = workload_config(wl, name, world)
+        cfg["parity_ok"] = not any("gather" not in f and "rank 0" not in f for f in failed)
+        cfg["gather_ok"] = not any("rank 0" in f for f in failed)
         line = {
             "metric": "sxi_frames_per_sec" if nframes > 1 else "frames_per_sec",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(wl, name, world),
-                           l2="flushed between timed steps (256 MiB memset, untimed)",
-                           cube_analysis=cube.info() if cube is not None else None,
-                           gather={"none": "none (1 GPU)",
-                                   "peer": "render kernels store their pixels into rank 0's buffer over NVLink (CUDA IPC), "
-                                           "one all-reduce fence; inside the timed region",
-                                   }.get(gather_mode, "NCCL grouped send/recv to rank 0, inside the timed region")),
+            "config": cfg,
+            "run": {"cube_analysis": cube.info() if cube is not None else None, "extra_flags": EXTRA_FLAGS,
+                    "gather": {"none": "none (1 GPU)",
+                               "peer": "render kernels store their pixels into rank 0's buffer over NVLink (CUDA IPC), "
+                                       "one all-reduce fence; inside the timed region",
+                               }.get(gather_mode, "NCCL grouped send/recv to rank 0, inside the timed region")},
             "rays_per_sec": value * W * H,
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),
             "e2e": {"value": frames_total / (e2e_s / e2e_steps), "unit": "frames/s",
@@ -655,30 +732,22 @@ def run_b200(args, wl, name):
                     "steps": e2e_steps,
                     "api": ("birp_render_cube_sweep / birp_render_cmem_sweep" if nframes > 1 else
                             "birp_frame_setup + birp_render_cube") + " (host poses in, pinned host images out)",
-                    "note": "bytes are per rank; every rank moves its own share"},
+                    "note": e2e_note},
             "gpu_launches": int(launches),
             "device_setup": device_setup,
             "single_frame_latency_ms": latency_ms,
             "render_only_ms_per_rank": kernel_only,
             "gather_check": gather_check,
-            "roofline": {"bound": "hbm" if field == "cube" else "fp32/fp64 pipes (no input bytes)",
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
-                         "gather_microbench_GBs": l2_gather, "issue_slots": issue,
-                         "note": "achieved = algorithmic bytes (32 B per live trilinear sample + 4 B per pixel) / "
-                                 "kernel time; the kernel's real DRAM traffic is ~0.06 % of that (the cube is served "
-                                 "from L1/L2), it is bound by instruction issue (88 % issue-active at 69 executed "
-                                 "instructions per warp-sample, all 64 warps resident) with the L1TEX path behind "
-                                 "(74 %): profiles/r1z_march_orbit_v9.md",
-                         "kernel": ("march_cube_kernel<trilinear>" if trilinear else "march_cube_kernel<nearest>") if field == "cube" else "march_kernel<CmemField>",
-                         "kernel_ms": float(kern_ms.mean()), "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "live_samples_per_launch": int(valid_mine)},
+            "e2e_gather_check": e2e_gather_check,
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "parity": parity,
-            "clocks": clocks.summary(),
+            "failed": failed,
+            "clocks": clk,
             "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line))
+
     h_frames.free()
     h_images.free()
     if peer is not None:
@@ -686,6 +755,9 @@ def run_b200(args, wl, name):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        print("bench.py: FAILED -- " + "; ".join(failed), file=sys.stderr)
+        sys.exit(1)
 
 
 def main():

@@ -19,7 +19,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
 DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY, CMEM_LIBM64, CMEM_NO_FILTER = 8, 16, 32, 64, 128, 256, 512, 1024, 2048
-WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH = 4096, 8192, 16384
+WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH, FAST_MARCH, NO_LEAN_MARCH = 4096, 8192, 16384, 32768, 65536
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),

@@ -468,12 +468,19 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
         if (m > mode) mode = m;
     }
     BIRP_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute));
+    BIRP_CUDA(cudaMemsetAsync(c->d_flags + 1, 0xff, sizeof(int), c->compute));  // running minimum of the bit patterns
     cudaError_t e = birp::launch_scan_positive(cube->d_data, cube->voxels, c->d_flags, c->compute);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "scan_positive launch: %s", cudaGetErrorString(e));
-    BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
     v.positive = (c->h_status[0] == 0) ? 1 : ((c->h_status[0] & 2) == 0) ? 2 : 0;
-    *c->h_status = 0;
+    // value range of a positive cube (every interpolated sample lies inside it): what the lean march relies on
+    v.vmin = v.vmax = 0.f;
+    if (v.positive == 1) {
+        std::memcpy(&v.vmin, &c->h_status[1], 4);
+        std::memcpy(&v.vmax, &c->h_status[2], 4);
+    }
+    c->h_status[0] = c->h_status[1] = c->h_status[2] = 0;
 
     // Layered-texture copy for the two-gather corner fetch (trilinear only).  Any failure here
     // just leaves the global-load path in place.
@@ -630,18 +637,6 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.sx = spacing[0];
     v.sy = spacing[1];
     v.sz = spacing[2];
-    // value range of the grid, for BIRP_LEAN_MARCH (host uploads of at most 2^24 voxels; only read for a cube the
-    // device scan classifies as positive, so NaNs -- which these comparisons skip -- cannot matter)
-    v.vmin = v.vmax = 0.f;
-    if (!src_on_device && voxels <= (size_t(1) << 24)) {
-        float lo = src[0], hi = src[0];
-        for (size_t i = 1; i < voxels; ++i) {
-            lo = src[i] < lo ? src[i] : lo;
-            hi = src[i] > hi ? src[i] : hi;
-        }
-        v.vmin = lo;
-        v.vmax = hi;
-    }
     rc = finish_cube(c, cube);
     if (rc) {
         destroy_cube(cube);

@@ -51,8 +51,8 @@ struct CubeView {
     // corners of a cell are ONE aligned 32-byte load (LDG.256), i.e. one L1 request per sample instead of two.
     // 8x the grid in device memory.
     const float* __restrict__ oct;
-    // smallest / largest voxel of a cube uploaded from the host (0, 0: unknown); every sample interpolated from a
-    // positive cube lies between them (BIRP_LEAN_MARCH; host-side use only)
+    // smallest / largest voxel of a positive cube, found by scan_positive_kernel at upload (0, 0 otherwise); every
+    // sample interpolated from a positive cube lies between them (lean march; host-side use only)
     float vmin, vmax;
 };
 

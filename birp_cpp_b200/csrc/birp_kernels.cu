@@ -430,17 +430,30 @@ __global__ void __launch_bounds__(256) verify_quads_kernel(const float* __restri
 }
 
 // ---- upload-time analysis kernels -------------------------------------------------------
-// flag |= 1 unless every voxel is finite and > 0; flag |= 2 unless every voxel is finite and > 0 or +0
+// flag[0] |= 1 unless every voxel is finite and > 0; flag[0] |= 2 unless every voxel is finite and > 0 or +0;
+// flag[1] / flag[2] = bit patterns of the smallest / largest finite positive voxel (positive floats order like
+// their bit patterns; flag[1] starts at 0xffffffff, flag[2] at 0) -- the value range the lean march relies on
 __global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restrict__ v, size_t n, int* flag) {
     int bad = 0;
+    unsigned lo = 0xffffffffu, hi = 0u;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float x = __ldg(v + i);
         const bool pos = x > 0.f && x < CUDART_INF_F;
         if (!pos) bad |= 1;
         if (!pos && __float_as_uint(x) != 0u) bad |= 2;
+        if (pos) {
+            lo = min(lo, __float_as_uint(x));
+            hi = max(hi, __float_as_uint(x));
+        }
     }
     bad = __reduce_or_sync(0xffffffffu, bad);
-    if (bad && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicOr(flag, bad);
+        atomicMin(reinterpret_cast<unsigned*>(flag) + 1, lo);
+        atomicMax(reinterpret_cast<unsigned*>(flag) + 2, hi);
+    }
 }
 
 // Exhaustive proof for one spacing: for EVERY fp32 ingress a of the hot window,
@@ -690,11 +703,12 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         view.loy = view.lox;
         view.loz = view.lox;
     }
-    // BIRP_LEAN_MARCH: fp32 cell index (grids of at most 2^24 voxels) and no range test in the scale -- allowed when
-    // every sample of the positive cube, which lies in [vmin, vmax], scales into [2^-120, 2^120) (the scale is a
-    // monotone function of the sample for a positive ray width)
+    // Lean march (the default where its preconditions hold; BIRP_NO_LEAN_MARCH keeps the general loop as the
+    // cross-check): fp32 cell index (grids of at most 2^24 voxels) and no range test in the scale -- allowed when
+    // every sample of the positive cube, which lies in [vmin, vmax] (scan_positive_kernel at upload), scales into
+    // [2^-120, 2^120) (the scale is a monotone function of the sample for a positive ray width)
     bool lean = false;
-    if ((flags & BIRP_LEAN_MARCH) && fetch == 5 && lerp == 1 && (long long)cube.nx * cube.ny * cube.nz <= (1LL << 24) &&
+    if (!(flags & BIRP_NO_LEAN_MARCH) && fetch == 5 && lerp == 1 && (long long)cube.nx * cube.ny * cube.nz <= (1LL << 24) &&
         cube.vmin > 0.f && cube.vmax >= cube.vmin && a.ray_width > 0.f) {
         const volatile float plo = cube.vmin * a.ray_width, phi = cube.vmax * a.ray_width;
         const float ylo = (float)((double)plo * BIRP_SCALE_K), yhi = (float)((double)phi * BIRP_SCALE_K);

@@ -85,7 +85,9 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
 
 # corner fetch (default: one 32-byte oct load, end of the in-bounds run located once per ray; two quad loads, same
 # march; two quad loads with the window test in every step; tld4 + 4 loads; two tld4; 8 loads) x division x lerp flavour
-_FETCH = [0, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY, capi.NO_QUADS | capi.NO_TEXTURE]
+# (flags 0 = the lean span march on a positive cube of at most 2^24 voxels, NO_LEAN_MARCH = the general span march)
+_FETCH = [0, capi.NO_LEAN_MARCH, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY,
+          capi.NO_QUADS | capi.NO_TEXTURE]
 _DIV = [0, capi.DIV_TWO_STEP, capi.DIV_IEEE]
 _LERP = [0, capi.GENERAL_LERP]
 
@@ -499,7 +501,8 @@ def test_config3_256cube_1024_image(gpu, n):
         assert_bit_exact(got, want, "256^3, 1024x1024, 200 samples")
         assert c.info()["texture"]
         assert c.info()["quads"]
-        for fl in (capi.NO_TEXTURE, capi.TEXTURE_ONLY, capi.NO_QUADS, capi.QUADS_ONLY, capi.NO_QUADS | capi.NO_TEXTURE):
+        for fl in (capi.NO_LEAN_MARCH, capi.NO_TEXTURE, capi.TEXTURE_ONLY, capi.NO_QUADS, capi.QUADS_ONLY,
+                   capi.NO_QUADS | capi.NO_TEXTURE):
             assert_bit_exact(c.render(fp, 1024, 1024, nsamples=200, trilinear=True, extra_flags=fl), want,
                              f"corner-fetch variant {fl}")
         # fine step: a row band against the oracle, the whole image through band-tiling consistency

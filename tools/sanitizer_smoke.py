@@ -21,7 +21,7 @@ zyx0[10:20] = 0.0  # a non-negative cube (lerp_nonneg)
 for grid in (zyx, zyx0):
     c = capi.Cube(grid, org, sp)
     for tri in (False, True):
-        for fl in (0, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.NO_QUADS | capi.NO_TEXTURE, capi.TEXTURE_ONLY,
+        for fl in (0, capi.NO_LEAN_MARCH, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.NO_QUADS | capi.NO_TEXTURE, capi.TEXTURE_ONLY,
                    capi.GENERAL_LERP, capi.DIV_IEEE):
             got = c.render(fp, W, H, trilinear=tri, extra_flags=fl)
             want = O.orc_render_cube(grid, org, sp, tri, fo, W, H)
