@@ -24,6 +24,8 @@ struct birp_cube {
     cudaArray_t tex_array = nullptr;  // layered copy for the gather path (optional)
     float4* d_quad = nullptr;         // quad copy for the 16-byte corner fetch (optional)
     float* d_oct = nullptr;           // oct copy for the 32-byte corner fetch (optional)
+    float* d_poly = nullptr;          // poly copy for the tolerance-mode march (built at the first BIRP_FAST_MARCH render)
+    bool poly_tried = false;
 };
 
 static_assert(birp::kTinyIngress == BIRP_TINY_INGRESS, "birp_host.h and birp_device.cuh disagree on 2^-100");
@@ -637,6 +639,10 @@ static int make_cube(const float* src, bool src_on_device, int nx, int ny, int n
     v.sx = spacing[0];
     v.sy = spacing[1];
     v.sz = spacing[2];
+    v.rx64 = 1.0 / (double)spacing[0];
+    v.ry64 = 1.0 / (double)spacing[1];
+    v.rz64 = 1.0 / (double)spacing[2];
+    v.poly = nullptr;
     rc = finish_cube(c, cube);
     if (rc) {
         destroy_cube(cube);
@@ -676,8 +682,37 @@ static void destroy_cube(birp_cube* cube) {
     if (cube->tex_array) cudaFreeArray(cube->tex_array);
     if (cube->d_quad) cudaFree(cube->d_quad);
     if (cube->d_oct) cudaFree(cube->d_oct);
+    if (cube->d_poly) cudaFree(cube->d_poly);
     cudaFree(cube->d_data);
     delete cube;
+}
+
+// The poly copy of the tolerance-mode march (BIRP_FAST_MARCH): built once, at the first render that asks for it
+// (8x the grid, only when it fits into half of the free device memory; without it the bit-exact march runs).
+// The cube handle is const at the C ABI; the copy is a cache inside the opaque object.
+static int ensure_poly(DeviceCtx* c, const birp_cube* cube_c, int flags) {
+    if (!(flags & BIRP_FAST_MARCH) || !(flags & BIRP_TRILINEAR)) return BIRP_OK;
+    birp_cube* cube = const_cast<birp_cube*>(cube_c);
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cube->poly_tried) return BIRP_OK;
+    cube->poly_tried = true;
+    const birp::CubeView& v = cube->view;
+    if (v.nx < 2 || v.ny < 2 || v.nz < 2) return BIRP_OK;
+    const size_t bytes = cube->voxels * 8 * sizeof(float);
+    size_t free_b = 0, total_b = 0;
+    cudaError_t e = cudaMemGetInfo(&free_b, &total_b);
+    if (e == cudaSuccess && free_b / 2 >= bytes) e = cudaMalloc(&cube->d_poly, bytes);
+    else if (e == cudaSuccess) e = cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = birp::launch_pack_poly(v, cube->d_poly, c->compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (cube->d_poly) cudaFree(cube->d_poly);
+        cube->d_poly = nullptr;
+        return BIRP_OK;  // optional copy: the exact march takes over
+    }
+    cube->view.poly = cube->d_poly;
+    return BIRP_OK;
 }
 
 void birp_cube_free(birp_cube* cube) {
@@ -693,6 +728,8 @@ int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframe
     rc = get_ctx(&c);
     if (rc) return rc;
     if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    rc = ensure_poly(c, cube, flags);
+    if (rc) return rc;
     const birp::CubeView view = cube->view;
     int* d_status = c->d_status;
     return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
@@ -751,6 +788,8 @@ int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframe
     rc = get_ctx(&c);
     if (rc) return rc;
     if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    rc = ensure_poly(c, cube, flags);
+    if (rc) return rc;
     const birp::CubeView view = cube->view;
     int* d_status = c->d_status;
     return render_host(c, sw.frames_out, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
@@ -889,6 +928,8 @@ int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_f
     rc = get_ctx(&c);
     if (rc) return rc;
     if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    rc = ensure_poly(c, cube, flags);
+    if (rc) return rc;
     RayTable table;
     {
         std::lock_guard<std::mutex> lk(c->mu);

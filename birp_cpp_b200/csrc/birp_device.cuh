@@ -54,6 +54,12 @@ struct CubeView {
     // smallest / largest voxel of a positive cube, found by scan_positive_kernel at upload (0, 0 otherwise); every
     // sample interpolated from a positive cube lies between them (lean march; host-side use only)
     float vmin, vmax;
+    // "poly" copy of the grid for the tolerance-mode march (BIRP_FAST_MARCH), or nullptr: 32-byte records, the
+    // trilinear interpolant of cell (x, y, z) as a polynomial in its three weights (see fast_sample); built at the
+    // first BIRP_FAST_MARCH render of the cube.  8x the grid.
+    const float* __restrict__ poly;
+    // 1 / spacing in double: the tolerance-mode march makes its per-ray index-space origin and direction with them
+    double rx64, ry64, rz64;
 };
 
 // one 32-byte load through the read-only path (sm_100: LDG.E.256)
@@ -584,6 +590,156 @@ __device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState
             return sdist;
         }
         r.acc = __fadd_rn(r.acc, s);
+        sdist += 4;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Tolerance-mode march (BIRP_FAST_MARCH; trilinear only; opt-in -- the bit-exact march stays the default).
+//
+// north_star asks for 1e-5 per pixel and 1e-4 in the integrated flux, not for bit parity.  What bit parity costs
+// is the arithmetic of the reference's un-fused x86 code: three rounded operations per coordinate, three
+// corrected divisions, seven three-operation lerps and an fp64 scale with exactness tests per SAMPLE.  This march
+// keeps everything that DECIDES something exact and relaxes only the value of a hot sample:
+//
+//  * which steps of a ray are inside the cube is decided with the reference's own arithmetic -- the same window
+//    test and the same bisection as march_steps_span -- and every sample outside the hot run (cube exit, first
+//    cell of an axis, NaN coordinates) goes through the literal transcription (cube_sample + scale_sample), which
+//    also decides where the ray ends.  So a ray ends at the same step as in the reference;
+//  * a hot sample whose cell has a negative or non-finite corner (only cubes outside the non-negative class have
+//    such cells) is evaluated by the literal transcription too: the sign of its value ends the ray.  Those cells
+//    are marked in their record (c0 = NaN), the test is one compare on the interpolated value.  In every other
+//    cell the reference's sample is >= 0 whatever the rounding (a lerp of non-negative numbers with weights in
+//    [0, 1]), so the ray lives on and only the VALUE matters;
+//  * the value: index = g + t_k * e per axis with the per-ray index-space origin g = (p - o) / s and direction
+//    e = d / s made once per ray in fp64 (one FFMA per axis and step instead of three roundings and a division),
+//    floor and weight by FRND + FADD, the cell's interpolant as a polynomial in the weights
+//        s = c0 + c1 tx + c2 ty + c3 tx ty + tz (c4 + c5 tx + c6 ty + c7 tx ty)
+//    whose eight coefficients are ONE 32-byte record of the poly copy (7 FFMA instead of 21 operations), the raw
+//    samples summed in fp32 and the scale (src/Camera.cpp:201) applied once per ray.
+//
+// A hot step is 1 LDS + 3 FFMA + 3 FRND + 3 FADD + (2 FFMA + F2I | FFMA + 2 F2I + IMAD) + IMAD.WIDE + LDG.256 +
+// 7 FFMA + FADD + loop: 27-29 instructions against 62-66.  Error against the reference: both sides place a sample
+// within a few ulp of the coordinate magnitude (~1e-5 of a cell); pixels differ by ~1e-6 relative
+// (tests/test_gpu_parity.py::test_fast_march_*: >= 99.9 % of pixels within 1e-5, flux within 1e-4).
+// ---------------------------------------------------------------------------------
+struct FastRay {
+    float gx, gy, gz;  // index-space position of the camera: (p - o) / s
+    float ex, ey, ez;  // index-space direction: d / s
+};
+
+__device__ __forceinline__ FastRay fast_ray(const CubeView& c, const RayState& r) {
+    FastRay q;
+    q.gx = (float)(((double)r.px - (double)c.ox) * c.rx64);
+    q.gy = (float)(((double)r.py - (double)c.oy) * c.ry64);
+    q.gz = (float)(((double)r.pz - (double)c.oz) * c.rz64);
+    q.ex = (float)((double)r.dx * c.rx64);
+    q.ey = (float)((double)r.dy * c.ry64);
+    q.ez = (float)((double)r.dz * c.rz64);
+    return q;
+}
+
+// coefficients of one cell from its eight corners (pack_poly_kernel and the host harness), in fp64, rounded once.
+// A cell with a negative or non-finite corner gets c0 = NaN: every sample in it comes out NaN and takes the
+// literal path.
+__device__ __forceinline__ void poly_coefficients(float v000, float v001, float v010, float v011, float v100, float v101,
+                                                  float v110, float v111, float c[8]) {
+    const double a = v000, b = v001, d = v010, e = v011, f = v100, g = v101, h = v110, k = v111;
+    c[0] = v000;
+    c[1] = (float)(b - a);
+    c[2] = (float)(d - a);
+    c[3] = (float)((e - d) - (b - a));
+    c[4] = (float)(f - a);
+    c[5] = (float)((g - f) - (b - a));
+    c[6] = (float)((h - f) - (d - a));
+    c[7] = (float)(((k - h) - (g - f)) - ((e - d) - (b - a)));
+    const float lo = fminf(fminf(fminf(v000, v001), fminf(v010, v011)), fminf(fminf(v100, v101), fminf(v110, v111)));
+    const float sum = v000 + v001 + v010 + v011 + v100 + v101 + v110 + v111;  // inf or NaN iff a corner is
+    if (!(lo >= 0.f) || !(fabsf(sum) <= 3.402823466e+38f)) c[0] = __int_as_float(0x7fc00000);
+}
+
+// value of the hot sample at table distance tk.  FIDX: grids of at most 2^24 voxels compute the cell index in fp32.
+template <bool FIDX>
+__device__ __forceinline__ float fast_sample(const CubeView& c, const FastRay& q, float tk) {
+    const float fx = __fmaf_rn(tk, q.ex, q.gx);
+    const float fy = __fmaf_rn(tk, q.ey, q.gy);
+    const float fz = __fmaf_rn(tk, q.ez, q.gz);
+    const float ix = floorf(fx), iy = floorf(fy), iz = floorf(fz);
+    const float tx = __fsub_rn(fx, ix), ty = __fsub_rn(fy, iy), tz = __fsub_rn(fz, iz);
+    long long cell;
+    if (FIDX) {
+        cell = (int)__fmaf_rn(__fmaf_rn(iz, c.fny, iy), c.fnx, ix);
+    } else {
+        cell = (int)iz * c.slab + (int)__fmaf_rn(iy, c.fnx, ix);  // (each term below 2^31: checked at upload)
+    }
+    float c0, c1, c2, c3, c4, c5, c6, c7;
+    load_oct(reinterpret_cast<const char*>(c.poly) + cell * 32, c0, c1, c2, c3, c4, c5, c6, c7);
+    const float hi = __fmaf_rn(ty, __fmaf_rn(tx, c7, c6), __fmaf_rn(tx, c5, c4));
+    const float lo = __fmaf_rn(ty, __fmaf_rn(tx, c3, c2), __fmaf_rn(tx, c1, c0));
+    return __fmaf_rn(tz, hi, lo);
+}
+
+// the literal sample of one step (cold path of the tolerance-mode march): returns false when the ray ends here
+__device__ __forceinline__ bool fast_cold_step(const CubeView& c, RayState& r, unsigned sdist, float ray_width,
+                                               int* status) {
+    const float tk = table_entry(sdist);
+    const float x = __fadd_rn(__fmul_rn(r.dx, tk), r.px);
+    const float y = __fadd_rn(__fmul_rn(r.dy, tk), r.py);
+    const float z = __fadd_rn(__fmul_rn(r.dz, tk), r.pz);
+    bool nan_index = false;
+    const float s = cube_sample<true>(c, x, y, z, nan_index);
+    if (nan_index) atomicOr(status, kStatusNanIndex);
+    if (scale_sample(s, ray_width) < 0.f) return false;  // src/Camera.cpp:207-210, decided on the reference's value
+    r.acc = __fadd_rn(r.acc, s);                         // (r.acc is the sum of RAW samples in this march)
+    return true;
+}
+
+// SIGNS: the cube has cells with negative / non-finite corners (class 0): test every hot sample for the NaN mark.
+template <bool SIGNS, bool FIDX>
+__device__ __forceinline__ unsigned march_steps_fast(const CubeView& c, RayState& r, const FastRay& q, unsigned sdist,
+                                                     const unsigned send, float ray_width, int* status, bool& alive) {
+    for (;;) {
+        asm volatile("" : "+r"(sdist));  // (keeps the outer loop separate from the hot one, see march_steps)
+        if (sdist == send) return sdist;
+        float xi, yi, zi;
+        if (step_ingress(c, r, sdist, xi, yi, zi)) {
+            // end of the hot run that starts here, by the reference's own window test (see march_steps_span)
+            unsigned lo = sdist + 4, hi = send;
+            while (lo < hi) {
+                const unsigned mid = lo + (((hi - lo) >> 3) << 2);
+                float ux, uy, uz;
+                if (step_ingress(c, r, mid, ux, uy, uz)) lo = mid + 4;
+                else hi = mid;
+            }
+            const unsigned hend = lo;
+            for (;;) {
+                asm volatile("" : "+r"(sdist));
+                bool marked = false;
+                do {
+                    const float s = fast_sample<FIDX>(c, q, table_entry(sdist));
+                    if (SIGNS && !(s >= 0.f)) {
+                        marked = true;
+                        break;
+                    }
+                    r.acc = __fadd_rn(r.acc, s);
+                    sdist += 4;
+                } while (sdist != hend);
+                if (!SIGNS || !marked) break;
+                // a cell with a negative / non-finite corner (or a rounding-level negative next to a zero corner):
+                // the literal sample decides
+                if (!fast_cold_step(c, r, sdist, ray_width, status)) {
+                    alive = false;
+                    return sdist;
+                }
+                sdist += 4;
+                if (sdist == hend) break;
+            }
+            if (sdist == send) return sdist;
+        }
+        if (!fast_cold_step(c, r, sdist, ray_width, status)) {
+            alive = false;
+            return sdist;
+        }
         sdist += 4;
     }
 }

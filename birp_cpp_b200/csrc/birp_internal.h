@@ -51,6 +51,8 @@ cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaSt
 cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, cudaStream_t stream);
 // the same for the oct copy (32-byte records: both z layers of a cell)
 cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cudaStream_t stream);
+// the poly copy for the tolerance-mode march (32-byte records: the cell's interpolant as polynomial coefficients)
+cudaError_t launch_pack_poly(const CubeView& cube, float* d_poly, cudaStream_t stream);
 cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 

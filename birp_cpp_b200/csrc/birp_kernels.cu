@@ -220,6 +220,86 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     }
 }
 
+
+// Tolerance-mode DataCube march (BIRP_FAST_MARCH): same work decomposition and prologue as march_cube_kernel; the
+// per-ray loop is march_steps_fast (birp_device.cuh), the pixel is the fp32 sum of the raw samples scaled once
+// (src/Camera.cpp:201 applied to the sum).
+#ifndef BIRP_FAST_MIN_BLOCKS
+#define BIRP_FAST_MIN_BLOCKS 8
+#endif
+template <bool SIGNS, bool FIDX>
+__global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cube_fast_kernel(const MarchArgs a, const CubeView c) {
+    __shared__ float s_dist[kSmemDist + 1];
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
+    const int first_chunk = min(kSmemDist, a.nsamples);
+    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
+    __syncthreads();
+    CubeView cc = c;
+    float ray_width = a.ray_width;
+    pin_uniform(cc.fnx), pin_uniform(cc.fny);
+    pin_uniform(cc.slab);
+    {
+        long long q0 = (long long)cc.poly;
+        pin_uniform(q0);
+        cc.poly = reinterpret_cast<const float*>(q0);
+    }
+
+    int f = 0, i = 0, j = 0;
+    const bool owns_pixel = lane_ray(a, f, i, j);
+    if (!owns_pixel && a.nsamples <= kSmemDist) return;
+    RayState r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    FastRay q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float* pix = nullptr;
+    if (owns_pixel) {
+        const birp_frame* __restrict__ frp = a.frames + f;
+        pixel_direction(*frp, i, j, (float)a.W, (float)a.H, r.dx, r.dy, r.dz);
+        r.px = frp->pos[0];
+        r.py = frp->pos[1];
+        r.pz = frp->pos[2];
+        q = fast_ray(cc, r);
+        pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
+    }
+    bool alive = owns_pixel;
+    unsigned nlive4 = 0;
+    if (alive)
+        nlive4 = march_steps_fast<SIGNS, FIDX>(cc, r, q, s_base, s_base + 4u * first_chunk, ray_width, a.status, alive) - s_base;
+    for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
+        const int chunk = min(kSmemDist, a.nsamples - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
+        __syncthreads();
+        if (alive)
+            nlive4 += march_steps_fast<SIGNS, FIDX>(cc, r, q, s_base, s_base + 4u * chunk, ray_width, a.status, alive) - s_base;
+    }
+    if (owns_pixel) {
+        const float total = __double2float_rn(__dmul_rn((double)__fmul_rn(r.acc, ray_width), a.scale_k));
+        *pix = a.accumulate ? __fadd_rn(*pix, total) : total;
+        if (a.valid) atomicAdd(a.valid, (unsigned long long)(nlive4 >> 2));
+    }
+}
+
+// poly copy: the trilinear interpolant of every cell as eight polynomial coefficients (poly_coefficients), neighbours
+// clamped at the last row / column / layer like the oct copy
+__global__ void __launch_bounds__(256) pack_poly_kernel(const float* __restrict__ v, int nx, int ny, int nz,
+                                                        float4* __restrict__ poly) {
+    const size_t n = (size_t)nx * ny * nz;
+    const size_t slab = (size_t)nx * ny;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(t % nx);
+        const int y = (int)((t / nx) % ny);
+        const int z = (int)(t / slab);
+        const int dx = (x + 1 < nx) ? 1 : 0;
+        const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+        const size_t u = t + ((z + 1 < nz) ? slab : 0);
+        float c[8];
+        poly_coefficients(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx), __ldg(v + u),
+                          __ldg(v + u + dx), __ldg(v + u + dy), __ldg(v + u + dy + dx), c);
+        poly[2 * t] = make_float4(c[0], c[1], c[2], c[3]);
+        poly[2 * t + 1] = make_float4(c[4], c[5], c[6], c[7]);
+    }
+}
+
 // Tile shape: split the warp's 32 rays so that the tile is as square as possible in ANGLE
 // (the SXI pixel is 1.7x wider than tall once the reference's extra aspect factor is applied):
 // compact ray bundles touch fewer cache lines per corner load.
@@ -697,6 +777,20 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         else if (has_quad) fetch = 4;
         else if (has_tex) fetch = 2;
     }
+    // BIRP_FAST_MARCH (trilinear, monotone ray table, poly copy present): the tolerance-mode march
+    if (tri && (flags & BIRP_FAST_MARCH) && cube.poly != nullptr && g.monotone_table) {
+        const bool signs = cube.positive == 0;
+        const bool fidx = (long long)cube.nx * cube.ny * cube.nz <= (1LL << 24);
+        if (signs) {
+            if (fidx) march_cube_fast_kernel<true, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            else march_cube_fast_kernel<true, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+        } else {
+            if (fidx) march_cube_fast_kernel<false, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            else march_cube_fast_kernel<false, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
     CubeView view = cube;
     if (!tri) {  // nearest neighbour has no interpolation weight to protect: the first cells stay hot
         view.lox = BIRP_TINY_INGRESS;
@@ -745,6 +839,12 @@ cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cud
     if (e != cudaSuccess) return e;
     verify_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_oct, d_bad);
     g_launches.fetch_add(2, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_poly(const CubeView& cube, float* d_poly, cudaStream_t stream) {
+    pack_poly_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, reinterpret_cast<float4*>(d_poly));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 

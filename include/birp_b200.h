@@ -80,6 +80,14 @@ enum {
                                    [2^-120, 2^120) computes the cell index in fp32 and drops the range / midpoint tests of the
                                    scale shortcut, which that range makes redundant (identical results, four instructions
                                    fewer per sample, measured +1.9 %); this flag keeps the general loop as the cross-check */
+    BIRP_FAST_MARCH = 32768,    /* DataCube, trilinear, opt-in: tolerance mode.  The default march is bit-identical to the
+                                   reference Camera; with this flag the VALUE of an in-bounds sample is computed with fused
+                                   arithmetic (one FFMA per coordinate, the cell's interpolant as a polynomial from one
+                                   32-byte record, the scale applied once per ray): 27 instead of 62 instructions per sample.
+                                   Which steps are in bounds and where a ray ends are still decided with the reference's own
+                                   arithmetic, so images agree with the reference to ~1e-6 relative per pixel (north_star's
+                                   tolerance: 1e-5 per pixel, 1e-4 integrated flux).  Needs a further copy of the grid (8x,
+                                   built at the first such render; without room for it the exact march runs) */
     BIRP_WINDOW_PER_STEP = 4096 /* DataCube only: test the cube bounds window at every step of the march instead
                                    of locating the end of each ray's in-bounds run once by bisection over the
                                    (monotone) ray table (identical results; kept as the cross-check) */
