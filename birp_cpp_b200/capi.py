@@ -91,6 +91,7 @@ SIGNATURES = {
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
     "birp_selftest_cmem_filter": (C.c_int, [_vp, C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
+    "birp_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 
@@ -450,6 +451,11 @@ def selftest_cmem_filter(params: np.ndarray, n: int = 1 << 24) -> dict:
 
 def launch_count() -> int:
     return int(lib().birp_launch_count())
+
+
+def set_tuning(name: str, value: int) -> None:
+    """diagnostic launch-shape knobs (birp_set_tuning): tile_w_log2, tile_swizzle, fast_variant, fast_kstep"""
+    _check(lib().birp_set_tuning(name.encode(), int(value)))
 
 
 def device_count() -> int:

@@ -58,6 +58,7 @@ struct RayTable {
     float* d_dist = nullptr;
     float ray_width = 0.f;
     bool monotone = false;  // dist[] never decreases, or never increases (no NaN): RenderGeom::monotone_table
+    double step = 0.0;      // maxdist / nsamples: the table is host_ray_table's uniform one (RenderGeom::fast_step)
 };
 
 // Per-device state.  Created lazily on first use from the thread that owns the device.
@@ -82,6 +83,9 @@ struct DeviceCtx {
     // CMEM parameter record (raw bytes) -> may the region filter be used?  (self-test at first use, see cmem_flags)
     std::map<std::string, bool> cmem_filter_ok;
     int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
+    int tile_swizzle = 0;     // BIRP_TILE_SWIZZLE override (experiments)
+    int fast_variant = -1;    // BIRP_FAST_VARIANT override (experiments)
+    int fast_kstep = 1;       // BIRP_FAST_KSTEP=0: the tolerance-mode march reads the ray table (experiments)
     std::mutex mu;
 };
 
@@ -113,6 +117,9 @@ int get_ctx(DeviceCtx** out) {
     BIRP_CUDA(cudaHostAlloc(&c->h_status, 4 * sizeof(int), cudaHostAllocDefault));
     BIRP_CUDA(cudaMalloc(&c->d_flags, 4 * sizeof(int)));
     if (const char* t = getenv("BIRP_TILE_W_LOG2")) c->tile_w_log2 = atoi(t);
+    if (const char* t = getenv("BIRP_TILE_SWIZZLE")) c->tile_swizzle = atoi(t);
+    if (const char* t = getenv("BIRP_FAST_VARIANT")) c->fast_variant = atoi(t);
+    if (const char* t = getenv("BIRP_FAST_KSTEP")) c->fast_kstep = atoi(t);
     g_ctx[dev] = c;
     *out = c;
     return BIRP_OK;
@@ -135,6 +142,7 @@ int get_ray_table(DeviceCtx* c, int nsamples, int maxdist, cudaStream_t stream, 
         if (i > 0 && !(h[i] <= h[i - 1])) down = false;
     }
     t.monotone = up || down;
+    t.step = (maxdist > 0 && nsamples < (1 << 22)) ? (double)maxdist / (double)nsamples : 0.0;
     BIRP_CUDA(cudaMalloc(&t.d_dist, sizeof(float) * nsamples));
     // synchronous copy from pageable memory: the table is ready for any stream afterwards
     BIRP_CUDA(cudaMemcpy(t.d_dist, h.data(), sizeof(float) * nsamples, cudaMemcpyHostToDevice));
@@ -295,6 +303,17 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
         g.monotone_table = table.monotone;
         g.tile_w_log2 = c->tile_w_log2;
+    g.fast_variant = c->fast_variant;
+    g.tile_swizzle = c->tile_swizzle;
+    g.fast_kstep = c->fast_kstep;
+    g.fast_step = table.step;
+        g.fast_variant = c->fast_variant;
+    g.tile_swizzle = c->tile_swizzle;
+        g.tile_swizzle = c->tile_swizzle;
+    g.fast_kstep = c->fast_kstep;
+    g.fast_step = table.step;
+        g.fast_kstep = c->fast_kstep;
+        g.fast_step = table.step;
         cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
         if (e != cudaSuccess)
             return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -939,6 +958,10 @@ int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_f
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
     g.monotone_table = table.monotone;
     g.tile_w_log2 = c->tile_w_log2;
+    g.fast_variant = c->fast_variant;
+    g.tile_swizzle = c->tile_swizzle;
+    g.fast_kstep = c->fast_kstep;
+    g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
     cudaError_t e = birp::launch_render_cube(cube->view, d_frames, g, table.d_dist, flags, d_images,
@@ -974,6 +997,10 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
     birp::RenderGeom g{nframes, W, H, row_begin, row_end, nsamples, table.ray_width};
     g.monotone_table = table.monotone;
     g.tile_w_log2 = c->tile_w_log2;
+    g.fast_variant = c->fast_variant;
+    g.tile_swizzle = c->tile_swizzle;
+    g.fast_kstep = c->fast_kstep;
+    g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
     rc = cmem_flags(c, *params, flags, &flags);  // (first use of a parameter set: a self-test on the library's stream)
@@ -1062,5 +1089,20 @@ int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out
 }
 
 unsigned long long birp_launch_count(void) { return birp::launch_count(); }
+
+int birp_set_tuning(const char* name, int value) {
+    if (!name) return set_error(BIRP_ERR_ARG, "null name");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const std::string n(name);
+    if (n == "tile_w_log2") c->tile_w_log2 = value;
+    else if (n == "tile_swizzle") c->tile_swizzle = value;
+    else if (n == "fast_variant") c->fast_variant = value;
+    else if (n == "fast_kstep") c->fast_kstep = value;
+    else return set_error(BIRP_ERR_ARG, "unknown tuning knob '%s'", name);
+    return BIRP_OK;
+}
 
 }  // extern "C"

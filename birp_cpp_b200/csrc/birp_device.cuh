@@ -58,6 +58,8 @@ struct CubeView {
     // trilinear interpolant of cell (x, y, z) as a polynomial in its three weights (see fast_sample); built at the
     // first BIRP_FAST_MARCH render of the cube.  8x the grid.
     const float* __restrict__ poly;
+    int poly_bytes;  // 32, opaque to the compiler (set by the kernel: the multiplier of the record address stays in a register)
+    int poly_bias;   // set by the kernel: (B * ny + B) * nx + B (mod 2^32) with B the bit pattern of 1.5 * 2^23 (fast_sample<0>)
     // 1 / spacing in double: the tolerance-mode march makes its per-ray index-space origin and direction with them
     double rx64, ry64, rz64;
 };
@@ -608,75 +610,108 @@ __device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState
 //    also decides where the ray ends.  So a ray ends at the same step as in the reference;
 //  * a hot sample whose cell has a negative or non-finite corner (only cubes outside the non-negative class have
 //    such cells) is evaluated by the literal transcription too: the sign of its value ends the ray.  Those cells
-//    are marked in their record (c0 = NaN), the test is one compare on the interpolated value.  In every other
-//    cell the reference's sample is >= 0 whatever the rounding (a lerp of non-negative numbers with weights in
-//    [0, 1]), so the ray lives on and only the VALUE matters;
-//  * the value: index = g + t_k * e per axis with the per-ray index-space origin g = (p - o) / s and direction
-//    e = d / s made once per ray in fp64 (one FFMA per axis and step instead of three roundings and a division),
-//    floor and weight by FRND + FADD, the cell's interpolant as a polynomial in the weights
-//        s = c0 + c1 tx + c2 ty + c3 tx ty + tz (c4 + c5 tx + c6 ty + c7 tx ty)
+//    are marked in their record (first coefficient NaN), the test is one compare on the interpolated value.  In
+//    every other cell the reference's sample is >= 0 whatever the rounding (a lerp of non-negative numbers with
+//    weights in [0, 1]), so the ray lives on and only the VALUE matters;
+//  * the value: per axis, index - 1/2 = g + t_k * e with the per-ray index-space origin g = (p - o) / s - 1/2 and
+//    direction e = d / s made once per ray in fp64 (one FFMA per axis and step instead of three roundings and a
+//    division); i = rint(index - 1/2) is the cell, u = (index - 1/2) - i in [-1/2, 1/2] its CENTRED weight -- either
+//    one FRND (XU pipe, a quarter of the FMA pipe's rate) or two FADD through the constant 1.5 * 2^23; on an
+//    integer index the tie may pick the cell below with u = +1/2, which is the same point of the same continuous
+//    interpolant; the cell's interpolant as a polynomial in the centred weights
+//        s = C0 + C1 u + C2 v + C3 uv + w (C4 + C5 u + C6 v + C7 uv)
 //    whose eight coefficients are ONE 32-byte record of the poly copy (7 FFMA instead of 21 operations), the raw
 //    samples summed in fp32 and the scale (src/Camera.cpp:201) applied once per ray.
 //
-// A hot step is 1 LDS + 3 FFMA + 3 FRND + 3 FADD + (2 FFMA + F2I | FFMA + 2 F2I + IMAD) + IMAD.WIDE + LDG.256 +
-// 7 FFMA + FADD + loop: 27-29 instructions against 62-66.  Error against the reference: both sides place a sample
-// within a few ulp of the coordinate magnitude (~1e-5 of a cell); pixels differ by ~1e-6 relative
-// (tests/test_gpu_parity.py::test_fast_march_*: >= 99.9 % of pixels within 1e-5, flux within 1e-4).
+// Error against the reference: both sides place a sample within a few ulp of the coordinate magnitude (~1e-5 of a
+// cell); pixels differ by ~1e-6 relative (tests/test_gpu_parity.py::test_fast_march_*: >= 99.9 % of pixels within
+// 1e-5, flux within 1e-4; the same source on the CPU: tests/test_device_on_host.py::test_fast_march_*).
 // ---------------------------------------------------------------------------------
+#define BIRP_RINT_MAGIC 12582912.0f /* 1.5 * 2^23: x + M - M = rint(x) for |x| < 2^22 */
+
 struct FastRay {
-    float gx, gy, gz;  // index-space position of the camera: (p - o) / s
-    float ex, ey, ez;  // index-space direction: d / s
+    float gx, gy, gz;  // index-space position of the camera minus 1/2: (p - o) / s - 1/2
+    float ex, ey, ez;  // index-space direction: d / s (KSTEP: times the step length, d / s * maxdist / nsamples)
 };
 
-__device__ __forceinline__ FastRay fast_ray(const CubeView& c, const RayState& r) {
+// `step`: 1 (the march reads the distance of every step from the ray table) or, KSTEP, the exact step length
+// maxdist / nsamples of the uniform table of Camera::GenerateRayDistWidth (src/Camera.cpp:73:
+// dist[k] = max * ((k + 0.5f) / ray_samples)), so that (k + 1/2) * e is the index-space offset of step k and the
+// march needs no table read
+__device__ __forceinline__ FastRay fast_ray(const CubeView& c, const RayState& r, double step) {
     FastRay q;
-    q.gx = (float)(((double)r.px - (double)c.ox) * c.rx64);
-    q.gy = (float)(((double)r.py - (double)c.oy) * c.ry64);
-    q.gz = (float)(((double)r.pz - (double)c.oz) * c.rz64);
-    q.ex = (float)((double)r.dx * c.rx64);
-    q.ey = (float)((double)r.dy * c.ry64);
-    q.ez = (float)((double)r.dz * c.rz64);
+    q.gx = (float)(((double)r.px - (double)c.ox) * c.rx64 - 0.5);
+    q.gy = (float)(((double)r.py - (double)c.oy) * c.ry64 - 0.5);
+    q.gz = (float)(((double)r.pz - (double)c.oz) * c.rz64 - 0.5);
+    q.ex = (float)((double)r.dx * c.rx64 * step);
+    q.ey = (float)((double)r.dy * c.ry64 * step);
+    q.ez = (float)((double)r.dz * c.rz64 * step);
     return q;
 }
 
-// coefficients of one cell from its eight corners (pack_poly_kernel and the host harness), in fp64, rounded once.
-// A cell with a negative or non-finite corner gets c0 = NaN: every sample in it comes out NaN and takes the
-// literal path.
+// Coefficients of one cell from its eight corners (pack_poly_kernel and the host harness), in fp64, rounded once:
+// index bit 0 / 1 / 2 of a coefficient = it multiplies u / v / w.  A cell with a negative or non-finite corner gets
+// C0 = NaN: every sample in it comes out NaN and takes the literal path.
 __device__ __forceinline__ void poly_coefficients(float v000, float v001, float v010, float v011, float v100, float v101,
                                                   float v110, float v111, float c[8]) {
     const double a = v000, b = v001, d = v010, e = v011, f = v100, g = v101, h = v110, k = v111;
-    c[0] = v000;
-    c[1] = (float)(b - a);
-    c[2] = (float)(d - a);
-    c[3] = (float)((e - d) - (b - a));
-    c[4] = (float)(f - a);
-    c[5] = (float)((g - f) - (b - a));
-    c[6] = (float)((h - f) - (d - a));
+    c[0] = (float)((((a + b) + (d + e)) + ((f + g) + (h + k))) * 0.125);
+    c[1] = (float)((((b - a) + (e - d)) + ((g - f) + (k - h))) * 0.25);
+    c[2] = (float)((((d - a) + (e - b)) + ((h - f) + (k - g))) * 0.25);
+    c[4] = (float)((((f - a) + (g - b)) + ((h - d) + (k - e))) * 0.25);
+    c[3] = (float)((((e - d) - (b - a)) + ((k - h) - (g - f))) * 0.5);
+    c[5] = (float)((((g - f) - (b - a)) + ((k - h) - (e - d))) * 0.5);
+    c[6] = (float)((((h - f) - (d - a)) + ((k - g) - (e - b))) * 0.5);
     c[7] = (float)(((k - h) - (g - f)) - ((e - d) - (b - a)));
     const float lo = fminf(fminf(fminf(v000, v001), fminf(v010, v011)), fminf(fminf(v100, v101), fminf(v110, v111)));
-    const float sum = v000 + v001 + v010 + v011 + v100 + v101 + v110 + v111;  // inf or NaN iff a corner is
-    if (!(lo >= 0.f) || !(fabsf(sum) <= 3.402823466e+38f)) c[0] = __int_as_float(0x7fc00000);
+    const float sum = fabsf(v000) + fabsf(v001) + fabsf(v010) + fabsf(v011) + fabsf(v100) + fabsf(v101) + fabsf(v110) + fabsf(v111);
+    // (fminf drops NaNs, the sum of magnitudes keeps them: inf or NaN iff a corner is non-finite -- or the eight
+    // magnitudes overflow together, which only marks a cell that was going to overflow anyway)
+    if (!(lo >= 0.f) || !(sum <= 3.402823466e+38f)) c[0] = __int_as_float(0x7fc00000);
 }
 
-// value of the hot sample at table distance tk.  FIDX: grids of at most 2^24 voxels compute the cell index in fp32.
-template <bool FIDX>
-__device__ __forceinline__ float fast_sample(const CubeView& c, const FastRay& q, float tk) {
-    const float fx = __fmaf_rn(tk, q.ex, q.gx);
-    const float fy = __fmaf_rn(tk, q.ey, q.gy);
-    const float fz = __fmaf_rn(tk, q.ez, q.gz);
-    const float ix = floorf(fx), iy = floorf(fy), iz = floorf(fz);
-    const float tx = __fsub_rn(fx, ix), ty = __fsub_rn(fy, iy), tz = __fsub_rn(fz, iz);
-    long long cell;
-    if (FIDX) {
-        cell = (int)__fmaf_rn(__fmaf_rn(iz, c.fny, iy), c.fnx, ix);
+// cell index i = rint(f) and centred weight u = f - i of one axis.  FRND: one XU instruction and one FADD; else three
+// FADD (no XU); *bits = the bit pattern of f + M, whose low mantissa bits are i (integer cell index without F2I)
+template <bool FRND>
+__device__ __forceinline__ void fast_axis(float f, float& i, float& u, unsigned& bits) {
+    if (FRND) {
+        i = rintf(f);
+        bits = 0u;
     } else {
-        cell = (int)iz * c.slab + (int)__fmaf_rn(iy, c.fnx, ix);  // (each term below 2^31: checked at upload)
+        const float m = __fadd_rn(f, BIRP_RINT_MAGIC);
+        bits = __float_as_uint(m);
+        i = __fsub_rn(m, BIRP_RINT_MAGIC);
+    }
+    u = __fsub_rn(f, i);
+}
+
+// Value of the hot sample whose three (index - 1/2) are fx, fy, fz.
+//   VARIANT 0: rint by FADD pairs on all axes, INTEGER cell index from the bit patterns (no XU instruction at all;
+//              the only form for grids of more than 2^24 voxels)
+//   VARIANT 1: rint by FADD pairs, cell index in fp32 + one F2I            (1 XU instruction per sample)
+//   VARIANT 2: z by FRND, x and y by FADD pairs, fp32 cell index + F2I     (2)
+//   VARIANT 3: y and z by FRND                                              (3)
+//   VARIANT 4: all three by FRND                                            (4: 26 instructions, but XU-bound)
+// (the XU pipe issues a warp instruction every 8 cycles per scheduler; which mix is fastest is a measurement)
+template <int VARIANT>
+__device__ __forceinline__ float fast_sample(const CubeView& c, float fx, float fy, float fz) {
+    float ix, iy, iz, u, v, w;
+    unsigned bx, by, bz;
+    fast_axis<(VARIANT >= 4)>(fx, ix, u, bx);
+    fast_axis<(VARIANT >= 3)>(fy, iy, v, by);
+    fast_axis<(VARIANT >= 2)>(fz, iz, w, bz);
+    int cell;
+    if (VARIANT == 0) {
+        // (bits - B) is the integer index, B = bits(M); the B terms are folded into c.poly_bias by the kernel
+        cell = (int)((bz * (unsigned)c.ny + by) * (unsigned)c.nx + bx) - c.poly_bias;
+    } else {
+        cell = (int)__fmaf_rn(__fmaf_rn(iz, c.fny, iy), c.fnx, ix);
     }
     float c0, c1, c2, c3, c4, c5, c6, c7;
-    load_oct(reinterpret_cast<const char*>(c.poly) + cell * 32, c0, c1, c2, c3, c4, c5, c6, c7);
-    const float hi = __fmaf_rn(ty, __fmaf_rn(tx, c7, c6), __fmaf_rn(tx, c5, c4));
-    const float lo = __fmaf_rn(ty, __fmaf_rn(tx, c3, c2), __fmaf_rn(tx, c1, c0));
-    return __fmaf_rn(tz, hi, lo);
+    load_oct(reinterpret_cast<const char*>(c.poly) + (long long)cell * c.poly_bytes, c0, c1, c2, c3, c4, c5, c6, c7);
+    const float hi = __fmaf_rn(v, __fmaf_rn(u, c7, c6), __fmaf_rn(u, c5, c4));
+    const float lo = __fmaf_rn(v, __fmaf_rn(u, c3, c2), __fmaf_rn(u, c1, c0));
+    return __fmaf_rn(w, hi, lo);
 }
 
 // the literal sample of one step (cold path of the tolerance-mode march): returns false when the ray ends here
@@ -695,9 +730,13 @@ __device__ __forceinline__ bool fast_cold_step(const CubeView& c, RayState& r, u
 }
 
 // SIGNS: the cube has cells with negative / non-finite corners (class 0): test every hot sample for the NaN mark.
-template <bool SIGNS, bool FIDX>
+// KSTEP: the distance of step k is (k + 1/2) * maxdist / nsamples (folded into q.e by fast_ray) instead of a read of
+// the staged table -- one LDS less per sample on the L1 data path, which is what bounds this march; `kfirst` is the
+// step index of shared address `sbase` (the chunk of the table that is staged).
+template <bool SIGNS, int VARIANT, bool KSTEP>
 __device__ __forceinline__ unsigned march_steps_fast(const CubeView& c, RayState& r, const FastRay& q, unsigned sdist,
-                                                     const unsigned send, float ray_width, int* status, bool& alive) {
+                                                     const unsigned send, float ray_width, int* status, bool& alive,
+                                                     unsigned sbase = 0u, int kfirst = 0) {
     for (;;) {
         asm volatile("" : "+r"(sdist));  // (keeps the outer loop separate from the hot one, see march_steps)
         if (sdist == send) return sdist;
@@ -715,15 +754,35 @@ __device__ __forceinline__ unsigned march_steps_fast(const CubeView& c, RayState
             for (;;) {
                 asm volatile("" : "+r"(sdist));
                 bool marked = false;
-                do {
-                    const float s = fast_sample<FIDX>(c, q, table_entry(sdist));
-                    if (SIGNS && !(s >= 0.f)) {
-                        marked = true;
-                        break;
-                    }
-                    r.acc = __fadd_rn(r.acc, s);
-                    sdist += 4;
-                } while (sdist != hend);
+                if (KSTEP) {
+                    // k + 1/2 as a float (exact below 2^23 steps), advanced by 1 per step
+                    const float k0 = __fadd_rn((float)(kfirst + (int)((sdist - sbase) >> 2)), 0.5f);
+                    const float kend = __fadd_rn(k0, (float)((hend - sdist) >> 2));
+                    float kf = k0;
+                    do {
+                        const float s = fast_sample<VARIANT>(c, __fmaf_rn(kf, q.ex, q.gx), __fmaf_rn(kf, q.ey, q.gy),
+                                                             __fmaf_rn(kf, q.ez, q.gz));
+                        if (SIGNS && !(s >= 0.f)) {
+                            marked = true;
+                            break;
+                        }
+                        r.acc = __fadd_rn(r.acc, s);
+                        kf = __fadd_rn(kf, 1.0f);
+                    } while (kf != kend);
+                    sdist += 4u * (unsigned)(int)__fsub_rn(kf, k0);
+                } else {
+                    do {
+                        const float tk = table_entry(sdist);
+                        const float s = fast_sample<VARIANT>(c, __fmaf_rn(tk, q.ex, q.gx), __fmaf_rn(tk, q.ey, q.gy),
+                                                             __fmaf_rn(tk, q.ez, q.gz));
+                        if (SIGNS && !(s >= 0.f)) {
+                            marked = true;
+                            break;
+                        }
+                        r.acc = __fadd_rn(r.acc, s);
+                        sdist += 4;
+                    } while (sdist != hend);
+                }
                 if (!SIGNS || !marked) break;
                 // a cell with a negative / non-finite corner (or a rounding-level negative next to a zero corner):
                 // the literal sample decides

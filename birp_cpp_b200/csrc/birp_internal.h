@@ -19,6 +19,12 @@ struct RenderGeom {
     // width (log2, -1 = choose from the angles); only used to shape the per-warp pixel tile
     float pixel_angle_x = 0.f, pixel_angle_y = 0.f;
     int tile_w_log2 = -1;
+    int tile_swizzle = 0;  // lanes in 2x2 pixel blocks (MarchArgs::swizzle)
+    // maxdist / nsamples when the ray table is the uniform one of Camera::GenerateRayDistWidth (else 0): the
+    // tolerance-mode march may then compute the distance of a step instead of reading it; fast_kstep = 0 forbids that
+    double fast_step = 0.0;
+    int fast_kstep = 1;
+    int fast_variant = -1;  // fast_sample<VARIANT> of the tolerance-mode march; -1 = the default (experiments: BIRP_FAST_VARIANT)
     // where frame f lands in the image buffer: slot out_frame_offset + f * out_frame_stride
     long long out_frame_offset = 0, out_frame_stride = 1;
 };

@@ -32,6 +32,7 @@ namespace {
 std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kFastVariantDefault = 2;  // fast_sample<VARIANT> of the tolerance-mode march (see birp_device.cuh)
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
 struct MarchArgs {
@@ -44,6 +45,7 @@ struct MarchArgs {
     int row_begin, rows;
     int nsamples;
     int tile_w_log2;  // a warp's 32 rays form a (1 << tile_w_log2) x (32 >> tile_w_log2) pixel tile
+    int swizzle;      // lanes 4n .. 4n+3 own a 2x2 pixel block of the tile instead of four pixels of one row
     int tiles_x, tiles_per_frame;
     long long total_tiles;
     float ray_width;
@@ -52,6 +54,8 @@ struct MarchArgs {
     // frame f of this launch is written to image slot out_offset + f * out_stride of `images`
     // (1-GPU: 0 / 1; multi-GPU sweeps scatter straight into the gathering rank's buffer)
     long long out_offset, out_stride;
+    // tolerance-mode march without table reads (KSTEP): maxdist / nsamples of the uniform ray table; 0 = read the table
+    double fast_step;
 };
 
 template <int MODE>  // 0 fp32 libdevice, 1 CUDA fp64 library, 2 own fp64 blocks, 3 + region filter (cmem_sample_mode)
@@ -71,8 +75,15 @@ __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int
     const int t = (int)(tile - (long long)f * a.tiles_per_frame);
     const int ty = t / a.tiles_x;
     const int tx = t - ty * a.tiles_x;
-    i = (tx << a.tile_w_log2) + (lane & ((1 << a.tile_w_log2) - 1));
-    const int jr = ty * (32 >> a.tile_w_log2) + (lane >> a.tile_w_log2);
+    int lx = lane & ((1 << a.tile_w_log2) - 1), ly = lane >> a.tile_w_log2;
+    if (a.swizzle) {
+        // A 32-byte-per-lane load is served four lanes at a time, one L1 wavefront per 128-byte line those four lanes
+        // touch: four rays of a 2x2 pixel block stay closer together than four rays of a row.
+        lx = (lane & 1) | (((lane >> 2) & ((1 << (a.tile_w_log2 - 1)) - 1)) << 1);
+        ly = ((lane >> 1) & 1) | ((lane >> (a.tile_w_log2 + 1)) << 1);
+    }
+    i = (tx << a.tile_w_log2) + lx;
+    const int jr = ty * (32 >> a.tile_w_log2) + ly;
     j = a.row_begin + jr;
     return i < a.W && jr < a.rows;
 }
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
 #ifndef BIRP_FAST_MIN_BLOCKS
 #define BIRP_FAST_MIN_BLOCKS 8
 #endif
-template <bool SIGNS, bool FIDX>
+template <bool SIGNS, int VARIANT, bool KSTEP>
 __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cube_fast_kernel(const MarchArgs a, const CubeView c) {
     __shared__ float s_dist[kSmemDist + 1];
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
@@ -237,13 +248,15 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
     __syncthreads();
     CubeView cc = c;
     float ray_width = a.ray_width;
-    pin_uniform(cc.fnx), pin_uniform(cc.fny);
-    pin_uniform(cc.slab);
-    {
-        long long q0 = (long long)cc.poly;
-        pin_uniform(q0);
-        cc.poly = reinterpret_cast<const float*>(q0);
+    if (VARIANT == 0) {
+        pin_uniform(cc.nx), pin_uniform(cc.ny);
+        const unsigned B = __float_as_uint(BIRP_RINT_MAGIC);
+        cc.poly_bias = (int)((B * (unsigned)cc.ny + B) * (unsigned)cc.nx + B);
+        pin_uniform(cc.poly_bias);
+    } else {
+        pin_uniform(cc.fnx), pin_uniform(cc.fny);
     }
+    cc.poly_bytes = 32;
 
     int f = 0, i = 0, j = 0;
     const bool owns_pixel = lane_ray(a, f, i, j);
@@ -257,20 +270,22 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
         r.px = frp->pos[0];
         r.py = frp->pos[1];
         r.pz = frp->pos[2];
-        q = fast_ray(cc, r);
+        q = fast_ray(cc, r, KSTEP ? a.fast_step : 1.0);
         pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
     }
     bool alive = owns_pixel;
     unsigned nlive4 = 0;
     if (alive)
-        nlive4 = march_steps_fast<SIGNS, FIDX>(cc, r, q, s_base, s_base + 4u * first_chunk, ray_width, a.status, alive) - s_base;
+        nlive4 = march_steps_fast<SIGNS, VARIANT, KSTEP>(cc, r, q, s_base, s_base + 4u * first_chunk, ray_width, a.status, alive,
+                                                         s_base, 0) - s_base;
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
         __syncthreads();
         for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
-            nlive4 += march_steps_fast<SIGNS, FIDX>(cc, r, q, s_base, s_base + 4u * chunk, ray_width, a.status, alive) - s_base;
+            nlive4 += march_steps_fast<SIGNS, VARIANT, KSTEP>(cc, r, q, s_base, s_base + 4u * chunk, ray_width, a.status, alive,
+                                                              s_base, base) - s_base;
     }
     if (owns_pixel) {
         const float total = __double2float_rn(__dmul_rn((double)__fmul_rn(r.acc, ray_width), a.scale_k));
@@ -337,6 +352,7 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.rows = g.row_end - g.row_begin;
     a.nsamples = g.nsamples;
     a.tile_w_log2 = pick_tile_w_log2(g);
+    a.swizzle = (g.tile_swizzle && a.tile_w_log2 >= 1 && a.tile_w_log2 <= 4) ? 1 : 0;
     const int tw = 1 << a.tile_w_log2, th = 32 >> a.tile_w_log2;
     a.tiles_x = (g.W + tw - 1) / tw;
     a.tiles_per_frame = a.tiles_x * ((a.rows + th - 1) / th);
@@ -344,6 +360,7 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.ray_width = g.ray_width;
     a.accumulate = (flags & BIRP_ACCUMULATE) ? 1 : 0;
     a.scale_k = BIRP_SCALE_K;
+    a.fast_step = 0.0;
     a.out_offset = g.out_frame_offset;
     a.out_stride = g.out_frame_stride;
     const long long nb = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -780,14 +797,32 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     // BIRP_FAST_MARCH (trilinear, monotone ray table, poly copy present): the tolerance-mode march
     if (tri && (flags & BIRP_FAST_MARCH) && cube.poly != nullptr && g.monotone_table) {
         const bool signs = cube.positive == 0;
-        const bool fidx = (long long)cube.nx * cube.ny * cube.nz <= (1LL << 24);
+        // grids of more than 2^24 voxels need the integer cell index (variant 0); else g.fast_variant (BIRP_FAST_VARIANT
+        // in the environment, experiments) or the measured default
+        int variant = ((long long)cube.nx * cube.ny * cube.nz <= (1LL << 24)) ? g.fast_variant : 0;
+        if (variant < 0 || variant > 4) variant = kFastVariantDefault;
+        // the uniform table of Camera::GenerateRayDistWidth lets the march compute its distances (KSTEP); any other
+        // table (none exists behind this API today) is read step by step
+        const bool kstep = g.fast_step > 0.0 && g.fast_kstep != 0;
+        a.fast_step = kstep ? g.fast_step : 0.0;
+#define BIRP_FAST_LAUNCH(S, V)                                                                       \
+    if (kstep) march_cube_fast_kernel<S, V, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);   \
+    else march_cube_fast_kernel<S, V, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube)
+#define BIRP_FAST_VARIANTS(S)                       \
+    switch (variant) {                              \
+        case 0: BIRP_FAST_LAUNCH(S, 0); break;      \
+        case 1: BIRP_FAST_LAUNCH(S, 1); break;      \
+        case 2: BIRP_FAST_LAUNCH(S, 2); break;      \
+        case 3: BIRP_FAST_LAUNCH(S, 3); break;      \
+        default: BIRP_FAST_LAUNCH(S, 4); break;     \
+    }
         if (signs) {
-            if (fidx) march_cube_fast_kernel<true, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
-            else march_cube_fast_kernel<true, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            BIRP_FAST_VARIANTS(true)
         } else {
-            if (fidx) march_cube_fast_kernel<false, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
-            else march_cube_fast_kernel<false, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            BIRP_FAST_VARIANTS(false)
         }
+#undef BIRP_FAST_VARIANTS
+#undef BIRP_FAST_LAUNCH
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return cudaGetLastError();
     }

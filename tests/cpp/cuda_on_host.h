@@ -26,6 +26,11 @@ static inline float __int_as_float(int i) {  // (math_constants.h spells CUDART_
     std::memcpy(&f, &i, 4);
     return f;
 }
+static inline unsigned __float_as_uint(float f) {
+    unsigned u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -30,7 +30,7 @@ struct HostTex {
 
 struct HostCube {
     birp::CubeView view;
-    std::vector<float> grid, quad, oct;
+    std::vector<float> grid, quad, oct, poly;
     HostTex tex;
 };
 
@@ -172,6 +172,57 @@ bool render_div(RenderJob& job, int div, int lerp, int fetch, int span) {
     return false;
 }
 
+// march_cube_fast_kernel over whole frames (BIRP_FAST_MARCH): per-ray prologue and epilogue restated, the march is
+// the device source (march_steps_fast).  variant: fast_sample<VARIANT>; signs < 0: as the kernel chooses (class 0).
+template <bool SIGNS, int VARIANT, bool KSTEP>
+void fast_variant(RenderJob& job) {
+    const CubeView c = job.cube->view;
+    std::vector<float> dist(job.nsamples);
+    float ray_width = 0.f;
+    birp::host_ray_table(job.nsamples, job.maxdist, dist.data(), &ray_width);
+    std::vector<std::vector<float>> staged;
+    std::vector<int> chunk_len;
+    std::vector<float> cur(birp::kSmemDist + 1, 0.f);
+    for (int base = 0; base < job.nsamples; base += birp::kSmemDist) {
+        const int n = std::min(birp::kSmemDist, job.nsamples - base);
+        std::copy(dist.begin() + base, dist.begin() + base + n, cur.begin());
+        staged.push_back(cur);
+        chunk_len.push_back(n);
+    }
+    const int nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<unsigned long long> valid(nthreads, 0);
+    std::vector<int> status(nthreads, 0);
+    std::vector<std::thread> pool;
+    const long rows_total = (long)job.nframes * job.H;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            for (long row = t; row < rows_total; row += nthreads) {
+                const int f = (int)(row / job.H), j = (int)(row % job.H);
+                for (int i = 0; i < job.W; ++i) {
+                    RayState r;
+                    birp::pixel_direction(job.frames[f], i, j, (float)job.W, (float)job.H, r.dx, r.dy, r.dz);
+                    r.px = job.frames[f].pos[0], r.py = job.frames[f].pos[1], r.pz = job.frames[f].pos[2];
+                    r.acc = 0.f;
+                    const birp::FastRay q = birp::fast_ray(c, r, KSTEP ? (double)job.maxdist / (double)job.nsamples : 1.0);
+                    bool alive = true;
+                    unsigned nlive4 = 0;
+                    for (size_t k = 0; k < staged.size() && alive; ++k) {
+                        t_table = staged[k].data();
+                        nlive4 += birp::march_steps_fast<SIGNS, VARIANT, KSTEP>(c, r, q, 0u, 4u * (unsigned)chunk_len[k],
+                                                                                ray_width, &status[t], alive, 0u,
+                                                                                (int)k * birp::kSmemDist);
+                    }
+                    float* pix = job.images + ((size_t)f * job.H + j) * job.W + i;
+                    const float total = (float)((double)(r.acc * ray_width) * BIRP_SCALE_K);
+                    *pix = job.accumulate ? *pix + total : total;
+                    valid[t] += nlive4 >> 2;
+                }
+            }
+        });
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < nthreads; ++t) job.valid += valid[t], job.status |= status[t];
+}
+
 }  // namespace
 
 extern "C" {
@@ -193,6 +244,7 @@ void* doh_cube_create(const float* zyx, int nx, int ny, int nz, const float orig
     v.fnx = (float)nx, v.fny = (float)ny, v.fnz = (float)nz;
     v.ox = origin[0], v.oy = origin[1], v.oz = origin[2];
     v.sx = spacing[0], v.sy = spacing[1], v.sz = spacing[2];
+    v.rx64 = 1.0 / (double)spacing[0], v.ry64 = 1.0 / (double)spacing[1], v.rz64 = 1.0 / (double)spacing[2];
     const volatile float rx = 1.0f / spacing[0], ry = 1.0f / spacing[1], rz = 1.0f / spacing[2];
     v.rx = rx, v.ry = ry, v.rz = rz;
     v.lx = birp::host_bounds_limit(spacing[0], nx);
@@ -228,6 +280,19 @@ void* doh_cube_create(const float* zyx, int nx, int ny, int nz, const float orig
             std::memcpy(&h->oct[8 * t], lo, sizeof(lo));
             std::memcpy(&h->oct[8 * t + 4], hi, sizeof(hi));
         }
+        h->poly.resize(8 * n);  // pack_poly_kernel
+        for (size_t t = 0; t < n; ++t) {
+            const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / slab);
+            const int dx = (x + 1 < nx) ? 1 : 0;
+            const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
+            const size_t u = t + ((z + 1 < nz) ? slab : 0);
+            birp::poly_coefficients(zyx[t], zyx[t + dx], zyx[t + dy], zyx[t + dy + dx], zyx[u], zyx[u + dx], zyx[u + dy],
+                                    zyx[u + dy + dx], &h->poly[8 * t]);
+        }
+        v.poly = h->poly.data();
+        v.poly_bytes = 32;
+        const unsigned B = __float_as_uint(BIRP_RINT_MAGIC);
+        v.poly_bias = (int)((B * (unsigned)ny + B) * (unsigned)nx + B);  // (march_cube_fast_kernel sets these two itself)
         v.quad = reinterpret_cast<const float4*>(h->quad.data());
         v.quad_up = v.quad + slab;  // (march_cube_kernel sets these three itself)
         v.quad_bytes = 16;
@@ -326,6 +391,26 @@ int doh_render_cube(const void* cube, int trilinear, int lerp, int divmode, int 
     if (!trilinear && lerp == 2) lerp = 0;  // launch_cube_div: nearest has the classes 1 and 0 only
     const bool ok = trilinear ? render_div<true>(job, divmode, lerp, fetch, span) : render_div<false>(job, divmode, lerp, 0, span);
     if (!ok) return -1;
+    if (valid) *valid = job.valid;
+    return job.status;
+}
+
+int doh_render_cube_fast(const void* cube, int variant, int signs, int kstep, const birp_frame* frames, int nframes, int W,
+                                    int H, int nsamples, int maxdist, int accumulate, float* images,
+                                    unsigned long long* valid) {
+    const HostCube* h = static_cast<const HostCube*>(cube);
+    RenderJob job{h, frames, nframes, W, H, nsamples, maxdist, accumulate, images};
+    if (signs < 0) signs = h->view.positive == 0;
+#define DOH_FAST(V)                              \
+    case V:                                      \
+        if (signs) kstep ? fast_variant<true, V, true>(job) : fast_variant<true, V, false>(job);    \
+        else kstep ? fast_variant<false, V, true>(job) : fast_variant<false, V, false>(job);         \
+        break;
+    switch (variant) {
+        DOH_FAST(0) DOH_FAST(1) DOH_FAST(2) DOH_FAST(3) DOH_FAST(4)
+        default: return -1;
+    }
+#undef DOH_FAST
     if (valid) *valid = job.valid;
     return job.status;
 }

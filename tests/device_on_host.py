@@ -30,6 +30,8 @@ def lib():
         L.doh_sample_cube.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_long, _vp, _vp, _vp]
         L.doh_render_cube.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_int, _vp, _vp]
+        L.doh_render_cube_fast.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           _vp, _vp]
         L.doh_scale.argtypes = [_vp, C.c_long, C.c_float, C.c_int, _vp, _vp, _vp, _vp]
         L.doh_lerps.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
         L.doh_scale_exhaustive.argtypes = [C.c_int, C.c_uint, C.c_int, _vp]
@@ -107,6 +109,19 @@ class HostCube:
         if st < 0:
             raise ValueError("unknown kernel variant")
         return img, int(valid.value), st
+
+
+def render_fast(cube: HostCube, frames, W, H, variant=2, signs=-1, kstep=False, nsamples=200, maxdist=44,
+                accumulate_into=None):
+    """march_cube_fast_kernel (BIRP_FAST_MARCH, tolerance mode) on the host; signs < 0: as the kernel chooses"""
+    fr = np.ascontiguousarray(frames).view(np.float32).reshape(-1, 16)
+    img = np.zeros((len(fr), H, W), np.float32) if accumulate_into is None else _f32(accumulate_into).copy()
+    valid = C.c_ulonglong(0)
+    st = lib().doh_render_cube_fast(cube._h, int(variant), int(signs), int(kstep), _p(fr), len(fr), W, H, nsamples, maxdist,
+                                    int(accumulate_into is not None), _p(img), C.byref(valid))
+    if st < 0:
+        raise ValueError("unknown variant")
+    return img, int(valid.value), st
 
 
 def scale(s, ray_width, maybe_zero=False):

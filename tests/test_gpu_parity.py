@@ -266,23 +266,33 @@ def test_cube_beyond_texture_limits_uses_global_loads(gpu):
         c.free()
 
 
-def test_whole_orbit_sweep_bit_exact(gpu):
-    """the headline workload itself, all of it: 10 000 SXI frames (69 M pixels, 1.4e10 samples) through a
-    256^3 cube, every pixel compared bit for bit with the CPU restatement (all host cores, ~20-60 s)"""
+@pytest.fixture(scope="module")
+def orbit_sweep(gpu):
+    """the headline workload and its CPU restatement (all host cores, ~20-60 s), shared by the exact and the
+    tolerance-mode test"""
     import os
     zyx, org, sp = S.make_cube(256, 256, 256)
     poses = S.orbit_poses(10000)
     fp = capi.frames_for_poses(poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
-    c = capi.Cube(zyx, org, sp)
-    try:
-        got = c.render(fp, W, H, trilinear=True)
-    finally:
-        c.free()
     fo = fp.view(np.float32).reshape(-1, 16)
     want, valid = O.orc_render_cube(zyx, org, sp, True, fo, W, H, nthreads=len(os.sched_getaffinity(0)),
                                     return_valid=True)
+    return zyx, org, sp, fp, want, valid
+
+
+def test_whole_orbit_sweep_bit_exact(orbit_sweep):
+    """the headline workload itself, all of it: 10 000 SXI frames (69 M pixels, 1.4e10 samples) through a
+    256^3 cube, every pixel compared bit for bit with the CPU restatement; default march (lean) and the general one"""
+    zyx, org, sp, fp, want, valid = orbit_sweep
+    c = capi.Cube(zyx, org, sp)
+    try:
+        got = c.render(fp, W, H, trilinear=True)
+        general = c.render(fp[::10], W, H, trilinear=True, extra_flags=capi.NO_LEAN_MARCH)
+    finally:
+        c.free()
     assert valid > 1.3e10
     assert_bit_exact(got, want, "orbit sweep")
+    assert_bit_exact(general, want[::10], "orbit sweep, general march, every 10th frame")
     assert (want.reshape(10000, -1).max(axis=1) > 0).mean() > 0.99  # the orbit stays inside the cube
 
 
@@ -431,6 +441,166 @@ def test_sweep_call_equals_frames_call(gpu, dev_cube1):
     got = capi.render_sweep(P, poses[:300], AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, rows=(5, 40))
     assert_bit_exact(got, capi.render_cmem(P, fp[:300], W, H, rows=(5, 40)), "cmem sweep, row band, no frames_out")
     assert capi.render_sweep(dev_cube1, np.zeros((0, 3), np.float32), AIM, 27.0, 16.0, W, H).shape == (0, H, W)
+
+
+
+# ------------------------------------------------------------------ tolerance-mode march (BIRP_FAST_MARCH)
+FAST = capi.FAST_MARCH
+FAST_MIN_FRACTION = 0.999  # of the pixels within 1e-5 (SURVEY 8(d) asks for 95 %); flux within 1e-4
+
+
+def assert_fast_parity(got, want, what):
+    """SURVEY 8(d) tolerance at 99.9 %, and the rays end where the reference ends them: a pixel that is exactly zero
+    in the reference (no live sample) is exactly zero here and vice versa"""
+    frac = assert_image_parity(got, want, what, min_fraction=FAST_MIN_FRACTION)
+    assert np.array_equal(np.asarray(got) == 0, np.asarray(want) == 0), f"{what}: zero pixels differ"
+    return frac
+
+
+@pytest.fixture
+def tuning(gpu):
+    """birp_set_tuning with the defaults restored afterwards"""
+    yield capi.set_tuning
+    for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1)):
+        capi.set_tuning(k, v)
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("kstep", [1, 0])
+@pytest.mark.parametrize("neg", [False, True])
+def test_fast_march_config1_every_variant(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tuning, variant, kstep, neg):
+    """tolerance mode on the reference test cube's shape, every rounding variant of the cell index, with computed
+    and with table-read step distances; the cube with a negative slab has marked cells (rays end at the reference's
+    step)"""
+    zyx, org, sp = cube1_neg if neg else cube1
+    dev = dev_cube1_neg if neg else dev_cube1
+    tuning("fast_variant", variant)
+    tuning("fast_kstep", kstep)
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    got = dev.render(fp, W, H, trilinear=True, extra_flags=FAST)
+    want = O.orc_render_cube(zyx, org, sp, True, fo, W, H)
+    assert_fast_parity(got, want, f"variant {variant} kstep {kstep} neg {neg}")
+    assert not np.array_equal(got, want), "the tolerance-mode kernel did not run (images are bit-identical)"
+
+
+def test_fast_march_flag_leaves_nearest_neighbour_exact(dev_cube1, cube1):
+    """nearest-neighbour sampling has no tolerance mode (a sample next to a cell boundary would pick another voxel):
+    the flag is ignored, the render stays bit-exact"""
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    assert_bit_exact(dev_cube1.render(fp, W, H, trilinear=False, extra_flags=FAST),
+                     O.orc_render_cube(zyx, org, sp, False, fo, W, H))
+
+
+def test_fast_march_live_samples_equal_the_reference(dev_cube1_neg, cube1_neg):
+    """termination is decided by the reference's arithmetic: the number of accumulated samples is the oracle's"""
+    torch = pytest.importorskip("torch")
+    zyx, org, sp = cube1_neg
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    _, valid = O.orc_render_cube(zyx, org, sp, True, fo, W, H, return_valid=True)
+    d_frames = torch.from_numpy(fp.view(np.float32).reshape(-1, 16).copy()).cuda()
+    d_images = torch.zeros((len(fp), H, W), device="cuda")
+    d_valid = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    capi.render_cube_device(dev_cube1_neg, d_frames.data_ptr(), len(fp), W, H, d_images.data_ptr(),
+                            d_valid=d_valid.data_ptr(), stream=stream, extra_flags=FAST)
+    capi.check_device_status(stream)
+    assert int(d_valid.item()) == valid
+
+
+def test_fast_march_zero_regions_negatives_and_nonfinite(gpu):
+    """a non-negative cube with zero regions (no marked cells), then 30 % negative voxels (marked cells everywhere),
+    then NaN / inf voxels: tolerance, termination, and NaN / inf pixels exactly where the reference has them"""
+    zyx, org, sp = S.make_cube(64, 64, 64)
+    zyx = zyx.copy()
+    x = org[0] + sp[0] * np.arange(64)
+    r = np.sqrt(x[None, None, :] ** 2 + x[None, :, None] ** 2 + x[:, None, None] ** 2)
+    zyx[r < 12.0] = 0.0
+    rng = np.random.default_rng(8)
+    zyx[rng.random(zyx.shape) < 0.08] = 0.0
+    poses = np.array([S.DEFAULT_POS, (20.0, -15.0, 3.0), (0.5, 0.25, 1.0)], np.float32)
+    fp, fo = frames_pair(poses, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    neg = zyx.copy()
+    neg[rng.random(zyx.shape) < 0.3] *= -1.0
+    bad = zyx.copy()
+    bad[10, 20, 30] = np.nan
+    bad[40, 30, 20] = np.inf
+    for name, grid in (("zeros", zyx), ("negatives", neg), ("nan/inf", bad)):
+        c = capi.Cube(grid, org, sp)
+        try:
+            got = c.render(fp, W, H, trilinear=True, extra_flags=FAST)
+            want = O.orc_render_cube(grid, org, sp, True, fo, W, H)
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want)), name
+            fin = np.isfinite(want)
+            assert pixel_fraction_within(got[fin], want[fin]) >= FAST_MIN_FRACTION, name
+            assert np.array_equal(got[fin] == 0, want[fin] == 0), name
+            assert want[fin].max() > 0
+        finally:
+            c.free()
+
+
+@pytest.mark.parametrize("w,h,n,maxdist", [(37, 21, 517, 44), (1, 1, 200, 44), (8, 4, 1, 44), (9, 5, 2, 10),
+                                             (131, 3, 64, 60), (18, 14, 5000, 44)])
+def test_fast_march_ragged_shapes_and_long_marches(dev_cube1, cube1, tuning, w, h, n, maxdist):
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES[:3], 37.0, 21.0, w, h)
+    want = O.orc_render_cube(zyx, org, sp, True, fo, w, h, nsamples=n, maxdist=maxdist)
+    for kstep in (1, 0):
+        tuning("fast_kstep", kstep)
+        got = dev_cube1.render(fp, w, h, nsamples=n, maxdist=maxdist, trilinear=True, extra_flags=FAST)
+        assert_fast_parity(got, want, f"{w}x{h} n={n} kstep={kstep}")
+
+
+def test_fast_march_row_bands_accumulate_and_sweep(dev_cube1, cube1):
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    full = dev_cube1.render(fp, W, H, extra_flags=FAST)
+    tiled = np.zeros_like(full)
+    for r0, r1 in ((0, 9), (9, 10), (10, 41), (41, 64)):
+        dev_cube1.render(fp, W, H, rows=(r0, r1), out=tiled, extra_flags=FAST)
+    assert_bit_exact(tiled, full, "row bands of the tolerance-mode march tile the image exactly")
+    twice = dev_cube1.render(fp, W, H, images=full.copy(), extra_flags=FAST)
+    want = O.orc_render_cube(zyx, org, sp, True, fo, W, H, images=O.orc_render_cube(zyx, org, sp, True, fo, W, H))
+    assert_fast_parity(twice, want, "accumulate")
+    poses = S.orbit_poses(300)
+    got = capi.render_sweep(dev_cube1, poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, extra_flags=FAST)
+    fq = capi.frames_for_poses(poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    assert_bit_exact(got, dev_cube1.render(fq, W, H, extra_flags=FAST), "sweep call = frames call")
+
+
+def test_fast_march_whole_orbit_sweep(orbit_sweep, tuning):
+    """the headline workload in tolerance mode, all 69 M pixels against the CPU restatement"""
+    zyx, org, sp, fp, want, valid = orbit_sweep
+    c = capi.Cube(zyx, org, sp)
+    try:
+        for swz in (0, 1):
+            tuning("tile_swizzle", swz)
+            got = c.render(fp, W, H, trilinear=True, extra_flags=FAST)
+            frac = assert_fast_parity(got, want, f"orbit sweep, tolerance mode, swizzle {swz}")
+            rel = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-5 * np.abs(want).max())
+            print(f"tolerance mode, whole sweep: {frac:.5%} of pixels within 1e-5, max relative difference {rel.max():.3g}")
+            assert rel.max() < 1e-5
+            tuning("tile_swizzle", 0)
+        # the exact march with swizzled lanes is the exact march
+        tuning("tile_swizzle", 1)
+        assert_bit_exact(c.render(fp[::20], W, H, trilinear=True), want[::20], "exact march, swizzled lanes")
+    finally:
+        c.free()
+
+
+def test_fast_march_config3_and_config4(gpu):
+    """BASELINE configs[2] and [3] in tolerance mode: 256^3 / 1024^2 (200 and 2048 samples) and 512^3 (integer cell
+    index: more than 2^24 voxels) / 1024^2, bands against the oracle"""
+    for n, nsamples, rows in ((256, 200, (0, 1024)), (256, 2048, (500, 532)), (512, 200, (500, 564))):
+        zyx, org, sp = S.make_cube(n, n, n)
+        c = capi.Cube(zyx, org, sp)
+        try:
+            fp, fo = frames_pair(np.array([S.DEFAULT_POS], np.float32), 36.0, 36.0, 1024, 1024)
+            got = c.render(fp, 1024, 1024, nsamples=nsamples, trilinear=True, extra_flags=FAST)
+            want = O.orc_render_cube(zyx, org, sp, True, fo, 1024, 1024, nsamples=nsamples, rows=rows, nthreads=16)
+            assert_fast_parity(got[:, rows[0]:rows[1]], want[:, rows[0]:rows[1]], f"{n}^3, {nsamples} samples")
+        finally:
+            c.free()
 
 
 # ------------------------------------------------------------------ device-side sweep setup (SURVEY 8(f)4)

@@ -1,7 +1,10 @@
 """A/B timing of march-kernel variants WITHOUT torch (seconds instead of tens of seconds of start-up): the orbit
 workload through birp_render_cube_device on the default stream, CUDA events from libcudart via ctypes.
 
-  python tools/ab_quick.py [--flags 0,16384] [--frames 10000] [--steps 4] [--dry]
+  python tools/ab_quick.py [--flags 0,65536,32768:fast_variant=0:fast_kstep=0] [--frames 10000] [--steps 4] [--dry]
+
+A combination is BIRP_* flags, optionally followed by :knob=value settings for birp_set_tuning (reset to the defaults
+before every combination).
 
 Prints one JSON line: per flag combination the best and mean kernel time, frames/s, and whether its images are
 bit-identical to those of the first combination.  No L2 flush between launches (the oct copy of the 256^3 cube is
@@ -58,7 +61,11 @@ def main():
     zyx, org, sp = S.make_cube(n, n, n)
     poses = S.orbit_poses(args.frames)
     frames = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
-    flags = [int(x) for x in args.flags.split(",")]
+    combos = []
+    for spec in args.flags.split(","):
+        parts = spec.split(":")
+        combos.append((spec, int(parts[0]), [(kv.split("=")[0], int(kv.split("=")[1])) for kv in parts[1:]]))
+    flags = [c[0] for c in combos]
     out = {"workload": "orbit", "frames": len(poses), "cube": n, "cudart": rt_path,
            "host_setup_s": round(time.perf_counter() - t0, 2)}
     if args.dry:
@@ -81,7 +88,14 @@ def main():
     ck(rt.cudaEventCreate(C.byref(e1)), "event")
     ref = None
     img = np.empty((len(poses), H, W), np.float32)
-    for fl in flags:
+    def tune(knobs):
+        for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1)):
+            capi.set_tuning(k, v)
+        for k, v in knobs:
+            capi.set_tuning(k, v)
+
+    for spec, fl, knobs in combos:
+        tune(knobs)
         ms = []
         for it in range(args.steps + 1):
             ck(rt.cudaEventRecord(e0, None), "record")
@@ -98,14 +112,16 @@ def main():
         same = True if ref is None else bool(np.array_equal(img.view(np.uint32), ref.view(np.uint32)))
         if ref is None:
             ref = img.copy()
-        out[f"flags_{fl}"] = {"ms_min": round(min(ms), 4), "ms_mean": round(float(np.mean(ms)), 4),
-                              "frames_per_s": round(len(poses) / (min(ms) * 1e-3), 1), "same_as_first": same,
-                              "nonzero_pixels": int(np.count_nonzero(img))}
+        rel = float((np.abs(img.astype(np.float64) - ref) / np.maximum(np.abs(ref), 1e-5 * np.abs(ref).max())).max())
+        out[f"flags_{spec}"] = {"ms_min": round(min(ms), 4), "ms_mean": round(float(np.mean(ms)), 4),
+                                "frames_per_s": round(len(poses) / (min(ms) * 1e-3), 1), "same_as_first": same,
+                                "max_rel_diff_vs_first": rel, "nonzero_pixels": int(np.count_nonzero(img))}
     if args.e2e:
         # end to end through birp_render_cube_sweep: host poses in, pinned host images out (wall clock, the call
         # synchronises before it returns)
         pinned = capi.PinnedArray((len(poses), H, W))
-        for fl in flags:
+        for spec, fl, knobs in combos:
+            tune(knobs)
             secs = []
             for it in range(args.steps + 1):
                 t1 = time.perf_counter()
@@ -113,9 +129,9 @@ def main():
                                   extra_flags=fl, out=pinned.array)
                 if it >= 1:
                     secs.append(time.perf_counter() - t1)
-            out[f"e2e_flags_{fl}"] = {"ms_min": round(min(secs) * 1e3, 4), "frames_per_s": round(len(poses) / min(secs), 1),
-                                      "same_as_device_render": bool(np.array_equal(pinned.array.view(np.uint32),
-                                                                                   ref.view(np.uint32)))}
+            out[f"e2e_flags_{spec}"] = {"ms_min": round(min(secs) * 1e3, 4), "frames_per_s": round(len(poses) / min(secs), 1),
+                                      "same_as_first_device_render": bool(np.array_equal(pinned.array.view(np.uint32),
+                                                                                         ref.view(np.uint32)))}
         pinned.free()
     out["total_s"] = round(time.perf_counter() - t0, 2)
     print(json.dumps(out))
