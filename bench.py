@@ -121,6 +121,19 @@ def issue_roofline(entry, live_samples, kernel_ms, sm_mhz):
     winst = entry["warp_instructions"] * scale
     out["achieved"] = winst / (kernel_ms / 1e3) / 1e9
     out["frac"] = out["achieved"] / peak
+    if entry.get("l1_wavefronts"):
+        # the other candidate: the L1 data pipe moves one wavefront per clock per SM (a 32-byte-per-lane load costs 8 or
+        # more).  Whichever unit is busier is the bound that is reported; the other rides along.
+        l1_peak = 148 * sm_mhz * 1e6 / 1e9
+        l1_ach = entry["l1_wavefronts"] * scale / (kernel_ms / 1e3) / 1e9
+        l1 = {"bound": "l1", "achieved": l1_ach, "peak": l1_peak, "unit": "Gwavefront/s", "frac": l1_ach / l1_peak,
+              "wavefronts_per_global_load": entry.get("l1_wavefronts_per_global_load"),
+              "peak_source": f"148 SMs x one L1 data-pipe wavefront per clock x {sm_mhz:.0f} MHz"}
+        issue = {k: out[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")}
+        if l1["frac"] > out["frac"]:
+            out.update({k: l1[k] for k in ("bound", "achieved", "peak", "unit", "frac", "peak_source")})
+            out["issue"] = issue
+        out["l1"] = l1
     out["traffic"] = int(entry["bytes"] * scale) if entry.get("bytes") is not None else None
     out["warp_instructions_per_launch"] = int(winst)
     out["warp_instructions_per_warp_sample"] = entry["warp_instructions"] / (entry["live_samples"] / 32.0)

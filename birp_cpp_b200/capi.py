@@ -57,6 +57,7 @@ SIGNATURES = {
     "birp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "birp_host_free": (C.c_int, [_vp]),
     "birp_frame_setup": (C.c_int, [_f32p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
+    "birp_frame_setup_aim": (C.c_int, [_f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
     "birp_frame_setup_batch": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp,
                                          C.c_int]),
     "birp_frame_setup_device": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, _vp]),
@@ -135,6 +136,15 @@ def frame_setup(pos, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H
     out = np.zeros(1, dtype=FRAME_DTYPE)
     p = _f32(pos, (3,))
     _check(lib().birp_frame_setup(p.ctypes.data_as(_f32p), aim_x, fov_x_deg, fov_y_deg, W, H, _ptr(out)))
+    return out
+
+
+def frame_setup_aim(pos, aim, fov_x_deg: float, fov_y_deg: float, W: int, H: int) -> np.ndarray:
+    """One birp_frame record for a camera aimed at the point `aim` (all three components, Camera::SetAim)."""
+    out = np.zeros(1, dtype=FRAME_DTYPE)
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    _check(lib().birp_frame_setup_aim(p.ctypes.data_as(_f32p), a.ctypes.data_as(_f32p), fov_x_deg, fov_y_deg, W, H,
+                                      _ptr(out)))
     return out
 
 

@@ -72,7 +72,7 @@ struct DeviceCtx {
     birp_frame* d_frames = nullptr;
     size_t frames_cap = 0;
     float* d_images[2] = {nullptr, nullptr};
-    size_t images_cap = 0;  // floats per buffer
+    size_t images_cap[2] = {0, 0};  // floats, per buffer (a failed grow of one leaves the other consistent)
     float* d_scratch = nullptr;
     size_t scratch_cap = 0;  // floats
     int* d_status = nullptr;
@@ -85,6 +85,7 @@ struct DeviceCtx {
     int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
     int tile_swizzle = 0;     // BIRP_TILE_SWIZZLE override (experiments)
     int fast_variant = -1;    // BIRP_FAST_VARIANT override (experiments)
+    int fast_coop = 0;        // experiment: warp-per-ray tolerance-mode march
     int fast_kstep = 1;       // BIRP_FAST_KSTEP=0: the tolerance-mode march reads the ray table (experiments)
     std::mutex mu;
 };
@@ -261,15 +262,20 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     if (chunk > (size_t)nframes) chunk = nframes;
     rc = ensure(&c->d_frames, &c->frames_cap, (size_t)nframes);
     if (rc) return rc;
-    {
-        size_t cap = c->images_cap;
-        rc = ensure(&c->d_images[0], &cap, chunk * frame_px);
+    for (int b = 0; b < 2; ++b) {
+        rc = ensure(&c->d_images[b], &c->images_cap[b], chunk * frame_px);
         if (rc) return rc;
-        cap = c->images_cap;
-        rc = ensure(&c->d_images[1], &cap, chunk * frame_px);
-        if (rc) return rc;
-        c->images_cap = cap;
     }
+    // From here on work is enqueued on two streams that read and write the caller's buffers: whatever way this
+    // function is left -- a singular pose in a later chunk, a CUDA error -- nothing may still be in flight when it
+    // returns ("synchronous on return"), and a pending device status must not leak into the next call.
+    struct DrainOnExit {
+        DeviceCtx* c;
+        ~DrainOnExit() {
+            cudaStreamSynchronize(c->compute);
+            cudaStreamSynchronize(c->copy);
+        }
+    } drain{c};
     if (!sweep)
         BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
                                   c->compute));
@@ -283,8 +289,12 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             // frame records of this chunk: host threads now (the GPU is busy with the previous chunk), then H2D
             int src = birp::host_frame_setup_batch(sweep->poses + 3 * f0, nf, sweep->aim_x, sweep->fov_x_deg,
                                                    sweep->fov_y_deg, W, H, sweep->frames_out + f0, 0);
-            if (src == BIRP_ERR_SINGULAR) return set_error(src, "Determinant is 0");
-            if (src) return src;
+            if (src) {
+                cudaStreamSynchronize(c->compute);
+                read_status(c, c->compute);  // (clears a status word set by the chunks already rendered)
+                if (src == BIRP_ERR_SINGULAR) return set_error(src, "Determinant is 0");
+                return src;
+            }
             BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, sweep->frames_out + f0, sizeof(birp_frame) * nf,
                                       cudaMemcpyHostToDevice, c->compute));
         }
@@ -306,13 +316,17 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
     g.fast_kstep = c->fast_kstep;
+    g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
         g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
         g.tile_swizzle = c->tile_swizzle;
     g.fast_kstep = c->fast_kstep;
+    g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
         g.fast_kstep = c->fast_kstep;
+    g.fast_coop = c->fast_coop;
+        g.fast_coop = c->fast_coop;
         g.fast_step = table.step;
         cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
         if (e != cudaSuccess)
@@ -368,6 +382,14 @@ int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov
                      birp_frame* out) {
     if (!pos || !out || W <= 0 || H <= 0) return set_error(BIRP_ERR_ARG, "bad frame_setup arguments");
     int rc = birp::host_frame_setup(pos, aim_x, fov_x_deg, fov_y_deg, W, H, out);
+    if (rc == BIRP_ERR_SINGULAR) return set_error(rc, "Determinant is 0");
+    return rc;
+}
+
+int birp_frame_setup_aim(const float pos[3], const float aim[3], float fov_x_deg, float fov_y_deg, int W, int H,
+                         birp_frame* out) {
+    if (!pos || !aim || !out || W <= 0 || H <= 0) return set_error(BIRP_ERR_ARG, "bad frame_setup arguments");
+    int rc = birp::host_frame_setup_aim(pos, aim, fov_x_deg, fov_y_deg, W, H, out);
     if (rc == BIRP_ERR_SINGULAR) return set_error(rc, "Determinant is 0");
     return rc;
 }
@@ -961,6 +983,7 @@ int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_f
     g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
     g.fast_kstep = c->fast_kstep;
+    g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
@@ -1000,6 +1023,7 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
     g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
     g.fast_kstep = c->fast_kstep;
+    g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
@@ -1101,6 +1125,7 @@ int birp_set_tuning(const char* name, int value) {
     else if (n == "tile_swizzle") c->tile_swizzle = value;
     else if (n == "fast_variant") c->fast_variant = value;
     else if (n == "fast_kstep") c->fast_kstep = value;
+    else if (n == "fast_coop") c->fast_coop = value;
     else return set_error(BIRP_ERR_ARG, "unknown tuning knob '%s'", name);
     return BIRP_OK;
 }

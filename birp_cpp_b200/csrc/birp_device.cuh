@@ -64,11 +64,19 @@ struct CubeView {
     double rx64, ry64, rz64;
 };
 
-// one 32-byte load through the read-only path (sm_100: LDG.E.256)
+// one 32-byte load through the read-only path (sm_100: LDG.E.NA.256.CONSTANT).
+// L1::no_allocate: the records of a cell are read by a handful of neighbouring rays at about the same time and then
+// never again, so the L1 hit rate is low (41 % on the orbit sweep) and every miss that ALLOCATES pays for its fill
+// in L1 data-pipe wavefronts -- the unit that bounds the tolerance-mode march.  Without allocation the data goes
+// from L2 to the registers: measured on the orbit sweep (profiles/r2c_ab_load_*.json) tolerance mode 23.6 -> 18.1 ms,
+// bit-exact march 28.4 -> 27.6 ms; plain ld.global, evict_first and evict_last are all within 0.2 % of the default.
 __device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, float& a2, float& a3, float& b0, float& b1,
                                          float& b2, float& b3) {
 #ifdef __CUDACC__
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#ifndef BIRP_OCT_LOAD
+#define BIRP_OCT_LOAD "ld.global.nc.L1::no_allocate.v8.f32"  // (A/B builds override it)
+#endif
+    asm(BIRP_OCT_LOAD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3), "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
         : "l"(p));
 #else

@@ -195,11 +195,12 @@ BIRP_HD Mat3 rot_x(float a) {
 // tan_half_x / tan_half_y / aspect do not depend on the pose: the caller supplies them
 // (host: tanf of the reference, src/Camera.cpp:150-151).  Returns BIRP_OK or BIRP_ERR_SINGULAR.
 template <class M>
-BIRP_HD int frame_setup_T(const float pos[3], float aim_x, float tan_half_x, float tan_half_y, float aspect,
+BIRP_HD int frame_setup_T(const float pos[3], const float aim3[3], float tan_half_x, float tan_half_y, float aspect,
                           birp_frame* out) {
     const float to_rad = BIRP_PI / 180.f;
     const Vec3 cam = {pos[0], pos[1], pos[2]};
-    const Vec3 aim = {aim_x, 0.f, 0.f};
+    // Orient() reads all three aim components (src/Camera.cpp:323-327); theta and phi below only aim.x (:99-104)
+    const Vec3 aim = {aim3[0], aim3[1], aim3[2]};
     const float angle_sun = sun_roll_angle<M>(cam, aim);
     const float angle_sun_corrected = 180.f - angle_sun;
 

@@ -8,6 +8,9 @@ void host_fov_terms(float fov_x_deg, float fov_y_deg, int W, int H, float* tan_h
                     float* aspect);
 int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out);
+// the same with the whole aim vector (Camera::SetAim(x, y, z): Orient() reads all three components)
+int host_frame_setup_aim(const float pos[3], const float aim[3], float fov_x_deg, float fov_y_deg, int W, int H,
+                         birp_frame* out);
 int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                            birp_frame* out, int nthreads);
 void host_ray_table(int nsamples, int maxdist, float* dist_out, float* ray_width_out);

@@ -48,11 +48,17 @@ void host_fov_terms(float fov_x_deg, float fov_y_deg, int W, int H, float* tan_h
     *aspect = (float)W / (float)H;                     // src/Camera.cpp:137
 }
 
-int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
-                     birp_frame* out) {
+int host_frame_setup_aim(const float pos[3], const float aim[3], float fov_x_deg, float fov_y_deg, int W, int H,
+                         birp_frame* out) {
     float tx, ty, aspect;
     host_fov_terms(fov_x_deg, fov_y_deg, W, H, &tx, &ty, &aspect);
-    return fm::frame_setup_T<HostMath>(pos, aim_x, tx, ty, aspect, out);
+    return fm::frame_setup_T<HostMath>(pos, aim, tx, ty, aspect, out);
+}
+
+int host_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
+                     birp_frame* out) {
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    return host_frame_setup_aim(pos, aim, fov_x_deg, fov_y_deg, W, H, out);
 }
 
 // frame_setup for a whole sweep: poses are independent, so they are split over host threads

@@ -24,6 +24,7 @@ struct RenderGeom {
     // tolerance-mode march may then compute the distance of a step instead of reading it; fast_kstep = 0 forbids that
     double fast_step = 0.0;
     int fast_kstep = 1;
+    int fast_coop = 0;  // experiment: the warp-per-ray form of the tolerance-mode march (march_cube_fast_coop_kernel)
     int fast_variant = -1;  // fast_sample<VARIANT> of the tolerance-mode march; -1 = the default (experiments: BIRP_FAST_VARIANT)
     // where frame f lands in the image buffer: slot out_frame_offset + f * out_frame_stride
     long long out_frame_offset = 0, out_frame_stride = 1;

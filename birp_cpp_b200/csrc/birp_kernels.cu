@@ -294,6 +294,82 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
     }
 }
 
+
+// EXPERIMENT (north_star: "warp-shuffle reductions of partial segment sums"): the tolerance-mode march with the 32
+// lanes of a warp cooperating on ONE ray at a time -- lane l takes steps l, l + 32, ... of the ray's first hot run,
+// the partial sums are reduced with shuffles -- instead of one lane per ray.  Only the accumulation order changes
+// (allowed in tolerance mode).  Measured on the orbit sweep (profiles/r2c_*): the 32 samples of a request are spread
+// over ~22 voxels along the ray instead of 2-3 across a pixel tile, i.e. many more 128-byte lines per load on an
+// L1-wavefront-bound kernel.  Selected by birp_set_tuning("fast_coop", 1); positive / non-negative cubes of at most
+// 2^24 voxels, uniform ray table.
+template <int VARIANT>
+__global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cube_fast_coop_kernel(const MarchArgs a, const CubeView c) {
+    __shared__ float s_dist[kSmemDist + 1];
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
+    const int first_chunk = min(kSmemDist, a.nsamples);
+    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
+    __syncthreads();
+    CubeView cc = c;
+    float ray_width = a.ray_width;
+    pin_uniform(cc.fnx), pin_uniform(cc.fny);
+    cc.poly_bytes = 32;
+    int f = 0, i = 0, j = 0;
+    const bool owns_pixel = lane_ray(a, f, i, j);  // (a whole warp shares `tile < total_tiles`: no early exit needed)
+    RayState r = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    FastRay q = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float* pix = nullptr;
+    unsigned sdist = s_base;
+    const unsigned send = s_base + 4u * first_chunk;
+    int nrun = 0;
+    if (owns_pixel) {
+        const birp_frame* __restrict__ frp = a.frames + f;
+        pixel_direction(*frp, i, j, (float)a.W, (float)a.H, r.dx, r.dy, r.dz);
+        r.px = frp->pos[0], r.py = frp->pos[1], r.pz = frp->pos[2];
+        q = fast_ray(cc, r, a.fast_step);
+        pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
+        float xi, yi, zi;
+        if (step_ingress(cc, r, sdist, xi, yi, zi)) {  // the run of hot steps that starts at step 0
+            unsigned lo = sdist + 4, hi = send;
+            while (lo < hi) {
+                const unsigned mid = lo + (((hi - lo) >> 3) << 2);
+                float ux, uy, uz;
+                if (step_ingress(cc, r, mid, ux, uy, uz)) lo = mid + 4;
+                else hi = mid;
+            }
+            nrun = (int)((lo - sdist) >> 2);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int src = 0; src < 32; ++src) {
+        const int n = __shfl_sync(0xffffffffu, nrun, src);
+        if (n == 0) continue;
+        const float gx = __shfl_sync(0xffffffffu, q.gx, src), gy = __shfl_sync(0xffffffffu, q.gy, src),
+                    gz = __shfl_sync(0xffffffffu, q.gz, src);
+        const float ex = __shfl_sync(0xffffffffu, q.ex, src), ey = __shfl_sync(0xffffffffu, q.ey, src),
+                    ez = __shfl_sync(0xffffffffu, q.ez, src);
+        float part = 0.f;
+        for (int k = lane; k < n; k += 32) {
+            const float kf = (float)k + 0.5f;
+            part += fast_sample<VARIANT>(cc, __fmaf_rn(kf, ex, gx), __fmaf_rn(kf, ey, gy), __fmaf_rn(kf, ez, gz));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == src) r.acc = part;
+    }
+    bool alive = owns_pixel;
+    unsigned nlive4 = 0;
+    if (alive) {
+        sdist += 4u * (unsigned)nrun;
+        nlive4 = march_steps_fast<false, VARIANT, true>(cc, r, q, sdist, send, ray_width, a.status, alive, s_base, 0) - s_base;
+    }
+    if (owns_pixel) {
+        const float total = __double2float_rn(__dmul_rn((double)__fmul_rn(r.acc, ray_width), a.scale_k));
+        *pix = a.accumulate ? __fadd_rn(*pix, total) : total;
+        if (a.valid) atomicAdd(a.valid, (unsigned long long)(nlive4 >> 2));
+    }
+}
+
 // poly copy: the trilinear interpolant of every cell as eight polynomial coefficients (poly_coefficients), neighbours
 // clamped at the last row / column / layer like the oct copy
 __global__ void __launch_bounds__(256) pack_poly_kernel(const float* __restrict__ v, int nx, int ny, int nz,
@@ -594,7 +670,8 @@ __global__ void __launch_bounds__(128) frame_setup_kernel(const float* __restric
     if (i >= n) return;
     const float pos[3] = {poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]};
     birp_frame fr;
-    const int rc = fm::frame_setup_T<DeviceFrameMath>(pos, aim_x, tan_half_x, tan_half_y, aspect, &fr);
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    const int rc = fm::frame_setup_T<DeviceFrameMath>(pos, aim, tan_half_x, tan_half_y, aspect, &fr);
     if (rc != BIRP_OK) {
         atomicOr(status, kStatusSingular);
         return;
@@ -805,6 +882,11 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         // table (none exists behind this API today) is read step by step
         const bool kstep = g.fast_step > 0.0 && g.fast_kstep != 0;
         a.fast_step = kstep ? g.fast_step : 0.0;
+        if (g.fast_coop && kstep && !signs && variant != 0 && a.nsamples <= kSmemDist) {  // (experiment, see the kernel)
+            march_cube_fast_coop_kernel<2><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            return cudaGetLastError();
+        }
 #define BIRP_FAST_LAUNCH(S, V)                                                                       \
     if (kstep) march_cube_fast_kernel<S, V, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);   \
     else march_cube_fast_kernel<S, V, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube)

@@ -19,7 +19,7 @@ public:
     ~Camera();
 
     void SetPosition(float&, float&, float&);  // GSE position, Earth radii
-    void SetAim(float, float, float);          // only x is used, like the reference
+    void SetAim(float, float, float);          // all three reach Orient(); theta / phi use x only, like the reference
     void Render();                             // 200 samples out to 44 RE, accumulated into `image`
     int ToDat(std::string filename);           // CSV rows, "<filename>.dat"
     int ToFITS(std::string filename);          // single-image FITS, "<filename>.fits"

@@ -34,7 +34,8 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
     namespace fs = std::filesystem;
     std::vector<std::string> files;
     for (const auto& entry : fs::directory_iterator(input_dir))
-        if (entry.is_regular_file()) files.push_back(entry.path().string());
+        if (entry.is_regular_file() && entry.path().extension() != ".birpcache")  // (side-cars of DataCube::Load)
+            files.push_back(entry.path().string());
     std::sort(files.begin(), files.end());
 
     const size_t n = files.size();
@@ -44,6 +45,9 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
     size_t next_to_parse = 0, next_to_render = 0;
     if (parser_threads <= 0) parser_threads = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency()));
     const size_t window = (size_t)parser_threads + 1;  // parsed-but-not-rendered cubes kept in memory
+    // each parser converts its file on its own share of the cores (a Load left to itself starts up to 16 workers:
+    // 8 parsers x 16 workers would oversubscribe the host and multiply the parse buffers)
+    const int load_threads = (int)std::max<size_t>(1, std::max<size_t>(1, std::thread::hardware_concurrency()) / (size_t)parser_threads);
 
     auto parser = [&]() {
         for (;;) {
@@ -57,7 +61,7 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
             Slot s;
             try {
                 s.cube = std::make_unique<DataCube>();
-                s.cube->Load(files[i], false);
+                s.cube->LoadParallel(files[i], false, load_threads);
                 s.cube->SetTrilinear(trilinear);
             } catch (const std::exception& e) {
                 s.cube.reset();

@@ -95,7 +95,8 @@ void Camera::Render() {
 
     birp_frame frame;
     const float pos[3] = {position.x, position.y, position.z};
-    int rc = birp_frame_setup(pos, aim.x, fov_x, fov_y, W, H, &frame);
+    const float aim3[3] = {aim.x, aim.y, aim.z};
+    int rc = birp_frame_setup_aim(pos, aim3, fov_x, fov_y, W, H, &frame);
     if (rc != BIRP_OK) raise(rc, "Camera::Render");
 
     // the reference adds into `image` without clearing it: a second Render() accumulates

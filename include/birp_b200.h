@@ -136,6 +136,11 @@ int birp_host_free(void* p);
 /* replaces Camera::Integrate's per-frame prologue + Camera::Orient (src/Camera.cpp:85-137,309-508) */
 int birp_frame_setup(const float pos[3], float aim_x, float fov_x_deg, float fov_y_deg, int W, int H,
                      birp_frame* out);
+/* the same with the whole aim vector of Camera::SetAim(x, y, z): Camera::Orient builds its look direction from all
+   three components (src/Camera.cpp:323-327), theta and phi only from aim x (:99-104); birp_frame_setup(pos, aim_x)
+   is this call with aim = {aim_x, 0, 0} */
+int birp_frame_setup_aim(const float pos[3], const float aim[3], float fov_x_deg, float fov_y_deg, int W, int H,
+                         birp_frame* out);
 /* the same for n poses (xyz interleaved) with a common aim / field of view: an orbit sweep's frames,
    computed on up to `nthreads` host threads (0 = choose) */
 int birp_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_deg, float fov_y_deg, int W,

@@ -340,6 +340,47 @@ def ref_render(space, pos, aim_x, px_deg, fov_h, fov_w, W=0, H=0, nsamples=200, 
     return (image, secs.value) if return_seconds else image
 
 
+def ref_render_aim(space, pos, aim, px_deg, fov_h, fov_w, W=0, H=0, nsamples=200, maxdist=44):
+    """One frame through the unmodified reference Camera aimed at the point `aim` (SetAim(x, y, z))."""
+    L = ref()
+    L.ref_render3.restype = C.c_int
+    L.ref_render3.argtypes = [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp, _vp, C.c_int,
+                              C.c_int, _vp, _vp, _vp]
+    wh = np.zeros(2, dtype=np.int32)
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    if L.ref_render3(space.h, space.is_cmem, px_deg, fov_h, fov_w, W, H, _p(p), _p(a), nsamples, maxdist, None, _p(wh),
+                     None):
+        raise RuntimeError(L.ref_last_error().decode())
+    image = np.zeros((int(wh[1]), int(wh[0])), dtype=np.float32)
+    if L.ref_render3(space.h, space.is_cmem, px_deg, fov_h, fov_w, W, H, _p(p), _p(a), nsamples, maxdist, _p(image),
+                     _p(wh), None):
+        raise RuntimeError(L.ref_last_error().decode())
+    return image
+
+
+def ref_orient_aim(pos, aim) -> np.float32:
+    L = ref()
+    L.ref_orient3.restype = C.c_int
+    L.ref_orient3.argtypes = [_vp, _vp, _vp]
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    out = np.zeros(1, dtype=np.float32)
+    if L.ref_orient3(_p(p), _p(a), _p(out)):
+        raise RuntimeError(L.ref_last_error().decode())
+    return out[0]
+
+
+def orc_frame_aim(pos, aim, fov_x, fov_y, W, H) -> np.ndarray:
+    """the restatement's frame record (16 floats) for a camera aimed at the point `aim`"""
+    L = orc()
+    L.orc_frame_setup3.restype = C.c_int
+    L.orc_frame_setup3.argtypes = [_vp, _vp, C.c_float, C.c_float, C.c_int, C.c_int, _vp]
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    out = np.zeros(FRAME_FLOATS, dtype=np.float32)
+    if L.orc_frame_setup3(_p(p), _p(a), fov_x, fov_y, W, H, _p(out)):
+        raise ZeroDivisionError("Determinant is 0")
+    return out
+
+
 def ref_orient(pos, aim_x) -> np.float32:
     p = _f32(pos, (3,))
     out = np.zeros(1, dtype=np.float32)

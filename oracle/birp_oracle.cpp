@@ -202,9 +202,13 @@ float orient(const float pos[3], const float aim[3]) {
 }
 
 // src/Camera.cpp:85-137 plus the per-frame factors of :150-151
+int frame_setup3(const float pos[3], const float aim[3], float fov_x, float fov_y, int W, int H, float* fr);
 int frame_setup(const float pos[3], float aim_x, float fov_x, float fov_y, int W, int H, float* fr) {
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    return frame_setup3(pos, aim, fov_x, fov_y, W, H, fr);
+}
+int frame_setup3(const float pos[3], const float aim[3], float fov_x, float fov_y, int W, int H, float* fr) {
     float to_rad = M_PI / 180.f;
-    float aim[3] = {aim_x, 0.f, 0.f};
     float angle_sun = orient(pos, aim);
     float angle_sun_corrected = 180.f - angle_sun;
     float x_diff = aim[0] - pos[0];
@@ -540,6 +544,10 @@ int orc_cmem_param_floats() { return P_COUNT; }
 // returns 0 ok, 2 singular rotation (reference: runtime_error)
 int orc_frame_setup(const float* pos, float aim_x, float fov_x, float fov_y, int W, int H, float* frame16) {
     return frame_setup(pos, aim_x, fov_x, fov_y, W, H, frame16);
+}
+
+int orc_frame_setup3(const float* pos, const float* aim, float fov_x, float fov_y, int W, int H, float* frame16) {
+    return frame_setup3(pos, aim, fov_x, fov_y, W, H, frame16);
 }
 
 float orc_orient(const float* pos, float aim_x) {

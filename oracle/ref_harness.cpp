@@ -192,9 +192,20 @@ int ref_space_sample(void* space_ptr, int is_cmem, const float* xyz, long n, flo
 // W/H <= 0 keeps the reference's own round(fov/px) sizes (src/Camera.cpp:38-39).
 // nsamples = 200 and maxdist = 44 reproduce Camera::Render() (src/Camera.cpp:63-67).
 // image is ACCUMULATED INTO, like the reference's image member (src/Camera.cpp:223).
+int ref_render3(void* space_ptr, int is_cmem, float px_deg, float fov_h, float fov_w, int W, int H,
+                const float* pos, const float* aim, int nsamples, int maxdist, float* image,
+                int* out_wh, double* seconds);
 int ref_render(void* space_ptr, int is_cmem, float px_deg, float fov_h, float fov_w, int W, int H,
                const float* pos, float aim_x, int nsamples, int maxdist, float* image,
                int* out_wh, double* seconds) {
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    return ref_render3(space_ptr, is_cmem, px_deg, fov_h, fov_w, W, H, pos, aim, nsamples, maxdist, image, out_wh, seconds);
+}
+
+// the same with the whole aim vector of Camera::SetAim
+int ref_render3(void* space_ptr, int is_cmem, float px_deg, float fov_h, float fov_w, int W, int H,
+                const float* pos, const float* aim, int nsamples, int maxdist, float* image,
+                int* out_wh, double* seconds) {
     try {
         Space* s = is_cmem ? static_cast<Space*>(static_cast<CMEM*>(space_ptr))
                            : static_cast<Space*>(static_cast<DataCube*>(space_ptr));
@@ -214,7 +225,7 @@ int ref_render(void* space_ptr, int is_cmem, float px_deg, float fov_h, float fo
             for (int i = 0; i < w; ++i) cam.image[j][i] = image[(size_t)j * w + i];
         float px = pos[0], py = pos[1], pz = pos[2];
         cam.SetPosition(px, py, pz);
-        cam.SetAim(aim_x, 0.f, 0.f);
+        cam.SetAim(aim[0], aim[1], aim[2]);
         auto t0 = std::chrono::steady_clock::now();
         if (nsamples == 200 && maxdist == 44) {
             cam.Render();
@@ -234,7 +245,13 @@ int ref_render(void* space_ptr, int is_cmem, float px_deg, float fov_h, float fo
 }
 
 // Camera::Orient() alone (src/Camera.cpp:309-417), for pinning the host-side frame setup.
+int ref_orient3(const float* pos, const float* aim, float* angle_out);
 int ref_orient(const float* pos, float aim_x, float* angle_out) {
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    return ref_orient3(pos, aim, angle_out);
+}
+
+int ref_orient3(const float* pos, const float* aim, float* angle_out) {
     try {
         struct Dummy : Space {
             void Init() override {}
@@ -243,7 +260,7 @@ int ref_orient(const float* pos, float aim_x, float* angle_out) {
         Camera cam(dummy, 1.f, 1.f, 1.f);
         float px = pos[0], py = pos[1], pz = pos[2];
         cam.SetPosition(px, py, pz);
-        cam.SetAim(aim_x, 0.f, 0.f);
+        cam.SetAim(aim[0], aim[1], aim[2]);
         *angle_out = cam.Orient();
     } catch (const std::exception& e) {
         return fail(e);

@@ -165,9 +165,20 @@ int mir_space_sample(void* p, int kind, const float* xyz, long n, float* out) {
 
 // renders `times` times into one Camera (the reference accumulates); nsamples/maxdist <= 0 keep
 // the reference's 200 / 44.  Optionally exports with ToDat / ToFITS.
+int mir_render3(void* p, int kind, float px_deg, float fov_h, float fov_w, const float* pos, const float* aim,
+                int nsamples, int maxdist, int times, float* image, int* out_wh, const char* dat_path,
+                const char* fits_path);
 int mir_render(void* p, int kind, float px_deg, float fov_h, float fov_w, const float* pos, float aim_x,
                int nsamples, int maxdist, int times, float* image, int* out_wh, const char* dat_path,
                const char* fits_path) {
+    const float aim[3] = {aim_x, 0.f, 0.f};
+    return mir_render3(p, kind, px_deg, fov_h, fov_w, pos, aim, nsamples, maxdist, times, image, out_wh, dat_path, fits_path);
+}
+
+// the same with the whole aim vector (Camera::SetAim(x, y, z))
+int mir_render3(void* p, int kind, float px_deg, float fov_h, float fov_w, const float* pos, const float* aim,
+                int nsamples, int maxdist, int times, float* image, int* out_wh, const char* dat_path,
+                const char* fits_path) {
     try {
         Space* s = as_space(p, kind);
         Camera cam(*s, px_deg, fov_h, fov_w);
@@ -179,7 +190,7 @@ int mir_render(void* p, int kind, float px_deg, float fov_h, float fov_w, const 
         if (!image) return 0;
         float x = pos[0], y = pos[1], z = pos[2];
         cam.SetPosition(x, y, z);
-        cam.SetAim(aim_x, 0.f, 0.f);
+        cam.SetAim(aim[0], aim[1], aim[2]);
         if (nsamples > 0) cam.SetMarch(nsamples, maxdist);
         for (int t = 0; t < times; ++t) cam.Render();
         for (int j = 0; j < h; ++j)

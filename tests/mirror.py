@@ -49,6 +49,9 @@ def lib():
         L.mir_render.restype = C.c_int
         L.mir_render.argtypes = [_vp, C.c_int, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int, C.c_int,
                                  C.c_int, _vp, _vp, C.c_char_p, C.c_char_p]
+        L.mir_render3.restype = C.c_int
+        L.mir_render3.argtypes = [_vp, C.c_int, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int, C.c_int,
+                                  C.c_int, _vp, _vp, C.c_char_p, C.c_char_p]
         L.mir_render_batch.restype = C.c_int
         L.mir_render_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int,
                                        C.c_int, _vp]
@@ -167,6 +170,20 @@ def render(space, pos, aim_x, px_deg, fov_h, fov_w, nsamples=0, maxdist=0, times
     img = np.zeros((int(wh[1]), int(wh[0])), np.float32)
     if lib().mir_render(space.h, space.kind, px_deg, fov_h, fov_w, _p(p), aim_x, nsamples, maxdist, times, _p(img),
                         _p(wh), str(dat).encode() if dat else None, str(fits).encode() if fits else None):
+        _raise()
+    return img
+
+
+def render_aim(space, pos, aim, px_deg, fov_h, fov_w, nsamples=0, maxdist=0):
+    """Camera(space, ...).SetPosition(pos).SetAim(aim x, y, z).Render()"""
+    wh = np.zeros(2, np.int32)
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    if lib().mir_render3(space.h, space.kind, px_deg, fov_h, fov_w, _p(p), _p(a), nsamples, maxdist, 1, None, _p(wh),
+                         None, None):
+        _raise()
+    img = np.zeros((int(wh[1]), int(wh[0])), np.float32)
+    if lib().mir_render3(space.h, space.kind, px_deg, fov_h, fov_w, _p(p), _p(a), nsamples, maxdist, 1, _p(img), _p(wh),
+                         None, None):
         _raise()
     return img
 

@@ -461,7 +461,7 @@ def assert_fast_parity(got, want, what):
 def tuning(gpu):
     """birp_set_tuning with the defaults restored afterwards"""
     yield capi.set_tuning
-    for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1)):
+    for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0)):
         capi.set_tuning(k, v)
 
 

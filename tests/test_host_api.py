@@ -39,6 +39,24 @@ def test_frame_setup_matches_oracle():
         assert_bit_exact(got.view(np.float32).reshape(-1, 16), want, "birp_frame_setup")
 
 
+def test_frame_setup_with_the_whole_aim_vector():
+    """birp_frame_setup_aim: the record of a camera aimed at (x, y, z) is the restatement's bit for bit, its Sun roll
+    angle the reference's own Orient() (which reads all three aim components, src/Camera.cpp:323-327); aim y = z = 0
+    is birp_frame_setup"""
+    rng = np.random.default_rng(3)
+    for t in range(400):
+        pos = rng.uniform(-30, 30, 3).astype(np.float32)
+        aim = rng.uniform(-10, 10, 3).astype(np.float32)
+        if t % 4 == 0:
+            aim[1:] = 0
+        fr = capi.frame_setup_aim(pos, aim, 27.0, 16.0, 108, 64).view(np.float32)
+        assert_bit_exact(fr, O.orc_frame_aim(pos, aim, 27.0, 16.0, 108, 64), f"pos {pos} aim {aim}")
+        if O.have_ref() and t < 100:
+            assert_bit_exact(fr[15:16], np.array([O.ref_orient_aim(pos, aim)]), "Orient()")
+        if t % 4 == 0:
+            assert_bit_exact(fr, capi.frame_setup(pos, float(aim[0]), 27.0, 16.0, 108, 64).view(np.float32))
+
+
 def test_frame_setup_batch_equals_single_calls():
     poses = S.orbit_poses(1000)
     batch = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, 27.0, 16.0, 108, 64)

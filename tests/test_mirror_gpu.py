@@ -45,6 +45,21 @@ def test_camera_datacube_matches_reference_classes(gpu, cube1, tri):
 
 
 @needs_ref
+def test_camera_aim_y_and_z_reach_orient_like_the_reference(gpu, cube1):
+    """Camera::SetAim(x, y, z): Orient() builds its look direction from all three components (src/Camera.cpp:323-327),
+    so a non-zero aim y / z changes the roll of the image (the frame setup used to drop them)"""
+    zyx, org, sp = cube1
+    ref, mir = O.RefCube(zyx, org, sp, True), M.Cube(zyx, org, sp, True)
+    base = O.ref_render(ref, S.DEFAULT_POS, AIM, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+    for aim in ((AIM, 3.0, -2.0), (AIM, 0.0, 5.0), (2.0, -4.0, 0.0)):
+        want = O.ref_render_aim(ref, S.DEFAULT_POS, aim, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+        got = M.render_aim(mir, S.DEFAULT_POS, aim, S.SXI_PX, S.SXI_FOV_H, S.SXI_FOV_W)
+        assert_bit_exact(got, want, f"aim {aim}")
+        assert not np.array_equal(want, base), "the aim's y / z components must matter"
+    ref.free(), mir.free()
+
+
+@needs_ref
 def test_render_sweep_equals_one_reference_camera_per_position(gpu, cube1):
     """RenderSweep (C++ helper over birp_render_*_sweep) against the unmodified reference classes driven with
     one Camera per position: bit-identical images for the DataCube, tolerance for CMEM"""

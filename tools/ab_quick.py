@@ -64,7 +64,8 @@ def main():
     combos = []
     for spec in args.flags.split(","):
         parts = spec.split(":")
-        combos.append((spec, int(parts[0]), [(kv.split("=")[0], int(kv.split("=")[1])) for kv in parts[1:]]))
+        # a leading "n" selects nearest-neighbour sampling ("n0")
+        combos.append((spec, int(parts[0].lstrip("n")), [(kv.split("=")[0], int(kv.split("=")[1])) for kv in parts[1:]]))
     flags = [c[0] for c in combos]
     out = {"workload": "orbit", "frames": len(poses), "cube": n, "cudart": rt_path,
            "host_setup_s": round(time.perf_counter() - t0, 2)}
@@ -89,7 +90,7 @@ def main():
     ref = None
     img = np.empty((len(poses), H, W), np.float32)
     def tune(knobs):
-        for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1)):
+        for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0)):
             capi.set_tuning(k, v)
         for k, v in knobs:
             capi.set_tuning(k, v)
@@ -99,8 +100,8 @@ def main():
         ms = []
         for it in range(args.steps + 1):
             ck(rt.cudaEventRecord(e0, None), "record")
-            capi.render_cube_device(cube, d_frames.ptr, len(poses), W, H, d_img.ptr, trilinear=True, stream=0,
-                                    extra_flags=fl)
+            capi.render_cube_device(cube, d_frames.ptr, len(poses), W, H, d_img.ptr, trilinear=not spec.startswith("n"),
+                                    stream=0, extra_flags=fl)
             ck(rt.cudaEventRecord(e1, None), "record")
             ck(rt.cudaEventSynchronize(e1), "sync")
             t = C.c_float(0)

@@ -54,9 +54,13 @@ def main():
         "l1_hit_pct": round(num("l1tex__t_sector_hit_rate.pct"), 2),
         "l2_hit_pct": round(num("lts__t_sector_hit_rate.pct"), 2),
     }
-    if req > 0 and "l1tex__data_pipe_lsu_wavefronts.sum" in col and r[col["l1tex__data_pipe_lsu_wavefronts.sum"]]:
-        entry["l1_wavefronts_per_request"] = round(
-            (num("l1tex__data_pipe_lsu_wavefronts.sum") - num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")) / req, 2)
+    # L1 data-pipe wavefronts (the unit's peak is one per clock per SM): ncu reports the utilisation, the count is
+    # utilisation x elapsed L1 cycles summed over the SMs
+    wf = num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0 * num("l1tex__cycles_elapsed.sum")
+    entry["l1_wavefronts"] = int(wf)
+    entry["l1_wavefront_pct"] = round(num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"), 2)
+    if req > 0:
+        entry["l1_wavefronts_per_global_load"] = round((wf - num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")) / req, 2)
     tj = ROOT / "profiles" / "traffic.json"
     d = json.loads(tj.read_text())
     d[key] = entry
