@@ -56,6 +56,10 @@ SIGNATURES = {
     "birp_set_device": (C.c_int, [C.c_int]),
     "birp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "birp_host_free": (C.c_int, [_vp]),
+    "birp_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "birp_host_unregister": (C.c_int, [_vp]),
+    "birp_render_cube_rows": (C.c_int, [_vp, _vp] + [C.c_int] * 9 + [_vp]),
+    "birp_render_cube_device_rows": (C.c_int, [_vp, _vp] + [C.c_int] * 9 + [_vp, C.c_longlong, C.c_longlong, _vp, _vp]),
     "birp_frame_setup": (C.c_int, [_f32p, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
     "birp_frame_setup_aim": (C.c_int, [_f32p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, _vp]),
     "birp_frame_setup_batch": (C.c_int, [_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _vp,
@@ -75,6 +79,16 @@ SIGNATURES = {
     "birp_render_cmem": (C.c_int, [_vp, _vp] + [C.c_int] * 8 + [_vp]),
     "birp_render_cube_sweep": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 + [_vp, _vp]),
     "birp_render_cmem_sweep": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 + [_vp, _vp]),
+    "birp_render_cube_sweep_strided": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 +
+                                       [_vp, _vp, C.c_longlong, C.c_longlong]),
+    "birp_render_cmem_sweep_strided": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float] + [C.c_int] * 7 +
+                                       [_vp, _vp, C.c_longlong, C.c_longlong]),
+    "birp_render_cube_sweep_multi": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float] +
+                                     [C.c_int] * 7 + [_vp, _vp]),
+    "birp_render_cmem_sweep_multi": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float] +
+                                     [C.c_int] * 7 + [_vp, _vp]),
+    "birp_cube_replicate": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "birp_cube_device": (C.c_int, [_vp, _i32p]),
     "birp_accumulate": (C.c_int, [_vp, C.c_long, C.c_int, C.c_float, C.c_int, _vp]),
     "birp_ray_directions": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "birp_sample_cube": (C.c_int, [_vp, _vp, C.c_long, C.c_int, _vp]),
@@ -257,6 +271,21 @@ class Cube:
     def handle(self):
         return self._h
 
+    def replicate(self, device: int) -> "Cube":
+        """the same grid on another GPU of the box (birp_cube_replicate)"""
+        other = Cube.__new__(Cube)
+        other.nx, other.ny, other.nz = self.nx, self.ny, self.nz
+        other.origin, other.spacing = self.origin, self.spacing
+        other._h = _vp()
+        _check(lib().birp_cube_replicate(self._h, int(device), C.byref(other._h)))
+        return other
+
+    @property
+    def device(self) -> int:
+        d = (C.c_int * 1)()
+        _check(lib().birp_cube_device(self._h, d))
+        return int(d[0])
+
     def free(self):
         if self._h:
             lib().birp_cube_free(self._h)
@@ -302,10 +331,71 @@ class Cube:
         return images
 
 
+def render_cube_rows(cube: "Cube", frames: np.ndarray, W: int, H: int, band_rows: int, phase: int, nphases: int, *,
+                     nsamples: int = 200, maxdist: int = 44, trilinear: bool = True, out: np.ndarray | None = None,
+                     extra_flags: int = 0) -> np.ndarray:
+    """interleaved row bands of every frame (host buffers): bands with index = phase (mod nphases) are rendered"""
+    frames = np.ascontiguousarray(frames, dtype=FRAME_DTYPE)
+    images = out if out is not None else np.zeros((len(frames), H, W), dtype=np.float32)
+    assert images.dtype == np.float32 and images.flags.c_contiguous and images.size == len(frames) * H * W
+    flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
+    _check(lib().birp_render_cube_rows(cube.handle, _ptr(frames), len(frames), W, H, band_rows, phase, nphases, nsamples,
+                                       maxdist, flags, _ptr(images)))
+    return images
+
+
+def render_cube_device_rows(cube: "Cube", d_frames: int, nframes: int, W: int, H: int, d_images: int, band_rows: int,
+                            phase: int, nphases: int, *, nsamples=200, maxdist=44, trilinear=True, d_valid: int = 0,
+                            stream: int = 0, extra_flags: int = 0, frame_offset: int = 0, frame_stride: int = 1) -> None:
+    flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
+    _check(lib().birp_render_cube_device_rows(cube.handle, _vp(d_frames), nframes, W, H, band_rows, phase, nphases,
+                                              nsamples, maxdist, flags, _vp(d_images), frame_offset, frame_stride,
+                                              _vp(d_valid), _vp(stream)))
+
+
+def host_register(array: np.ndarray) -> None:
+    _check(lib().birp_host_register(_ptr(array), array.nbytes))
+
+
+def host_unregister(array: np.ndarray) -> None:
+    _check(lib().birp_host_unregister(_ptr(array)))
+
+
 def render_sweep(field, poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int, *, nsamples: int = 200,
                  maxdist: int = 44, trilinear: bool = True, fast=False, rows=(0, 0), extra_flags: int = 0,
-                 frames_out: np.ndarray | None = None, out: np.ndarray | None = None) -> np.ndarray:
-    """poses (host) -> images (host) in one call; `field` is a Cube or a CMEM parameter record"""
+                 frames_out: np.ndarray | None = None, out: np.ndarray | None = None, frame_offset: int = 0,
+                 frame_stride: int = 1) -> np.ndarray:
+    """poses (host) -> images (host) in one call; `field` is a Cube or a CMEM parameter record.  frame_offset /
+    frame_stride: frame f of the call lands in slot offset + f * stride of `out` (which then holds the whole sweep)"""
+    poses = _f32(poses).reshape(-1, 3)
+    n = len(poses)
+    images = out if out is not None else np.zeros((n, H, W), dtype=np.float32)
+    assert images.dtype == np.float32 and images.flags.c_contiguous
+    assert images.size >= (frame_offset + max(n - 1, 0) * frame_stride + (1 if n else 0)) * H * W
+    fr = _vp(0)
+    if frames_out is not None:
+        assert frames_out.dtype == FRAME_DTYPE and len(frames_out) == n and frames_out.flags.c_contiguous
+        fr = _ptr(frames_out)
+    if isinstance(field, Cube):
+        flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
+        _check(lib().birp_render_cube_sweep_strided(field.handle, _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H,
+                                                    rows[0], rows[1], nsamples, maxdist, flags, fr, _ptr(images),
+                                                    frame_offset, frame_stride))
+    else:
+        params = np.ascontiguousarray(field, dtype=CMEM_DTYPE)
+        _check(lib().birp_render_cmem_sweep_strided(_ptr(params), _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H,
+                                                    rows[0], rows[1], nsamples, maxdist,
+                                                    _cmem_mode(fast) | extra_flags, fr, _ptr(images), frame_offset,
+                                                    frame_stride))
+    return images
+
+
+def render_sweep_multi(fields, poses, aim_x: float, fov_x_deg: float, fov_y_deg: float, W: int, H: int, *,
+                       nsamples: int = 200, maxdist: int = 44, trilinear: bool = True, fast=False, rows=(0, 0),
+                       extra_flags: int = 0, frames_out: np.ndarray | None = None, out: np.ndarray | None = None,
+                       devices=None) -> np.ndarray:
+    """one sweep over several GPUs from this process: `fields` is a list of Cubes (one per device) or a CMEM parameter
+    record with `devices`"""
     poses = _f32(poses).reshape(-1, 3)
     n = len(poses)
     images = out if out is not None else np.zeros((n, H, W), dtype=np.float32)
@@ -314,15 +404,17 @@ def render_sweep(field, poses, aim_x: float, fov_x_deg: float, fov_y_deg: float,
     if frames_out is not None:
         assert frames_out.dtype == FRAME_DTYPE and len(frames_out) == n and frames_out.flags.c_contiguous
         fr = _ptr(frames_out)
-    if isinstance(field, Cube):
+    if isinstance(fields, (list, tuple)):
+        handles = (_vp * len(fields))(*[f.handle for f in fields])
         flags = (TRILINEAR if trilinear else NEAREST) | extra_flags
-        _check(lib().birp_render_cube_sweep(field.handle, _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H, rows[0],
-                                            rows[1], nsamples, maxdist, flags, fr, _ptr(images)))
+        _check(lib().birp_render_cube_sweep_multi(handles, len(fields), _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H,
+                                                  rows[0], rows[1], nsamples, maxdist, flags, fr, _ptr(images)))
     else:
-        params = np.ascontiguousarray(field, dtype=CMEM_DTYPE)
-        _check(lib().birp_render_cmem_sweep(_ptr(params), _ptr(poses), n, aim_x, fov_x_deg, fov_y_deg, W, H, rows[0],
-                                            rows[1], nsamples, maxdist, _cmem_mode(fast) | extra_flags, fr,
-                                            _ptr(images)))
+        params = np.ascontiguousarray(fields, dtype=CMEM_DTYPE)
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        _check(lib().birp_render_cmem_sweep_multi(_ptr(params), _ptr(devs), len(devs), _ptr(poses), n, aim_x, fov_x_deg,
+                                                  fov_y_deg, W, H, rows[0], rows[1], nsamples, maxdist,
+                                                  _cmem_mode(fast) | extra_flags, fr, _ptr(images)))
     return images
 
 

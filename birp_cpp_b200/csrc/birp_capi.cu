@@ -2,6 +2,7 @@
 // residency, pinned staging, chunked host<->device pipelines around the kernels.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -10,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -240,11 +242,28 @@ struct SweepPoses {
     birp_frame* frames_out = nullptr;  // host buffer the records are written to (caller's or a scratch vector)
 };
 
+// Where the frames of a host-buffer call land and who hands them out.
+//   slot of frame f in the caller's image buffer = out_offset + f * out_stride (1-GPU calls: 0 / 1; a sweep whose
+//   frames are interleaved over several processes writes straight into the shared result with stride = #processes);
+//   feed: the next unrendered frame of the sweep, shared by the device threads of a multi-GPU sweep (each takes a
+//   chunk at a time: dynamic load balance, the frames of an orbit do not cost the same); nullptr = this call renders
+//   every frame itself;
+//   host_threads: threads for the per-chunk frame setup (0 = choose).
+struct HostPlan {
+    long long out_offset = 0, out_stride = 1;
+    // interleaved row bands of every frame (RenderGeom::row_band ...): only those bands are rendered and copied
+    int row_band = 0, row_phase = 0, row_nphases = 1;
+    std::atomic<long long>* feed = nullptr;
+    size_t feed_chunk = 0;
+    int host_threads = 0;
+};
+
 template <class Launch>
 int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int H, int row_begin, int row_end,
                 int nsamples, int maxdist, int flags, float* images, Launch&& launch,
-                const SweepPoses* sweep = nullptr) {
+                const SweepPoses* sweep = nullptr, const HostPlan* plan_in = nullptr) {
     std::lock_guard<std::mutex> lk(c->mu);
+    const HostPlan plan = plan_in ? *plan_in : HostPlan();
     RayTable table;
     int rc = get_ray_table(c, nsamples, maxdist, c->compute, &table);
     if (rc) return rc;
@@ -258,8 +277,12 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     // set-up of the next, for a sweep) overlaps the render of another
     // (four: eight pieces of a 10 000-frame sweep were measured slower, 283.9 k against 288.8 k frames/s end to end)
     if ((size_t)nframes >= 256 && chunk > ((size_t)nframes + 3) / 4) chunk = ((size_t)nframes + 3) / 4;
+    if (plan.feed && plan.feed_chunk) chunk = plan.feed_chunk < chunk ? plan.feed_chunk : chunk;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)nframes) chunk = nframes;
+    // a sweep: a small first chunk, so that the GPU starts after the host set-up of a few frames instead of a quarter
+    // of the sweep (what stays exposed end to end is the first chunk's set-up + H2D and the last chunk's D2H)
+    const size_t first_chunk = (sweep && !plan.feed && chunk >= 512) ? chunk / 8 : chunk;
     rc = ensure(&c->d_frames, &c->frames_cap, (size_t)nframes);
     if (rc) return rc;
     for (int b = 0; b < 2; ++b) {
@@ -276,19 +299,67 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             cudaStreamSynchronize(c->copy);
         }
     } drain{c};
-    if (!sweep)
+    if (!sweep && !plan.feed)
         BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
                                   c->compute));
     const bool full_rows = (row_begin == 0 && row_end == H);
+    const size_t frame_bytes = sizeof(float) * frame_px;
+    // interleaved row bands: per frame, the own bands are `own_full` whole bands at a pitch of row_nphases bands
+    // (one 2-D copy) plus, when the image's last band is short and ours, that piece
+    const bool interleaved = plan.row_band > 0 && plan.row_nphases > 1;
+    auto copy_interleaved = [&](bool to_device, float* d_img, float* h_first, size_t h_pitch, int nf, cudaStream_t st) -> int {
+        const int rows_total = row_end - row_begin;
+        const int total_bands = (rows_total + plan.row_band - 1) / plan.row_band;
+        const int last_rows = rows_total - (total_bands - 1) * plan.row_band;  // rows of the image's last band
+        int own = (total_bands > plan.row_phase) ? (total_bands - plan.row_phase + plan.row_nphases - 1) / plan.row_nphases : 0;
+        const bool own_last = own > 0 && ((total_bands - 1) % plan.row_nphases) == plan.row_phase;
+        int own_full = own;
+        if (own_last && last_rows < plan.row_band) --own_full;
+        const size_t band_bytes = sizeof(float) * (size_t)plan.row_band * W;
+        const size_t first = (size_t)W * ((size_t)row_begin + (size_t)plan.row_phase * plan.row_band);
+        for (int f = 0; f < nf; ++f) {
+            float* d = d_img + (size_t)f * frame_px;
+            float* h = reinterpret_cast<float*>(reinterpret_cast<char*>(h_first) + (size_t)f * h_pitch);
+            if (own_full > 0) {
+                BIRP_CUDA(cudaMemcpy2DAsync(to_device ? d + first : h + first, band_bytes * plan.row_nphases,
+                                            to_device ? h + first : d + first, band_bytes * plan.row_nphases, band_bytes,
+                                            (size_t)own_full, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+            }
+            if (own_full < own) {
+                const size_t off = (size_t)W * ((size_t)row_begin + (size_t)(total_bands - 1) * plan.row_band);
+                BIRP_CUDA(cudaMemcpyAsync(to_device ? d + off : h + off, to_device ? h + off : d + off,
+                                          sizeof(float) * (size_t)last_rows * W,
+                                          to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st));
+            }
+        }
+        return BIRP_OK;
+    };
     int nchunks = 0;
-    for (size_t f0 = 0; f0 < (size_t)nframes; f0 += chunk, ++nchunks) {
+    size_t cursor = 0;  // next frame of a call that renders everything itself
+    for (;; ++nchunks) {
+        size_t f0;
+        int nf;
+        if (plan.feed) {
+            const long long got = plan.feed->fetch_add((long long)chunk);
+            if (got >= (long long)nframes) break;
+            f0 = (size_t)got;
+            nf = (int)((f0 + chunk <= (size_t)nframes) ? chunk : (size_t)nframes - f0);
+        } else {
+            if (cursor >= (size_t)nframes) break;
+            f0 = cursor;
+            // (and a small LAST chunk: its D2H is the other exposed piece)
+            const size_t rem = (size_t)nframes - f0;
+            size_t want = (nchunks == 0) ? first_chunk : chunk;
+            if (first_chunk < chunk && nchunks > 0 && rem > first_chunk && rem <= chunk + first_chunk) want = rem - first_chunk;
+            nf = (int)(want <= rem ? want : rem);
+            cursor += (size_t)nf;
+        }
         const int b = nchunks & 1;
-        const int nf = (int)((f0 + chunk <= (size_t)nframes) ? chunk : (size_t)nframes - f0);
         float* d_img = c->d_images[b];
         if (sweep) {
             // frame records of this chunk: host threads now (the GPU is busy with the previous chunk), then H2D
             int src = birp::host_frame_setup_batch(sweep->poses + 3 * f0, nf, sweep->aim_x, sweep->fov_x_deg,
-                                                   sweep->fov_y_deg, W, H, sweep->frames_out + f0, 0);
+                                                   sweep->fov_y_deg, W, H, sweep->frames_out + f0, plan.host_threads);
             if (src) {
                 cudaStreamSynchronize(c->compute);
                 read_status(c, c->compute);  // (clears a status word set by the chunks already rendered)
@@ -297,50 +368,54 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             }
             BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, sweep->frames_out + f0, sizeof(birp_frame) * nf,
                                       cudaMemcpyHostToDevice, c->compute));
+        } else if (plan.feed) {
+            BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, frames + f0, sizeof(birp_frame) * nf, cudaMemcpyHostToDevice,
+                                      c->compute));
         }
+        // caller's image slot of the chunk's first frame, and the distance between consecutive frames there
+        float* h_first = images + (size_t)(plan.out_offset + (long long)f0 * plan.out_stride) * frame_px;
+        const size_t h_pitch = (size_t)plan.out_stride * frame_bytes;
         if (nchunks >= 2) BIRP_CUDA(cudaStreamWaitEvent(c->compute, c->drained[b], 0));
         if (flags & BIRP_ACCUMULATE) {
-            if (full_rows) {
-                BIRP_CUDA(cudaMemcpyAsync(d_img, images + f0 * frame_px, sizeof(float) * nf * frame_px,
-                                          cudaMemcpyHostToDevice, c->compute));
+            if (interleaved) {
+                rc = copy_interleaved(true, d_img, h_first, h_pitch, nf, c->compute);
+                if (rc) return rc;
+            } else if (full_rows) {
+                BIRP_CUDA(cudaMemcpy2DAsync(d_img, frame_bytes, h_first, h_pitch, frame_bytes, (size_t)nf,
+                                            cudaMemcpyHostToDevice, c->compute));
             } else {
-                for (int f = 0; f < nf; ++f)
-                    BIRP_CUDA(cudaMemcpyAsync(d_img + f * frame_px + band_off,
-                                              images + (f0 + f) * frame_px + band_off, sizeof(float) * band_px,
-                                              cudaMemcpyHostToDevice, c->compute));
+                BIRP_CUDA(cudaMemcpy2DAsync(d_img + band_off, frame_bytes, h_first + band_off, h_pitch,
+                                            sizeof(float) * band_px, (size_t)nf, cudaMemcpyHostToDevice, c->compute));
             }
         }
         birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
         g.monotone_table = table.monotone;
         g.tile_w_log2 = c->tile_w_log2;
-    g.fast_variant = c->fast_variant;
-    g.tile_swizzle = c->tile_swizzle;
-    g.fast_kstep = c->fast_kstep;
-    g.fast_coop = c->fast_coop;
-    g.fast_step = table.step;
         g.fast_variant = c->fast_variant;
-    g.tile_swizzle = c->tile_swizzle;
         g.tile_swizzle = c->tile_swizzle;
-    g.fast_kstep = c->fast_kstep;
-    g.fast_coop = c->fast_coop;
-    g.fast_step = table.step;
         g.fast_kstep = c->fast_kstep;
-    g.fast_coop = c->fast_coop;
         g.fast_coop = c->fast_coop;
         g.fast_step = table.step;
+        g.row_band = plan.row_band, g.row_phase = plan.row_phase, g.row_nphases = plan.row_nphases;
         cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
         if (e != cudaSuccess)
             return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         BIRP_CUDA(cudaEventRecord(c->rendered[b], c->compute));
         BIRP_CUDA(cudaStreamWaitEvent(c->copy, c->rendered[b], 0));
-        if (full_rows) {
-            BIRP_CUDA(cudaMemcpyAsync(images + f0 * frame_px, d_img, sizeof(float) * nf * frame_px,
-                                      cudaMemcpyDeviceToHost, c->copy));
+        if (interleaved) {
+            rc = copy_interleaved(false, d_img, h_first, h_pitch, nf, c->copy);
+            if (rc) return rc;
+        } else if (full_rows) {
+            if (plan.out_stride == 1) {
+                BIRP_CUDA(cudaMemcpyAsync(h_first, d_img, frame_bytes * nf, cudaMemcpyDeviceToHost, c->copy));
+            } else {
+                BIRP_CUDA(cudaMemcpy2DAsync(h_first, h_pitch, d_img, frame_bytes, frame_bytes, (size_t)nf,
+                                            cudaMemcpyDeviceToHost, c->copy));
+            }
         } else {
-            for (int f = 0; f < nf; ++f)
-                BIRP_CUDA(cudaMemcpyAsync(images + (f0 + f) * frame_px + band_off,
-                                          d_img + f * frame_px + band_off, sizeof(float) * band_px,
-                                          cudaMemcpyDeviceToHost, c->copy));
+            // the band of every frame: rows of band_px floats, one per frame
+            BIRP_CUDA(cudaMemcpy2DAsync(h_first + band_off, h_pitch, d_img + band_off, frame_bytes,
+                                        sizeof(float) * band_px, (size_t)nf, cudaMemcpyDeviceToHost, c->copy));
         }
         BIRP_CUDA(cudaEventRecord(c->drained[b], c->copy));
     }
@@ -370,6 +445,17 @@ int birp_set_device(int ordinal) {
 int birp_host_alloc(size_t bytes, void** out) {
     if (!out) return set_error(BIRP_ERR_ARG, "null out");
     BIRP_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return BIRP_OK;
+}
+
+int birp_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return set_error(BIRP_ERR_ARG, "null buffer");
+    BIRP_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return BIRP_OK;
+}
+
+int birp_host_unregister(void* p) {
+    if (p) BIRP_CUDA(cudaHostUnregister(p));
     return BIRP_OK;
 }
 
@@ -703,6 +789,39 @@ int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const fl
     return make_cube(d_zyx, true, nx, ny, nz, origin, spacing, (cudaStream_t)stream, out);
 }
 
+// A resident cube copied to another GPU of the box: the linear grid travels device to device (cudaMemcpyPeer over
+// NVLink), the upload-time analysis and the copies for the corner fetch are rebuilt there.
+int birp_cube_replicate(const birp_cube* src, int device, birp_cube** out) {
+    if (!src || !out) return set_error(BIRP_ERR_ARG, "null pointer");
+    int prev = 0;
+    BIRP_CUDA(cudaGetDevice(&prev));
+    int ndev = 0;
+    BIRP_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_error(BIRP_ERR_ARG, "no device %d", device);
+    BIRP_CUDA(cudaSetDevice(device));
+    const birp::CubeView& v = src->view;
+    float* d_tmp = nullptr;
+    int rc = BIRP_OK;
+    cudaError_t e = cudaMalloc(&d_tmp, src->voxels * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyPeer(d_tmp, device, src->d_data, src->device, src->voxels * sizeof(float));
+    if (e != cudaSuccess) {
+        rc = set_error(e == cudaErrorMemoryAllocation ? BIRP_ERR_NOMEM : BIRP_ERR_CUDA, "cube replication to device %d: %s",
+                       device, cudaGetErrorString(e));
+    } else {
+        const float origin[3] = {v.ox, v.oy, v.oz}, spacing[3] = {v.sx, v.sy, v.sz};
+        rc = make_cube(d_tmp, true, v.nx, v.ny, v.nz, origin, spacing, nullptr, out);
+    }
+    if (d_tmp) cudaFree(d_tmp);
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int birp_cube_device(const birp_cube* cube, int* device) {
+    if (!cube || !device) return set_error(BIRP_ERR_ARG, "null pointer");
+    *device = cube->device;
+    return BIRP_OK;
+}
+
 int birp_cube_info(const birp_cube* cube, int info[4]) {
     if (!cube || !info) return set_error(BIRP_ERR_ARG, "null pointer");
     info[0] = cube->view.divmode;
@@ -781,6 +900,33 @@ int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframe
                        });
 }
 
+int birp_render_cube_rows(const birp_cube* cube, const birp_frame* frames, int nframes, int W, int H, int band_rows,
+                          int phase, int nphases, int nsamples, int maxdist, int flags, float* images) {
+    if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
+    if (band_rows < 1 || nphases < 1 || phase < 0 || phase >= nphases)
+        return set_error(BIRP_ERR_ARG, "bad row interleave: band %d phase %d of %d", band_rows, phase, nphases);
+    int row_begin = 0, row_end = H;
+    int rc = check_geom(frames, nframes, W, H, &row_begin, &row_end, nsamples, images);
+    if (rc) return rc;
+    DeviceCtx* c;
+    rc = get_ctx(&c);
+    if (rc) return rc;
+    if (c->device != cube->device) return set_error(BIRP_ERR_ARG, "cube lives on device %d", cube->device);
+    rc = ensure_poly(c, cube, flags);
+    if (rc) return rc;
+    const birp::CubeView view = cube->view;
+    int* d_status = c->d_status;
+    HostPlan plan;
+    plan.row_band = band_rows, plan.row_phase = phase, plan.row_nphases = nphases;
+    return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
+                       [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
+                           cudaStream_t s) {
+                           return birp::launch_render_cube(view, d_fr, g, d_dist, flags, d_img, nullptr,
+                                                           d_status, s);
+                       },
+                       nullptr, &plan);
+}
+
 int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, int nframes, int W, int H,
                      int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images) {
     if (!params) return set_error(BIRP_ERR_ARG, "null params");
@@ -815,9 +961,11 @@ static int check_sweep(const float* poses, int nframes, birp_frame* frames_out, 
     return BIRP_OK;
 }
 
-int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
-                           float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
-                           int flags, birp_frame* frames_out, float* images) {
+// one device's share of a sweep (the calling thread's device): everything birp_render_cube_sweep does, with the
+// plan saying where the frames land and who hands them out
+static int cube_sweep_on_device(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                                float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                                int flags, birp_frame* frames_out, float* images, const HostPlan* plan) {
     if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
     std::vector<birp_frame> scratch;
     SweepPoses sw;
@@ -838,12 +986,12 @@ int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframe
                            cudaStream_t s) {
                            return birp::launch_render_cube(view, d_fr, g, d_dist, flags, d_img, nullptr, d_status, s);
                        },
-                       &sw);
+                       &sw, plan);
 }
 
-int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
-                           float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
-                           int maxdist, int flags, birp_frame* frames_out, float* images) {
+static int cmem_sweep_on_device(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                                float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
+                                int maxdist, int flags, birp_frame* frames_out, float* images, const HostPlan* plan) {
     if (!params) return set_error(BIRP_ERR_ARG, "null params");
     std::vector<birp_frame> scratch;
     SweepPoses sw;
@@ -862,7 +1010,143 @@ int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, i
                            cudaStream_t s) {
                            return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
                        },
-                       &sw);
+                       &sw, plan);
+}
+
+int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                           float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                           int flags, birp_frame* frames_out, float* images) {
+    return cube_sweep_on_device(cube, poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end, nsamples,
+                                maxdist, flags, frames_out, images, nullptr);
+}
+
+int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                           float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
+                           int maxdist, int flags, birp_frame* frames_out, float* images) {
+    return cmem_sweep_on_device(params, poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end, nsamples,
+                                maxdist, flags, frames_out, images, nullptr);
+}
+
+static int check_stride(long long frame_offset, long long frame_stride) {
+    if (frame_offset < 0 || frame_stride < 1) return set_error(BIRP_ERR_ARG, "bad frame offset/stride");
+    return BIRP_OK;
+}
+
+int birp_render_cube_sweep_strided(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                                   float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                                   int flags, birp_frame* frames_out, float* images, long long frame_offset,
+                                   long long frame_stride) {
+    int rc = check_stride(frame_offset, frame_stride);
+    if (rc) return rc;
+    HostPlan plan;
+    plan.out_offset = frame_offset;
+    plan.out_stride = frame_stride;
+    return cube_sweep_on_device(cube, poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end, nsamples,
+                                maxdist, flags, frames_out, images, &plan);
+}
+
+int birp_render_cmem_sweep_strided(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                                   float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end,
+                                   int nsamples, int maxdist, int flags, birp_frame* frames_out, float* images,
+                                   long long frame_offset, long long frame_stride) {
+    int rc = check_stride(frame_offset, frame_stride);
+    if (rc) return rc;
+    HostPlan plan;
+    plan.out_offset = frame_offset;
+    plan.out_stride = frame_stride;
+    return cmem_sweep_on_device(params, poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end, nsamples,
+                                maxdist, flags, frames_out, images, &plan);
+}
+
+// ---- one sweep over several GPUs of the box, from one process: a host thread per device, each taking the next
+// chunk of frames from a shared counter (host frame setup -> H2D -> render -> D2H straight into the caller's buffer,
+// double-buffered per device), so every GPU's copy engine and PCIe link carry their own share and all the images end
+// up in ONE host buffer.  The first failure stops the hand-out; its code and message are returned.
+}  // extern "C"
+template <class Work>
+static int sweep_multi(int ndevices, const int* devices, int nframes, int W, int H, Work&& work) {
+    if (ndevices < 1 || !devices) return set_error(BIRP_ERR_ARG, "no devices");
+    std::atomic<long long> feed{0};
+    HostPlan plan;
+    plan.feed = &feed;
+    // a chunk per grab: about four grabs per device (balance against kernel tails), at least 64 frames
+    size_t chunk = ((size_t)nframes + (size_t)ndevices * 4 - 1) / ((size_t)ndevices * 4);
+    if (chunk < 64) chunk = 64;
+    plan.feed_chunk = chunk;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    plan.host_threads = (int)(hw / (unsigned)ndevices > 0 ? hw / (unsigned)ndevices : 1);
+    if (plan.host_threads > 8) plan.host_threads = 8;
+    (void)W, (void)H;
+    std::vector<int> rcs(ndevices, BIRP_OK);
+    std::vector<std::string> msgs(ndevices);
+    std::vector<std::thread> pool;
+    for (int d = 0; d < ndevices; ++d)
+        pool.emplace_back([&, d] {
+            cudaError_t e = cudaSetDevice(devices[d]);
+            int rc = (e == cudaSuccess) ? work(d, &plan)
+                                        : set_error(BIRP_ERR_CUDA, "cudaSetDevice(%d): %s", devices[d], cudaGetErrorString(e));
+            if (rc != BIRP_OK) {
+                feed.store((long long)nframes);  // nobody starts another chunk
+                msgs[d] = g_error;
+            }
+            rcs[d] = rc;
+        });
+    for (auto& th : pool) th.join();
+    for (int d = 0; d < ndevices; ++d)
+        if (rcs[d] != BIRP_OK) {
+            g_error = msgs[d];
+            return rcs[d];
+        }
+    return BIRP_OK;
+}
+extern "C" {
+
+int birp_render_cube_sweep_multi(const birp_cube* const* cubes, int ndevices, const float* poses, int nframes,
+                                 float aim_x, float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end,
+                                 int nsamples, int maxdist, int flags, birp_frame* frames_out, float* images) {
+    if (!cubes || ndevices < 1) return set_error(BIRP_ERR_ARG, "no cubes");
+    std::vector<int> devices(ndevices);
+    for (int d = 0; d < ndevices; ++d) {
+        if (!cubes[d]) return set_error(BIRP_ERR_ARG, "null cube");
+        devices[d] = cubes[d]->device;
+        for (int k = 0; k < d; ++k)
+            if (devices[k] == devices[d]) return set_error(BIRP_ERR_ARG, "two cubes on device %d", devices[d]);
+    }
+    if (nframes <= 0) return nframes == 0 ? BIRP_OK : set_error(BIRP_ERR_ARG, "negative frame count");
+    std::vector<birp_frame> scratch;
+    if (!frames_out) {  // one record buffer for all device threads
+        scratch.resize((size_t)nframes);
+        frames_out = scratch.data();
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = sweep_multi(ndevices, devices.data(), nframes, W, H, [&](int d, const HostPlan* plan) {
+        return cube_sweep_on_device(cubes[d], poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end,
+                                    nsamples, maxdist, flags, frames_out, images, plan);
+    });
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int birp_render_cmem_sweep_multi(const birp_cmem_params* params, const int* devices, int ndevices, const float* poses,
+                                 int nframes, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H, int row_begin,
+                                 int row_end, int nsamples, int maxdist, int flags, birp_frame* frames_out, float* images) {
+    if (!params) return set_error(BIRP_ERR_ARG, "null params");
+    if (nframes <= 0) return nframes == 0 ? BIRP_OK : set_error(BIRP_ERR_ARG, "negative frame count");
+    std::vector<birp_frame> scratch;
+    if (!frames_out) {
+        scratch.resize((size_t)nframes);
+        frames_out = scratch.data();
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = sweep_multi(ndevices, devices, nframes, W, H, [&](int, const HostPlan* plan) {
+        return cmem_sweep_on_device(params, poses, nframes, aim_x, fov_x_deg, fov_y_deg, W, H, row_begin, row_end, nsamples,
+                                    maxdist, flags, frames_out, images, plan);
+    });
+    cudaSetDevice(prev);
+    return rc;
 }
 
 int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags, float* image) {
@@ -957,10 +1241,33 @@ int birp_render_cube_device(const birp_cube* cube, const birp_frame* d_frames, i
                                            flags, d_images, 0, 1, d_valid_samples, stream);
 }
 
+static int cube_device_launch(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H, int row_begin,
+                              int row_end, int band_rows, int phase, int nphases, int nsamples, int maxdist, int flags,
+                              float* d_images, long long frame_offset, long long frame_stride,
+                              unsigned long long* d_valid_samples, void* stream);
+
 int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
                                     int row_begin, int row_end, int nsamples, int maxdist, int flags,
                                     float* d_images, long long frame_offset, long long frame_stride,
                                     unsigned long long* d_valid_samples, void* stream) {
+    return cube_device_launch(cube, d_frames, nframes, W, H, row_begin, row_end, 0, 0, 1, nsamples, maxdist, flags, d_images,
+                              frame_offset, frame_stride, d_valid_samples, stream);
+}
+
+int birp_render_cube_device_rows(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                                 int band_rows, int phase, int nphases, int nsamples, int maxdist, int flags,
+                                 float* d_images, long long frame_offset, long long frame_stride,
+                                 unsigned long long* d_valid_samples, void* stream) {
+    if (band_rows < 1 || nphases < 1 || phase < 0 || phase >= nphases)
+        return set_error(BIRP_ERR_ARG, "bad row interleave: band %d phase %d of %d", band_rows, phase, nphases);
+    return cube_device_launch(cube, d_frames, nframes, W, H, 0, H, band_rows, phase, nphases, nsamples, maxdist, flags,
+                              d_images, frame_offset, frame_stride, d_valid_samples, stream);
+}
+
+static int cube_device_launch(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H, int row_begin,
+                              int row_end, int band_rows, int phase, int nphases, int nsamples, int maxdist, int flags,
+                              float* d_images, long long frame_offset, long long frame_stride,
+                              unsigned long long* d_valid_samples, void* stream) {
     if (!cube) return set_error(BIRP_ERR_ARG, "null cube");
     if (frame_offset < 0 || frame_stride < 1) return set_error(BIRP_ERR_ARG, "bad frame offset/stride");
     int rc = check_geom(d_frames, nframes, W, H, &row_begin, &row_end, nsamples, d_images);
@@ -987,6 +1294,7 @@ int birp_render_cube_device_strided(const birp_cube* cube, const birp_frame* d_f
     g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
+    g.row_band = band_rows, g.row_phase = phase, g.row_nphases = nphases;
     cudaError_t e = birp::launch_render_cube(cube->view, d_frames, g, table.d_dist, flags, d_images,
                                              d_valid_samples, c->d_status, (cudaStream_t)stream);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));

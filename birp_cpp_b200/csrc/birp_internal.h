@@ -19,6 +19,9 @@ struct RenderGeom {
     // width (log2, -1 = choose from the angles); only used to shape the per-warp pixel tile
     float pixel_angle_x = 0.f, pixel_angle_y = 0.f;
     int tile_w_log2 = -1;
+    // interleaved row bands: of the bands of row_band rows counted from row_begin, only those with
+    // index = row_phase (mod row_nphases) are rendered (row_band = 0 or row_nphases = 1: all rows)
+    int row_band = 0, row_phase = 0, row_nphases = 1;
     int tile_swizzle = 0;  // lanes in 2x2 pixel blocks (MarchArgs::swizzle)
     // maxdist / nsamples when the ray table is the uniform one of Camera::GenerateRayDistWidth (else 0): the
     // tolerance-mode march may then compute the distance of a step instead of reading it; fast_kstep = 0 forbids that

@@ -43,6 +43,10 @@ struct MarchArgs {
     int* status;
     int W, H;
     int row_begin, rows;
+    // interleaved row bands (one large image over several GPUs): this launch renders, of the bands of `row_band`
+    // rows counted from row_begin, those with index = row_phase mod row_nphases; row_band = 0: every row of
+    // [row_begin, row_end).  `rows` counts the rows of this launch's own bands, row_end bounds the last one.
+    int row_band, row_phase, row_nphases, row_end;
     int nsamples;
     int tile_w_log2;  // a warp's 32 rays form a (1 << tile_w_log2) x (32 >> tile_w_log2) pixel tile
     int swizzle;      // lanes 4n .. 4n+3 own a 2x2 pixel block of the tile instead of four pixels of one row
@@ -84,8 +88,13 @@ __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int
     }
     i = (tx << a.tile_w_log2) + lx;
     const int jr = ty * (32 >> a.tile_w_log2) + ly;
-    j = a.row_begin + jr;
-    return i < a.W && jr < a.rows;
+    if (a.row_band > 0) {
+        const int lb = jr / a.row_band;
+        j = a.row_begin + (lb * a.row_nphases + a.row_phase) * a.row_band + (jr - lb * a.row_band);
+    } else {
+        j = a.row_begin + jr;
+    }
+    return i < a.W && jr < a.rows && j < a.row_end;
 }
 
 // Generic march: any Field functor (used for CMEM; the DataCube path has its own kernel below).
@@ -426,6 +435,14 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.H = g.H;
     a.row_begin = g.row_begin;
     a.rows = g.row_end - g.row_begin;
+    a.row_end = g.row_end;
+    a.row_band = 0, a.row_phase = 0, a.row_nphases = 1;
+    if (g.row_band > 0 && g.row_nphases > 1) {
+        const int total_bands = (a.rows + g.row_band - 1) / g.row_band;
+        const int own = (total_bands > g.row_phase) ? (total_bands - g.row_phase + g.row_nphases - 1) / g.row_nphases : 0;
+        a.row_band = g.row_band, a.row_phase = g.row_phase, a.row_nphases = g.row_nphases;
+        a.rows = own * g.row_band;
+    }
     a.nsamples = g.nsamples;
     a.tile_w_log2 = pick_tile_w_log2(g);
     a.swizzle = (g.tile_swizzle && a.tile_w_log2 >= 1 && a.tile_w_log2 <= 4) ? 1 : 0;

@@ -127,6 +127,9 @@ public:
     void Invalidate();
     // Device-resident copy (uploads on first use).  Throws std::runtime_error on CUDA failure.
     const birp_cube* Resident();
+    // The same grid on another GPU of the box (copied device to device from the first resident copy); the copies
+    // live until Load() / Invalidate().  The calling thread's current device is left as it was.
+    const birp_cube* ResidentOn(int device);
     // true while the nested `slices` have not been built (nobody touched them since Load)
     bool SlicesAreLazy() const { return flat_valid; }
 
@@ -140,6 +143,7 @@ private:
     void WriteCache(const std::string& filename, long long src_size, long long src_mtime_ns) const;
     bool trilinear = false;  // the reference leaves this uninitialised until SetTrilinear
     birp_cube* device_cube = nullptr;
+    std::vector<birp_cube*> replicas;  // ResidentOn: copies on other devices
     // the grid as Load() parsed it: flat[(z * ny + y) * nx + x]; valid until somebody touches `slices`
     std::vector<float> flat;
     bool flat_valid = false;

@@ -19,6 +19,16 @@
 #include "Cmem.h"
 #include "DataCube.h"
 
+int BirpDeviceCount() {
+    int n = 0;
+    if (birp_device_count(&n) != BIRP_OK || n < 1) return 1;
+    if (const char* env = std::getenv("BIRP_DEVICES")) {
+        const int want = std::atoi(env);
+        if (want >= 1 && want < n) n = want;
+    }
+    return n;
+}
+
 namespace {
 struct Slot {
     std::unique_ptr<DataCube> cube;
@@ -30,7 +40,7 @@ struct Slot {
 std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, const std::string& output_dir,
                                               float pixel_size_deg, float plot_fov_h, float plot_fov_w,
                                               float pos_x, float pos_y, float pos_z, float aim_x, bool trilinear,
-                                              int parser_threads) {
+                                              int parser_threads, int devices) {
     namespace fs = std::filesystem;
     std::vector<std::string> files;
     for (const auto& entry : fs::directory_iterator(input_dir))
@@ -44,7 +54,8 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
     std::condition_variable cv;
     size_t next_to_parse = 0, next_to_render = 0;
     if (parser_threads <= 0) parser_threads = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency()));
-    const size_t window = (size_t)parser_threads + 1;  // parsed-but-not-rendered cubes kept in memory
+    // parsed-but-not-rendered cubes kept in memory (the render threads hold up to two per device on top)
+    const size_t window = (size_t)parser_threads + 1 + 2 * (size_t)(devices > 0 ? devices : BirpDeviceCount());
     // each parser converts its file on its own share of the cores (a Load left to itself starts up to 16 workers:
     // 8 parsers x 16 workers would oversubscribe the host and multiply the parse buffers)
     const int load_threads = (int)std::max<size_t>(1, std::max<size_t>(1, std::thread::hardware_concurrency()) / (size_t)parser_threads);
@@ -81,39 +92,56 @@ std::vector<BatchResult> RenderBatchDirectory(const std::string& input_dir, cons
     std::vector<BatchResult> results(n);
     std::string out_prefix = output_dir;
     if (!out_prefix.empty() && out_prefix.back() != '/') out_prefix += '/';
-    for (size_t i = 0; i < n; ++i) {
-        Slot s;
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return slots[i].ready; });
-            s = std::move(slots[i]);
-            next_to_render = i + 1;
+    if (devices <= 0) devices = BirpDeviceCount();
+    size_t next_to_claim = 0;  // next cube a render thread takes (in order; next_to_render trails it for the window)
+    size_t finished = 0;
+    auto render = [&](int device) {
+        birp_set_device(device);
+        for (;;) {
+            size_t i;
+            Slot s;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (next_to_claim >= n) return;
+                i = next_to_claim++;
+                cv.wait(lk, [&] { return slots[i].ready; });
+                s = std::move(slots[i]);
+            }
+            results[i].input = files[i];
+            if (!s.cube) {
+                results[i].error = s.error;
+            } else {
+                try {
+                    Camera camera(*s.cube, pixel_size_deg, plot_fov_h, plot_fov_w);
+                    camera.SetPosition(pos_x, pos_y, pos_z);
+                    camera.SetAim(aim_x, 0.f, 0.f);
+                    camera.Render();
+                    const std::string base = files[i].substr(files[i].find_last_of("/\\") + 1);
+                    camera.ToFITS(out_prefix + base);
+                    results[i].output = out_prefix + base + ".fits";
+                } catch (const std::exception& e) {
+                    results[i].error = e.what();
+                }
+                s.cube.reset();  // (frees the device copy on this thread's device)
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ++finished;
+                next_to_render = finished;  // the parse-ahead window counts cubes that are done
+            }
+            cv.notify_all();
         }
-        cv.notify_all();
-        results[i].input = files[i];
-        if (!s.cube) {
-            results[i].error = s.error;
-            continue;
-        }
-        try {
-            Camera camera(*s.cube, pixel_size_deg, plot_fov_h, plot_fov_w);
-            camera.SetPosition(pos_x, pos_y, pos_z);
-            camera.SetAim(aim_x, 0.f, 0.f);
-            camera.Render();
-            const std::string base = files[i].substr(files[i].find_last_of("/\\") + 1);
-            camera.ToFITS(out_prefix + base);
-            results[i].output = out_prefix + base + ".fits";
-        } catch (const std::exception& e) {
-            results[i].error = e.what();
-        }
-    }
+    };
+    std::vector<std::thread> renderers;
+    for (int t = 0; t < 2 * devices; ++t) renderers.emplace_back(render, t % devices);
+    for (auto& th : renderers) th.join();
     for (auto& th : pool) th.join();
     return results;
 }
 
 std::vector<float> RenderSweep(Space& space, const std::vector<float>& positions_xyz, float aim_x,
                                float pixel_size_deg, float plot_fov_h, float plot_fov_w, int* width, int* height,
-                               int samples, int max_distance) {
+                               int samples, int max_distance, int devices) {
     // image size and fields of view exactly as Camera's constructor derives them (src/Camera.cpp:32-39)
     const int H = (int)std::round(plot_fov_h / pixel_size_deg), W = (int)std::round(plot_fov_w / pixel_size_deg);
     if (width) *width = W;
@@ -123,14 +151,32 @@ std::vector<float> RenderSweep(Space& space, const std::vector<float>& positions
     std::vector<float> images((size_t)n * H * W, 0.f);
     if (n == 0 || W <= 0 || H <= 0) return images;
     int rc;
+    if (devices <= 0) devices = BirpDeviceCount();
+    if (n < 64 * devices) devices = 1;  // too few frames to be worth a second GPU
     if (auto* cube = dynamic_cast<DataCube*>(&space)) {
         const int flags = cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST;
-        rc = birp_render_cube_sweep(cube->Resident(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H, 0, H,
-                                    samples, max_distance, flags, nullptr, images.data());
+        if (devices > 1) {
+            std::vector<const birp_cube*> cubes(devices);
+            for (int d = 0; d < devices; ++d) cubes[d] = cube->ResidentOn(d);
+            rc = birp_render_cube_sweep_multi(cubes.data(), devices, positions_xyz.data(), n, aim_x, plot_fov_w,
+                                              plot_fov_h, W, H, 0, H, samples, max_distance, flags, nullptr,
+                                              images.data());
+        } else {
+            rc = birp_render_cube_sweep(cube->Resident(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H,
+                                        0, H, samples, max_distance, flags, nullptr, images.data());
+        }
     } else if (auto* cmem = dynamic_cast<CMEM*>(&space)) {
         const int flags = cmem->FastMath() ? BIRP_CMEM_FAST : 0;
-        rc = birp_render_cmem_sweep(&cmem->Params(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H, 0, H,
-                                    samples, max_distance, flags, nullptr, images.data());
+        if (devices > 1) {
+            std::vector<int> ids(devices);
+            for (int d = 0; d < devices; ++d) ids[d] = d;
+            rc = birp_render_cmem_sweep_multi(&cmem->Params(), ids.data(), devices, positions_xyz.data(), n, aim_x,
+                                              plot_fov_w, plot_fov_h, W, H, 0, H, samples, max_distance, flags, nullptr,
+                                              images.data());
+        } else {
+            rc = birp_render_cmem_sweep(&cmem->Params(), positions_xyz.data(), n, aim_x, plot_fov_w, plot_fov_h, W, H, 0,
+                                        H, samples, max_distance, flags, nullptr, images.data());
+        }
     } else {
         throw std::invalid_argument("RenderSweep: the Space must be a DataCube or a CMEM");
     }

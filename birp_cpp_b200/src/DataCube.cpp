@@ -471,10 +471,25 @@ void DataCube::InitSize() {
 void DataCube::SetTrilinear(bool option) { trilinear = option; }
 
 void DataCube::Invalidate() {
+    for (birp_cube* r : replicas) birp_cube_free(r);
+    replicas.clear();
     if (device_cube) {
         birp_cube_free(device_cube);
         device_cube = nullptr;
     }
+}
+
+const birp_cube* DataCube::ResidentOn(int device) {
+    const birp_cube* first = Resident();
+    int dev = -1;
+    if (birp_cube_device(first, &dev) == BIRP_OK && dev == device) return first;
+    for (birp_cube* r : replicas)
+        if (birp_cube_device(r, &dev) == BIRP_OK && dev == device) return r;
+    birp_cube* copy = nullptr;
+    int rc = birp_cube_replicate(first, device, &copy);
+    if (rc != BIRP_OK) throw std::runtime_error(std::string("DataCube replication: ") + birp_last_error());
+    replicas.push_back(copy);
+    return copy;
 }
 
 const birp_cube* DataCube::Resident() {

@@ -131,6 +131,10 @@ int birp_device_count(int* count);
 int birp_set_device(int ordinal);           /* cudaSetDevice for the calling thread */
 int birp_host_alloc(size_t bytes, void** out); /* pinned host memory for images / frames */
 int birp_host_free(void* p);
+/* page-lock memory the caller already owns (e.g. a POSIX shared-memory segment that several processes drain their
+   images into) so that copies to and from it run asynchronously at full PCIe rate; undo with birp_host_unregister */
+int birp_host_register(void* p, size_t bytes);
+int birp_host_unregister(void* p);
 
 /* ------------------------------------------------------------------ host-side setup */
 /* replaces Camera::Integrate's per-frame prologue + Camera::Orient (src/Camera.cpp:85-137,309-508) */
@@ -178,6 +182,10 @@ int birp_cube_upload(const float* zyx, int nx, int ny, int nz, const float origi
 int birp_cube_upload_device(const float* d_zyx, int nx, int ny, int nz, const float origin[3],
                             const float spacing[3], void* stream, birp_cube** out);
 void birp_cube_free(birp_cube* cube);
+/* a resident cube copied to another GPU of the box (device to device over NVLink, then the same upload-time
+   analysis there); *device = the ordinal a cube lives on */
+int birp_cube_replicate(const birp_cube* src, int device, birp_cube** out);
+int birp_cube_device(const birp_cube* cube, int* device);
 /* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
    spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0, 2 when
    finite and > 0 or +0 (each class has its own exact form of std::lerp), 0 otherwise,
@@ -197,6 +205,13 @@ int birp_render_cube(const birp_cube* cube, const birp_frame* frames, int nframe
                      int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
 int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, int nframes, int W, int H,
                      int row_begin, int row_end, int nsamples, int maxdist, int flags, float* images);
+/* One large image over several GPUs in INTERLEAVED row bands (reference pixel loops: src/Camera.cpp:140-141): of the
+   bands of `band_rows` rows counted from the top, this call renders and writes those with index = phase (mod
+   nphases) -- every GPU gets the same mix of cheap rows (rays that leave the cube early) and expensive ones, which
+   contiguous bands do not give.  band_rows should be a multiple of 8 (a warp's pixel tile is 4x8 or 8x4).  Rows of
+   other phases are neither read nor written. */
+int birp_render_cube_rows(const birp_cube* cube, const birp_frame* frames, int nframes, int W, int H, int band_rows,
+                          int phase, int nphases, int nsamples, int maxdist, int flags, float* images);
 /* A sweep given as camera POSITIONS (xyz interleaved, common aim / field of view): what the reference would do
    with one Camera per pose -- SetPosition, SetAim(aim_x, 0, 0), Render() -- in one call.  The frame records are
    made by birp_frame_setup_batch chunk by chunk while the GPU renders the previous chunk and the copy engine
@@ -207,6 +222,33 @@ int birp_render_cube_sweep(const birp_cube* cube, const float* poses, int nframe
 int birp_render_cmem_sweep(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
                            float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples,
                            int maxdist, int flags, birp_frame* frames_out, float* images);
+/* The same with a scatter of the output frames: frame f of the call is written to image slot
+   frame_offset + f * frame_stride of `images` (the plain entry points are offset 0, stride 1).  A sweep whose frames
+   are interleaved over several processes (frame f of the sweep -> process f mod N) lands in ONE host buffer that the
+   processes share (POSIX shared memory, registered with the CUDA driver by each of them): every GPU drains its own
+   share over its own PCIe link. */
+int birp_render_cube_sweep_strided(const birp_cube* cube, const float* poses, int nframes, float aim_x, float fov_x_deg,
+                                   float fov_y_deg, int W, int H, int row_begin, int row_end, int nsamples, int maxdist,
+                                   int flags, birp_frame* frames_out, float* images, long long frame_offset,
+                                   long long frame_stride);
+int birp_render_cmem_sweep_strided(const birp_cmem_params* params, const float* poses, int nframes, float aim_x,
+                                   float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end,
+                                   int nsamples, int maxdist, int flags, birp_frame* frames_out, float* images,
+                                   long long frame_offset, long long frame_stride);
+/* One sweep over several GPUs of the box from ONE process (what north_star calls "frames sharded across the GPUs of
+   one box, images gathered"): cubes[d] is the same grid resident on a different device (birp_cube_upload there, or
+   birp_cube_replicate), ndevices of them.  One host thread per device; each takes the next chunk of frames from a
+   shared counter (the frames of an orbit do not cost the same), makes its frame records on the host while its GPU
+   renders the previous chunk, and drains its images straight into `images` (pinned memory: birp_host_alloc) over
+   its own PCIe link.  Same results as the single-GPU call, frame for frame.  The first failure stops the hand-out
+   and is returned.  The calling thread's current device is restored. */
+int birp_render_cube_sweep_multi(const birp_cube* const* cubes, int ndevices, const float* poses, int nframes,
+                                 float aim_x, float fov_x_deg, float fov_y_deg, int W, int H, int row_begin, int row_end,
+                                 int nsamples, int maxdist, int flags, birp_frame* frames_out, float* images);
+int birp_render_cmem_sweep_multi(const birp_cmem_params* params, const int* devices, int ndevices, const float* poses,
+                                 int nframes, float aim_x, float fov_x_deg, float fov_y_deg, int W, int H, int row_begin,
+                                 int row_end, int nsamples, int maxdist, int flags, birp_frame* frames_out,
+                                 float* images);
 /* src/Camera.cpp:201-223 on samples[nrays][nsamples] taken on the host from a user-defined Space
    subclass (e.g. the reference tests' CubeFake, tests/Camera_test.cpp:25-29). image: nrays floats. */
 int birp_accumulate(const float* samples, long nrays, int nsamples, float ray_width, int flags,
@@ -243,6 +285,11 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
                                     int W, int H, int row_begin, int row_end, int nsamples, int maxdist, int flags,
                                     float* d_images, long long frame_offset, long long frame_stride,
                                     unsigned long long* d_valid_samples, void* stream);
+/* the interleaved row bands of birp_render_cube_rows, device buffers (d_images may be another GPU's memory) */
+int birp_render_cube_device_rows(const birp_cube* cube, const birp_frame* d_frames, int nframes, int W, int H,
+                                 int band_rows, int phase, int nphases, int nsamples, int maxdist, int flags,
+                                 float* d_images, long long frame_offset, long long frame_stride,
+                                 unsigned long long* d_valid_samples, void* stream);
 /* device memory that other processes on the same box can map (CUDA IPC): the owner allocates and exports
    a 64-byte handle, a peer imports it and gets a pointer valid in its own process */
 int birp_device_alloc(size_t bytes, void** d_ptr);

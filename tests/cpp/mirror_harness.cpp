@@ -118,6 +118,42 @@ int mir_cube_export(void* cube, float* zyx) {
 
 void mir_cube_free(void* cube) { delete static_cast<DataCube*>(cube); }
 
+// state[0] = the nested slices have not been built since Load, state[1] = Load was served by a side-car
+void mir_cube_state(void* cube, int* state) {
+    DataCube* c = static_cast<DataCube*>(cube);
+    state[0] = c->SlicesAreLazy() ? 1 : 0;
+    state[1] = c->LoadedFromCache() ? 1 : 0;
+}
+
+// slices[k][j][i] = v through the public member, like reference-side code that edits the grid by hand
+int mir_cube_poke(void* cube, int k, int j, int i, float v) {
+    try {
+        DataCube* c = static_cast<DataCube*>(cube);
+        c->slices.at(k).at(j).at(i) = v;
+        c->Invalidate();
+    } catch (const std::exception& e) {
+        return fail(e);
+    }
+    return 0;
+}
+
+void mir_cache_policy(int writes, const char* dir) {
+    DataCube::SetCacheWrites(writes != 0);
+    DataCube::SetCacheDirectory(dir ? dir : "");
+}
+
+// DataCube::GetSamples (batched GetSample)
+int mir_cube_samples(void* cube, const float* xyz, long n, float* out) {
+    try {
+        std::vector<float> pts(xyz, xyz + 3 * n);
+        const std::vector<float> got = static_cast<DataCube*>(cube)->GetSamples(pts);
+        std::copy(got.begin(), got.end(), out);
+    } catch (const std::exception& e) {
+        return fail(e);
+    }
+    return 0;
+}
+
 void* mir_cmem_create_default() {
     CMEM* m = new CMEM();
     m->Init();

@@ -34,6 +34,12 @@ def lib():
         L.mir_cube_export.restype = C.c_int
         L.mir_cube_export.argtypes = [_vp, _vp]
         L.mir_cube_free.argtypes = [_vp]
+        L.mir_cube_state.argtypes = [_vp, _vp]
+        L.mir_cube_poke.restype = C.c_int
+        L.mir_cube_poke.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_float]
+        L.mir_cache_policy.argtypes = [C.c_int, C.c_char_p]
+        L.mir_cube_samples.restype = C.c_int
+        L.mir_cube_samples.argtypes = [_vp, _vp, C.c_long, _vp]
         L.mir_cmem_create_default.restype = _vp
         L.mir_cmem_create.restype = _vp
         L.mir_cmem_create.argtypes = [C.c_int, _vp, C.c_int, _vp, C.c_float, C.c_float, C.c_int, C.c_int,
@@ -112,6 +118,23 @@ class Cube(Space):
             _raise()
         return out
 
+    def state(self):
+        """(nested slices not built since Load, Load served by a side-car)"""
+        st = np.zeros(2, np.int32)
+        lib().mir_cube_state(self.h, _p(st))
+        return bool(st[0]), bool(st[1])
+
+    def poke(self, k, j, i, v):
+        if lib().mir_cube_poke(self.h, k, j, i, v):
+            _raise()
+
+    def samples(self, xyz):
+        xyz = _f32(xyz).reshape(-1, 3)
+        out = np.zeros(len(xyz), np.float32)
+        if lib().mir_cube_samples(self.h, _p(xyz), len(xyz), _p(out)):
+            _raise()
+        return out
+
     def free(self):
         if self.h:
             lib().mir_cube_free(self.h)
@@ -151,6 +174,11 @@ class Fake(Space):
         if self.h:
             lib().mir_fake_free(self.h)
             self.h = None
+
+
+def cache_policy(writes: bool, directory=None):
+    """DataCube::SetCacheWrites / SetCacheDirectory"""
+    lib().mir_cache_policy(int(writes), str(directory).encode() if directory else None)
 
 
 def sample(space, xyz):

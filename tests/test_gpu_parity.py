@@ -373,6 +373,42 @@ def test_render_row_bands_tile_the_image(dev_cube1):
     assert (canvas[:, :9] == 3.0).all() and (canvas[:, 10:] == 3.0).all() and (canvas[:, 9] > 3.0).all()
 
 
+@pytest.mark.parametrize("h,band,nph", [(64, 8, 4), (70, 16, 3), (64, 32, 8), (24, 8, 5)])
+def test_render_interleaved_row_bands_tile_the_image(dev_cube1, h, band, nph):
+    """interleaved row bands (one large image over several GPUs, birp_render_cube_rows): the phases tile the image
+    exactly, a phase touches only its own rows, also when the last band is short or a phase owns no band at all"""
+    fp, _ = frames_pair(POSES[:2], S.SXI_FOV_W, float(h) / 4, W, h)
+    full = dev_cube1.render(fp, W, h)
+    tiled = np.full_like(full, -7.0)
+    for ph in range(nph):
+        one = np.full_like(full, -7.0)
+        capi.render_cube_rows(dev_cube1, fp, W, h, band, ph, nph, out=one)
+        own = ((np.arange(h) // band) % nph) == ph
+        assert (one[:, ~own] == -7.0).all(), "a phase wrote rows of another phase"
+        assert_bit_exact(one[:, own], full[:, own], f"phase {ph}")
+        capi.render_cube_rows(dev_cube1, fp, W, h, band, ph, nph, out=tiled)
+    assert_bit_exact(tiled, full, "all phases")
+
+
+def test_sweep_with_strided_output_interleaves_into_one_buffer(dev_cube1):
+    """birp_render_cube_sweep_strided: two calls over the even and the odd frames of a sweep (what two processes
+    would do) fill one buffer that equals the single sweep"""
+    poses = S.orbit_poses(601)
+    whole = capi.render_sweep(dev_cube1, poses, AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    both = np.full_like(whole, -1.0)
+    for r in range(2):
+        capi.render_sweep(dev_cube1, poses[r::2], AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, out=both, frame_offset=r,
+                          frame_stride=2)
+    assert_bit_exact(both, whole)
+    P = capi.cmem_init()
+    whole = capi.render_sweep(P, poses[:100], AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    both = np.full_like(whole, -1.0)
+    for r in range(4):
+        capi.render_sweep(P, poses[:100][r::4], AIM, S.SXI_FOV_W, S.SXI_FOV_H, W, H, out=both, frame_offset=r,
+                          frame_stride=4)
+    assert_bit_exact(both, whole, "cmem, stride 4")
+
+
 def test_render_many_frames_chunked_pipeline(dev_cube1, cube1):
     """more frames than one staging chunk of a larger image, odd count"""
     zyx, org, sp = cube1

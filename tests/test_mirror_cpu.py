@@ -76,6 +76,114 @@ def test_loader_worker_threads_do_not_change_the_result(tmp_path, monkeypatch, t
     assert_bit_exact(mir.export(), ref.export(), "slices")
 
 
+@needs_ref
+@pytest.mark.parametrize("flavour", ["crlf", "trailing-space", "tabs", "cr-only-separators"])
+def test_loader_whitespace_like_the_reference(tmp_path, small_dat, flavour):
+    """the reference runs Helper::trim (isspace at both ends) over every VALUE line before splitting it at ' ':
+    CRLF files, lines ending in spaces / tabs and "\r"-only separator lines between slices load there (ADVICE r1:
+    they used to abort our loader)"""
+    path, zyx, org, sp = small_dat
+    lines = path.read_text().splitlines()
+    nx, ny, nz = 13, 7, 9
+    ncoord = -(-nx // 5) + -(-ny // 5) + -(-nz // 5)
+    head, coords, data = lines[:10], lines[10:10 + ncoord], lines[10 + ncoord:]
+    if flavour == "crlf":
+        text = "\r\n".join(head + coords + data) + "\r\n"
+    elif flavour == "trailing-space":
+        text = "\n".join(head + coords + [d + "   " for d in data]) + "\n"
+    elif flavour == "tabs":
+        text = "\n".join(head + coords + ["\t" + d + " \t" for d in data]) + "\n"
+    else:
+        per_thread = -(-nx // 5)
+        out = []
+        for k in range(nz):
+            out += data[k * ny * per_thread:(k + 1) * ny * per_thread] + ["\r"]
+        text = "\n".join(head + coords + out) + "\n"
+    p2 = tmp_path / f"{flavour}.dat"
+    p2.write_bytes(text.encode())
+    ref, mir = O.RefCube(path=p2), M.Cube(path=p2)
+    assert list(mir.info()[0]) == list(ref.info()[0])
+    assert_bit_exact(mir.info()[1], ref.info()[1], "origin / spacing")
+    assert_bit_exact(mir.export(), ref.export(), flavour)
+    assert_bit_exact(mir.export(), zyx)
+
+
+@needs_ref
+def test_loader_irregular_files_like_the_reference(tmp_path, small_dat):
+    """files the flat fast path must NOT take: a value line that overshoots its row (the reference never completes
+    that row), and a file that stops short -- the nested vectors come out as the reference leaves them"""
+    path, zyx, org, sp = small_dat
+    lines = path.read_text().splitlines()
+    for name, edit in (("overshoot", lambda L: L[:40] + [L[40] + " 1.0 2.0"] + L[41:]), ("short", lambda L: L[:-30])):
+        p2 = tmp_path / f"{name}.dat"
+        p2.write_text("\n".join(edit(lines)) + "\n")
+        ref, mir = O.RefCube(path=p2), M.Cube(path=p2)
+        assert not mir.state()[0], "an irregular file must be loaded into the nested vectors"
+        assert list(mir.info()[0]) == list(ref.info()[0]), name
+
+
+def test_loader_keeps_one_flat_copy_until_slices_are_touched(small_dat):
+    """Load() parses straight into the flat buffer; the nested vectors appear when somebody touches `slices`, and a
+    write through them is what the next upload sees"""
+    path, zyx, org, sp = small_dat
+    c = M.Cube(path=path)
+    assert c.state() == (True, False)
+    dims, _ = c.info()  # (reads slices.size(): a const access keeps the flat buffer)
+    assert dims[3] == 9 and c.state()[0]
+    assert_bit_exact(c.export(), zyx)  # non-const access: the nested vectors are the truth now
+    assert not c.state()[0]
+    c.free()
+
+
+def test_loader_side_car_cache(tmp_path, small_dat):
+    """a side-car is written only on request, used whenever it is valid, ignored when the ASCII file changed, and
+    can live in a directory of its own"""
+    import os
+    import shutil
+    path, zyx, org, sp = small_dat
+    src = tmp_path / "cube.dat"
+    shutil.copy(path, src)
+    try:
+        M.cache_policy(False)
+        a = M.Cube(path=src)
+        assert not (tmp_path / "cube.dat.birpcache").exists() and a.state() == (True, False)
+        M.cache_policy(True)
+        b = M.Cube(path=src)
+        assert (tmp_path / "cube.dat.birpcache").exists() and not b.state()[1]
+        M.cache_policy(False)  # reading needs no switch
+        c = M.Cube(path=src)
+        assert c.state() == (True, True)
+        assert list(c.info()[0]) == list(a.info()[0])
+        assert_bit_exact(c.info()[1], a.info()[1])
+        assert_bit_exact(c.export(), zyx)
+        # the ASCII file changes (same size, new mtime): the side-car is stale and ignored
+        text = src.read_text()
+        src.write_text(text)
+        os.utime(src, ns=(1_000_000_000, 1_000_000_000))
+        d = M.Cube(path=src)
+        assert d.state() == (True, False)
+        # a truncated side-car is ignored, not trusted
+        M.cache_policy(True)
+        M.Cube(path=src)
+        cache = tmp_path / "cube.dat.birpcache"
+        cache.write_bytes(cache.read_bytes()[:-8])
+        M.cache_policy(False)
+        assert M.Cube(path=src).state() == (True, False)
+        # side-cars in their own directory
+        cdir = tmp_path / "caches"
+        cdir.mkdir()
+        cache.unlink()
+        M.cache_policy(True, cdir)
+        M.Cube(path=src)
+        assert not cache.exists() and len(list(cdir.glob("cube.dat.*.birpcache"))) == 1
+        M.cache_policy(False, cdir)
+        e = M.Cube(path=src)
+        assert e.state() == (True, True)
+        assert_bit_exact(e.export(), zyx)
+    finally:
+        M.cache_policy(False, None)
+
+
 def test_loader_errors(tmp_path):
     with pytest.raises(ValueError):
         M.Cube(path=tmp_path / "missing.dat")

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round 2, call E (2 GPUs): whole GPU suite incl. the multi-GPU tests, 2-GPU bench lines.
+tag=${1:-r2e}
+N=${2:-2}
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 600 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${tag}_pytest_${N}gpu.log 2>&1
+tail -6 gpurun_out/${tag}_pytest_${N}gpu.log
+for spec in "orbit:0" "orbit:32768" "hires512x4k:0" "cmem:0"; do
+w=${spec%%:*}; fl=${spec#*:}
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $w --extra-flags $fl > gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.json 2> gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.err; echo "bench $w $fl rc=$?"
+python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.json').read().strip().splitlines()[-1])
+    print(d['value'], d['e2e']['value'], d['parity'], d['gather_check'], d['e2e_gather_check'], d['failed'], d.get('render_only_ms_per_rank'), (d.get('tolerance_mode') or {}).get('value'))
+except Exception as e:
+    print('no line', e)
+PY
+tail -3 gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.err
+done

@@ -41,6 +41,17 @@ for th in ("1", "4", "16"):
 os.environ.pop("BIRP_LOAD_THREADS")
 t, c = best(lambda: M.Cube(path=path))
 out["ours_default_s"] = round(t, 4)
+# side-car: written once (on request), then every Load is one read of the flat grid
+M.cache_policy(True)
+M.Cube(path=path)
+M.cache_policy(False)
+t, c = best(lambda: M.Cube(path=path))
+out["ours_side_car_s"] = round(t, 4)
+out["side_car_used"] = bool(c.state()[1])
+out["side_car_MB"] = round(os.path.getsize(path + ".birpcache") / 1e6, 1)
+got_cache = c.export()
+os.remove(path + ".birpcache")
+out["side_car_identical"] = bool(np.array_equal(got_cache.view(np.uint32), got.view(np.uint32)))
 if O.have_ref():
     t, r = best(lambda: O.RefCube(path=path), n=3)
     out["reference_s"] = round(t, 4)
