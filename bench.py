@@ -76,15 +76,33 @@ WORKLOADS = {
     "orbit-nearest": ("orbit sweep: 10000 SMILE-orbit poses, SXI 64x108 rays x 200 nearest-neighbour samples (the "
                       "reference CLI's default sampling), synthetic 256^3 cube",
                       256, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cube-nearest"),
+    "orbit-zeros": ("orbit sweep: 10000 SMILE-orbit poses, SXI 64x108 rays x 200 trilinear samples, synthetic 256^3 cube "
+                    "that is ZERO inside r < 8 RE (what MHD emissivity grids hold inside the magnetosphere)",
+                    256, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cube-zeros"),
+    "orbit-neg": ("orbit sweep: 10000 SMILE-orbit poses, SXI 64x108 rays x 200 trilinear samples, synthetic 256^3 cube with "
+                  "a slab of NEGATIVE voxels at 20 <= x < 22 RE (rays end at their first negative sample)",
+                  256, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cube-neg"),
     "cmem": ("orbit sweep: 10000 poses, SXI 64x108 rays x 200 samples of the analytic CMEM field (Init() defaults)",
              0, S.SXI_W, S.SXI_H, S.SXI_FOV_W, S.SXI_FOV_H, 200, 10000, "cmem"),
 }
 
 
+def workload_cube(cube_n, field):
+    """the synthetic grid of a workload: strictly positive, zero inside 8 RE, or with a negative slab"""
+    zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n, negative_slab=(field == "cube-neg"))
+    if field == "cube-zeros":
+        x = org[0].astype(np.float64) + sp[0].astype(np.float64) * np.arange(cube_n)
+        r2 = x[None, None, :] ** 2 + x[None, :, None] ** 2 + x[:, None, None] ** 2
+        zyx = zyx.copy()
+        zyx[r2 < 64.0] = 0.0
+    return zyx, org, sp
+
+
 def workload_config(wl, name, world):
     """the `config` object both arms print (same workload description for the driver's ratio)"""
     desc, cube_n, W, H, fov_w, fov_h, nsamples, nframes, field = wl
-    interp = {"cube": "trilinear", "cube-nearest": "nearest", "cmem": "analytic"}[field]
+    interp = {"cube": "trilinear", "cube-zeros": "trilinear", "cube-neg": "trilinear", "cube-nearest": "nearest",
+              "cmem": "analytic"}[field]
     return {"workload": desc, "name": name, "image": [H, W], "samples_per_ray": nsamples, "maxdist_RE": MAXDIST,
             "interpolation": interp, "frames": nframes, "cube": cube_n,
             "parallelism": (f"frames x{world}" if nframes > 1 else f"row tiles x{world}"),
@@ -232,8 +250,8 @@ def _ref_worker(args):
     key = (field, cube_n)
     if key not in _REF_SPACES:  # one reference DataCube / CMEM object per worker process
         if field.startswith("cube"):
-            zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n)
-            _REF_SPACES[key] = O.RefCube(zyx, org, sp, field == "cube")
+            zyx, org, sp = workload_cube(cube_n, field)
+            _REF_SPACES[key] = O.RefCube(zyx, org, sp, field != "cube-nearest")
         else:
             _REF_SPACES[key] = O.RefCmem()
     space = _REF_SPACES[key]
@@ -344,7 +362,8 @@ def run_b200(args, wl, name):
 
     desc, cube_n, W, H, fov_w, fov_h, nsamples, nframes, field = wl
     trilinear = field != "cube-nearest"
-    if field == "cube-nearest":
+    cube_kind = field
+    if field.startswith("cube"):
         field = "cube"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -362,7 +381,7 @@ def run_b200(args, wl, name):
     cube = None
     if field == "cube":
         if rank == 0:
-            zyx, org, sp = S.make_cube(cube_n, cube_n, cube_n)
+            zyx, org, sp = workload_cube(cube_n, cube_kind)
             d_cube = torch.from_numpy(zyx).to(dev)
             geom = torch.tensor(np.concatenate([org, sp]), device=dev)
         else:
@@ -620,13 +639,13 @@ def run_b200(args, wl, name):
     shm = None
     if world > 1:
         from multiprocessing import shared_memory
-        name = [None]
+        shm_name = [None]
         if rank == 0:
             shm = shared_memory.SharedMemory(create=True, size=frames_total_n * H * W * 4)
-            name[0] = shm.name
-        dist.broadcast_object_list(name, src=0)
+            shm_name[0] = shm.name
+        dist.broadcast_object_list(shm_name, src=0)
         if rank != 0:
-            shm = shared_memory.SharedMemory(name=name[0])
+            shm = shared_memory.SharedMemory(name=shm_name[0])
         h_all = np.ndarray((frames_total_n, H, W), dtype=np.float32, buffer=shm.buf)
         if rank == 0:
             h_all[:] = 0

@@ -684,6 +684,7 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
     // Oct copy for the 32-byte corner fetch (the default of the trilinear kernel): 8x the grid.  Optional like
     // the quads: when memory is short or the self-check fails the kernels use the quad copy.
     v.oct = nullptr;
+    v.oct_marked = 0;
     if (v.nx >= 2 && v.ny >= 2 && v.nz >= 2 && !getenv("BIRP_DISABLE_OCTS")) {
         const size_t bytes = cube->voxels * 8 * sizeof(float);
         size_t free_b = 0, total_b = 0;
@@ -692,7 +693,8 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
         else if (oe == cudaSuccess) oe = cudaErrorMemoryAllocation;
         if (oe == cudaSuccess) {
             cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute);
-            oe = birp::launch_pack_octs(v, cube->d_oct, c->d_flags, c->compute);
+            v.oct_marked = (v.positive == 1) ? 0 : 1;
+            oe = birp::launch_pack_octs(v, cube->d_oct, c->d_flags, v.oct_marked, c->compute);
             if (oe == cudaSuccess)
                 oe = cudaMemcpyAsync(c->h_status, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, c->compute);
             if (oe == cudaSuccess) oe = cudaStreamSynchronize(c->compute);

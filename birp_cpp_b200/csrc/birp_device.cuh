@@ -51,6 +51,11 @@ struct CubeView {
     // corners of a cell are ONE aligned 32-byte load (LDG.256), i.e. one L1 request per sample instead of two.
     // 8x the grid in device memory.
     const float* __restrict__ oct;
+    // 1: the oct copy MARKS every record that is neither "all eight corners finite and > 0" nor "all eight corners +0"
+    // by storing a NaN as its first corner (cubes outside the positive class): a sample in a marked record comes out
+    // NaN, fails the scale's range test and takes the literal path; every other record interpolates exactly with the
+    // three-operation lerp (LERP 3)
+    int oct_marked;
     // smallest / largest voxel of a positive cube, found by scan_positive_kernel at upload (0, 0 otherwise); every
     // sample interpolated from a positive cube lies between them (lean march; host-side use only)
     float vmin, vmax;
@@ -83,6 +88,21 @@ __device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, fl
     const float* f = static_cast<const float*>(p);
     a0 = f[0], a1 = f[1], a2 = f[2], a3 = f[3], b0 = f[4], b1 = f[5], b2 = f[6], b3 = f[7];
 #endif
+}
+
+// Does the oct record of these eight corners interpolate exactly with the three-operation lerp?  Yes when all are finite
+// and > 0 (proof at cube_sample_hot) or all are +0; anything else (a negative, -0, NaN or infinite corner, zeros next
+// to positive values: std::lerp's sign branch and clamp are live) is marked.
+__device__ __forceinline__ bool oct_record_is_clean(float a0, float a1, float a2, float a3, float b0, float b1, float b2,
+                                                    float b3) {
+    const float lo = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(b0, b1), fminf(b2, b3)));
+    const float hi = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)));
+    const float sum = a0 + a1 + a2 + a3 + b0 + b1 + b2 + b3;  // NaN iff a corner is NaN (or +inf and -inf meet)
+    const unsigned any_bits = __float_as_uint(a0) | __float_as_uint(a1) | __float_as_uint(a2) | __float_as_uint(a3) |
+                              __float_as_uint(b0) | __float_as_uint(b1) | __float_as_uint(b2) | __float_as_uint(b3);
+    const bool all_positive = (sum == sum) && lo > 0.f && hi < CUDART_INF_F;
+    const bool all_plus_zero = any_bits == 0u;
+    return all_positive || all_plus_zero;
 }
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
@@ -409,7 +429,11 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
         const float high_y = lerp_nonneg(high_x1, high_x2, ty, oy);
         return lerp_nonneg(low_y, high_y, tz, oz);
     }
-    if (LERP == 1) {
+    if (LERP == 1 || LERP == 3) {
+        // LERP 3 (cubes outside the positive class, oct records with marks): a record whose corners are all positive
+        // interpolates exactly as in a positive cube; one whose corners are all +0 gives 0 + t * (0 - 0) = +0, which is
+        // what std::lerp's sign branch t * 0 + (1 - t) * 0 gives; every other record carries a NaN in s000, so the
+        // sample is NaN and the caller's range test sends it to the literal sampler
         const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
         const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
         const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));
@@ -577,7 +601,7 @@ __device__ __forceinline__ unsigned march_steps_span(const CubeView& c, RayState
             do {
                 const float s = cube_sample_hot<TRILINEAR, DIVMODE, LERP, FETCH, LEAN>(c, xi, yi, zi);
                 float v;
-                const bool exact = scale_fast<LERP != 1, LEAN>(s, ray_width, K, v);
+                const bool exact = scale_fast<LERP != 1, LEAN>(s, ray_width, K, v);  // (LERP 3: a NaN sample is not exact)
                 step_ingress_only(c, r, sdist + 4, xi, yi, zi);
                 if (exact) {
                     r.acc = __fadd_rn(r.acc, v);

@@ -60,7 +60,8 @@ cudaError_t launch_scan_positive(const float* d_v, size_t n, int* d_flag, cudaSt
 // build the quad copy of the grid and compare every entry with the linear copy (*d_bad |= 1 on a mismatch)
 cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, cudaStream_t stream);
 // the same for the oct copy (32-byte records: both z layers of a cell)
-cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cudaStream_t stream);
+// (mark: CubeView::oct_marked, for cubes outside the positive class)
+cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, int mark, cudaStream_t stream);
 // the poly copy for the tolerance-mode march (32-byte records: the cell's interpolant as polynomial coefficients)
 cudaError_t launch_pack_poly(const CubeView& cube, float* d_poly, cudaStream_t stream);
 cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);

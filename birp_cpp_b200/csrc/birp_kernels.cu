@@ -492,7 +492,9 @@ cudaError_t launch_cube_fetch(const MarchArgs& a, const CubeView& c, unsigned bl
         case 2: return launch_cube_variant<true, DIV, LERP, 2, 0>(a, c, blocks, stream);
         case 5:
             if (lean && LERP == 1) return launch_cube_variant<true, DIV, 1, 5, 2>(a, c, blocks, stream);
-            return launch_cube_variant<true, DIV, LERP, 5, 1>(a, c, blocks, stream);
+            // a marked oct copy (cubes outside the positive class) is only ever read by the mark-aware form
+            if (LERP != 1) return launch_cube_variant<true, DIV, 3, 5, 1>(a, c, blocks, stream);
+            return launch_cube_variant<true, DIV, 1, 5, 1>(a, c, blocks, stream);
         case 4:
             if (span) return launch_cube_variant<true, DIV, LERP, 4, 1>(a, c, blocks, stream);
             return launch_cube_variant<true, DIV, LERP, 4, 0>(a, c, blocks, stream);
@@ -564,7 +566,7 @@ __global__ void __launch_bounds__(256) pack_quads_kernel(const float* __restrict
 
 // oct copy: oct[t] = {quad of layer z, quad of layer z + 1 (clamped at the last layer)}, 32 bytes per cell
 __global__ void __launch_bounds__(256) pack_octs_kernel(const float* __restrict__ v, int nx, int ny, int nz,
-                                                        float4* __restrict__ oct) {
+                                                        float4* __restrict__ oct, int mark) {
     const size_t n = (size_t)nx * ny * nz;
     const size_t slab = (size_t)nx * ny;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
@@ -574,14 +576,18 @@ __global__ void __launch_bounds__(256) pack_octs_kernel(const float* __restrict_
         const int dx = (x + 1 < nx) ? 1 : 0;
         const size_t dy = (y + 1 < ny) ? (size_t)nx : 0;
         const size_t u = t + ((z + 1 < nz) ? slab : 0);
-        oct[2 * t] = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
-        oct[2 * t + 1] = make_float4(__ldg(v + u), __ldg(v + u + dx), __ldg(v + u + dy), __ldg(v + u + dy + dx));
+        float4 lo = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
+        const float4 hi = make_float4(__ldg(v + u), __ldg(v + u + dx), __ldg(v + u + dy), __ldg(v + u + dy + dx));
+        // (CubeView::oct_marked) a record the three-operation lerp cannot interpolate exactly gets a NaN first corner
+        if (mark && !oct_record_is_clean(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w)) lo.x = __int_as_float(0x7fc00000);
+        oct[2 * t] = lo;
+        oct[2 * t + 1] = hi;
     }
 }
 
 // upload-time self-check of the oct copy, every entry, bit for bit, through the load the march uses
 __global__ void __launch_bounds__(256) verify_octs_kernel(const float* __restrict__ v, int nx, int ny, int nz,
-                                                          const float* __restrict__ oct, int* bad) {
+                                                          const float* __restrict__ oct, int* bad, int mark) {
     const size_t n = (size_t)nx * ny * nz;
     const size_t slab = (size_t)nx * ny;
     bool ok = true;
@@ -594,7 +600,11 @@ __global__ void __launch_bounds__(256) verify_octs_kernel(const float* __restric
         const size_t u = t + ((z + 1 < nz) ? slab : 0);
         float a0, a1, a2, a3, b0, b1, b2, b3;
         load_oct(oct + 8 * t, a0, a1, a2, a3, b0, b1, b2, b3);
-        ok &= __float_as_uint(a0) == __float_as_uint(v[t]) && __float_as_uint(a1) == __float_as_uint(v[t + dx]) &&
+        // the first corner of a record that must carry the mark is the quiet NaN, nothing else
+        const bool marked = mark && !oct_record_is_clean(v[t], v[t + dx], v[t + dy], v[t + dy + dx], v[u], v[u + dx],
+                                                         v[u + dy], v[u + dy + dx]);
+        const unsigned want0 = marked ? 0x7fc00000u : __float_as_uint(v[t]);
+        ok &= __float_as_uint(a0) == want0 && __float_as_uint(a1) == __float_as_uint(v[t + dx]) &&
               __float_as_uint(a2) == __float_as_uint(v[t + dy]) && __float_as_uint(a3) == __float_as_uint(v[t + dy + dx]) &&
               __float_as_uint(b0) == __float_as_uint(v[u]) && __float_as_uint(b1) == __float_as_uint(v[u + dx]) &&
               __float_as_uint(b2) == __float_as_uint(v[u + dy]) && __float_as_uint(b3) == __float_as_uint(v[u + dy + dx]);
@@ -879,8 +889,11 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     const bool has_quad = cube.quad != nullptr && !(flags & BIRP_NO_QUADS);
     // the run-end search needs a monotone ray table (RenderGeom::monotone_table, checked where the table is made)
     const bool span = g.monotone_table && !(flags & BIRP_WINDOW_PER_STEP);
-    // (the oct kernel exists in the span form only)
-    const bool has_oct = cube.oct != nullptr && span && !(flags & (BIRP_NO_OCTS | BIRP_NO_QUADS | BIRP_QUADS_ONLY));
+    // (the oct kernel exists in the span form only; the oct copy of a cube outside the positive class carries marks
+    // that only the default, mark-aware lerp form understands: the cross-check forms read the quad copy)
+    const bool has_oct = cube.oct != nullptr && span &&
+                         !(flags & (BIRP_NO_OCTS | BIRP_NO_QUADS | BIRP_QUADS_ONLY | BIRP_GENERAL_LERP)) &&
+                         (cube.positive == 1) == (cube.oct_marked == 0);
     int fetch = 0;
     if (tri) {
         if (has_tex && (flags & BIRP_TEXTURE_ONLY)) fetch = 1;
@@ -967,11 +980,11 @@ cudaError_t launch_pack_quads(const CubeView& cube, float4* d_quad, int* d_bad, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, cudaStream_t stream) {
-    pack_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, reinterpret_cast<float4*>(d_oct));
+cudaError_t launch_pack_octs(const CubeView& cube, float* d_oct, int* d_bad, int mark, cudaStream_t stream) {
+    pack_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, reinterpret_cast<float4*>(d_oct), mark);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    verify_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_oct, d_bad);
+    verify_octs_kernel<<<148 * 8, 256, 0, stream>>>(cube.v, cube.nx, cube.ny, cube.nz, d_oct, d_bad, mark);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -30,7 +30,8 @@ struct HostTex {
 
 struct HostCube {
     birp::CubeView view;
-    std::vector<float> grid, quad, oct, poly;
+    std::vector<float> grid, quad, oct, oct_marked, poly;  // oct_marked: the oct copy as the GPU builds it for a cube
+                                                           // outside the positive class (CubeView::oct_marked)
     HostTex tex;
 };
 
@@ -96,6 +97,10 @@ template <bool TRI, int DIV, int LERP, int FETCH, int SPAN>
 void render_variant(RenderJob& job) {
     CubeView c = job.cube->view;
     if (!TRI) c.lox = c.loy = c.loz = BIRP_TINY_INGRESS;  // launch_render_cube: nearest keeps the first cells hot
+    if (LERP == 3) {  // the mark-aware lerp form reads the marked oct copy
+        c.oct = job.cube->oct_marked.data();
+        c.oct_marked = 1;
+    }
     std::vector<float> dist(job.nsamples);
     float ray_width = 0.f;
     birp::host_ray_table(job.nsamples, job.maxdist, dist.data(), &ray_width);
@@ -158,6 +163,10 @@ bool render_lerp(RenderJob& job, int lerp, int fetch, int span) {
         case 0: return render_fetch<TRI, DIV, 0>(job, fetch, span);
         case 1: return render_fetch<TRI, DIV, 1>(job, fetch, span);
         case 2: return render_fetch<TRI, DIV, 2>(job, fetch, span);
+        case 3:  // marked oct records: exists, like the kernel, for the oct fetch and the span march only
+            if (!TRI || fetch != 5 || span != 1) return false;
+            render_variant<TRI, DIV, 3, 5, 1>(job);
+            return true;
     }
     return false;
 }
@@ -279,6 +288,12 @@ void* doh_cube_create(const float* zyx, int nx, int ny, int nz, const float orig
             std::memcpy(&h->quad[4 * t], lo, sizeof(lo));
             std::memcpy(&h->oct[8 * t], lo, sizeof(lo));
             std::memcpy(&h->oct[8 * t + 4], hi, sizeof(hi));
+        }
+        h->oct_marked = h->oct;  // pack_octs_kernel with mark = 1
+        for (size_t t = 0; t < n; ++t) {
+            const float* r = &h->oct[8 * t];
+            if (!birp::oct_record_is_clean(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]))
+                h->oct_marked[8 * t] = __int_as_float(0x7fc00000);
         }
         h->poly.resize(8 * n);  // pack_poly_kernel
         for (size_t t = 0; t < n; ++t) {

@@ -455,3 +455,39 @@ def test_fast_march_on_host_orbit_frames():
         print(f"orbit frames, kstep={kstep}: {frac:.4%} within 1e-5, max rel {rel.max():.3g}")
         assert rel.max() < 1e-5
     c.free()
+
+
+# ------------------------------------------------------------------ marked oct records (cubes outside the positive class)
+@pytest.mark.parametrize("kind", ["zeros", "negative-slab", "random-negatives", "negative-zeros", "nan-inf"])
+def test_marked_oct_records_march_equals_oracle(kind):
+    """the default march of a cube outside the positive class (LERP 3): records whose corners are all positive or
+    all +0 interpolate with the three-operation lerp, every other record carries a NaN mark and its samples take the
+    literal path -- images bit for bit those of the oracle, incl. where rays end"""
+    rng = np.random.default_rng(7)
+    zyx, org, sp = small_grid()
+    zyx = zyx.copy()
+    if kind == "zeros":
+        zyx[8:14] = 0.0
+        zyx[rng.random(zyx.shape) < 0.05] = 0.0
+    elif kind == "negative-slab":
+        zyx[:, :, 14:16] *= -1.0
+    elif kind == "random-negatives":
+        zyx[rng.random(zyx.shape) < 0.2] *= -1.0
+    elif kind == "negative-zeros":
+        zyx[8:14] = 0.0
+        zyx[10, 5:9, :] = -0.0
+    else:
+        zyx[5, 6, 7] = np.nan
+        zyx[15, 16, 17] = np.inf
+        zyx[12, 3, 20] = -np.inf
+    poses = np.array([(0.5, 2.0, 3.0), (1.0, 4.0, 2.5), (org[0] + 13.0 * sp[0], org[1] + 12.2 * sp[1], org[2] + 11.0 * sp[2])],
+                     np.float32)
+    fp, fo = frames_pair(poses, 40.0, 40.0, 24, 24)
+    c = D.HostCube(zyx, org, sp, divmode=1)
+    assert c.lerp_class != 1
+    for nsamples in (300, 4500):
+        want, wvalid = O.orc_render_cube(zyx, org, sp, True, fo, 24, 24, nsamples=nsamples, maxdist=12, return_valid=True)
+        got, gvalid, st = c.render(fp, 24, 24, lerp=3, fetch=5, span=1, nsamples=nsamples, maxdist=12)
+        assert st == 0 and gvalid == wvalid
+        assert_bit_exact(got, want, f"{kind}, n={nsamples}")
+    c.free()

@@ -6,7 +6,10 @@ the quick check of a hot loop's size without a GPU.
     python tools/sass_loops.py /tmp/k.sass
 """
 import re
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early
 
 for line in open(sys.argv[1]):
     m = re.match(r'\s+/\*([0-9a-f]{4})\*/\s+(.*?)\s*;', line)
