@@ -555,6 +555,38 @@ def run_b200(args, wl, name):
         total_ms, kern_ms_mean, valid_total = float(t[0]), float(t[1]), float(t[2])
     capi.check_device_status(sptr)
 
+    # ---- N > 1: what rank 0 holds must be what one GPU renders (a few frames / rows of other ranks' shares)
+    gather_check = None
+    e2e_gather_check = None
+    e2e_note = "bytes are per rank; every rank moves its own share"
+    parity_rows = (rows[0], min(rows[0] + 16, rows[1]))
+    if peer is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            full = peer.tensor((nframes, H, W) if nframes > 1 else (1, H, W))
+            if nframes > 1:
+                probe = np.unique(np.linspace(0, nframes - 1, 24).astype(int))
+                d_pf = torch.from_numpy(frames_all[probe].view(np.float32).reshape(-1, 16).copy()).to(dev)
+                d_pi = torch.zeros((len(probe), H, W), dtype=torch.float32, device=dev)
+                if field == "cube":
+                    capi.render_cube_device(cube, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(), nsamples=nsamples,
+                                            maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
+                else:
+                    capi.render_cmem_device(params, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(),
+                                            nsamples=nsamples, maxdist=MAXDIST, stream=sptr,
+                                            fast=cmem_mode())
+                torch.cuda.synchronize()
+                same = bool(torch.equal(full[torch.from_numpy(probe).to(dev)], d_pi))
+                gather_check = {"frames_compared": int(len(probe)), "identical_to_single_gpu_render": same}
+            else:
+                d_one = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
+                capi.render_cube_device(cube, d_frames.data_ptr(), 1, W, H, d_one.data_ptr(), nsamples=nsamples,
+                                        maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
+                torch.cuda.synchronize()
+                gather_check = {"rows_compared": int(H), "identical_to_single_gpu_render": bool(torch.equal(full, d_one))}
+        dist.barrier()
+
     # ---- the same job in tolerance mode (BIRP_FAST_MARCH), when the main measurement is the bit-exact default: device
     # timed like `value`, its images compared with the default's (which are the reference's, bit for bit)
     fast_arm = None
@@ -596,38 +628,6 @@ def run_b200(args, wl, name):
         EXTRA_FLAGS = saved
         launch()  # (d_images hold the default's pixels again)
         torch.cuda.synchronize()
-
-    # ---- N > 1: what rank 0 holds must be what one GPU renders (a few frames / rows of other ranks' shares)
-    gather_check = None
-    e2e_gather_check = None
-    e2e_note = "bytes are per rank; every rank moves its own share"
-    parity_rows = (rows[0], min(rows[0] + 16, rows[1]))
-    if peer is not None:
-        torch.cuda.synchronize()
-        dist.barrier()
-        if rank == 0:
-            full = peer.tensor((nframes, H, W) if nframes > 1 else (1, H, W))
-            if nframes > 1:
-                probe = np.unique(np.linspace(0, nframes - 1, 24).astype(int))
-                d_pf = torch.from_numpy(frames_all[probe].view(np.float32).reshape(-1, 16).copy()).to(dev)
-                d_pi = torch.zeros((len(probe), H, W), dtype=torch.float32, device=dev)
-                if field == "cube":
-                    capi.render_cube_device(cube, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(), nsamples=nsamples,
-                                            maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
-                else:
-                    capi.render_cmem_device(params, d_pf.data_ptr(), len(probe), W, H, d_pi.data_ptr(),
-                                            nsamples=nsamples, maxdist=MAXDIST, stream=sptr,
-                                            fast=cmem_mode())
-                torch.cuda.synchronize()
-                same = bool(torch.equal(full[torch.from_numpy(probe).to(dev)], d_pi))
-                gather_check = {"frames_compared": int(len(probe)), "identical_to_single_gpu_render": same}
-            else:
-                d_one = torch.zeros((1, H, W), dtype=torch.float32, device=dev)
-                capi.render_cube_device(cube, d_frames.data_ptr(), 1, W, H, d_one.data_ptr(), nsamples=nsamples,
-                                        maxdist=MAXDIST, trilinear=trilinear, stream=sptr, extra_flags=EXTRA_FLAGS)
-                torch.cuda.synchronize()
-                gather_check = {"rows_compared": int(H), "identical_to_single_gpu_render": bool(torch.equal(full, d_one))}
-        dist.barrier()
 
     # ---- e2e: the host-buffer C ABI call, pinned host memory, H2D + D2H inside the timed region.
     # N > 1: ALL images land in one host buffer that rank 0 owns -- a POSIX shared-memory segment every rank maps and

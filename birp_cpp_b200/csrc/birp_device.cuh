@@ -90,19 +90,26 @@ __device__ __forceinline__ void load_oct(const void* p, float& a0, float& a1, fl
 #endif
 }
 
-// Does the oct record of these eight corners interpolate exactly with the three-operation lerp?  Yes when all are finite
-// and > 0 (proof at cube_sample_hot) or all are +0; anything else (a negative, -0, NaN or infinite corner, zeros next
-// to positive values: std::lerp's sign branch and clamp are live) is marked.
-__device__ __forceinline__ bool oct_record_is_clean(float a0, float a1, float a2, float a3, float b0, float b1, float b2,
-                                                    float b3) {
+// How does the oct record of these eight corners interpolate (cubes outside the positive class, CubeView::oct_marked)?
+//   0  exactly with the three-operation lerp: all corners finite and > 0 (proof at cube_sample_hot), or all +0;
+//   1  all corners finite and >= +0 but zeros next to positive values: std::lerp's sign branch gives RN((1-t) a) where
+//      the three-operation form gives RN(a - RN(t a)) -- the record is SIGN-marked (its first corner, which is >= +0,
+//      is stored negated) and the march interpolates it with lerp_nonneg, inside the hot loop;
+//   2  anything else (a negative, -0, NaN or infinite corner): NaN-marked, the sample takes the literal path (where
+//      a negative sample ends the ray).
+__device__ __forceinline__ int oct_record_class(float a0, float a1, float a2, float a3, float b0, float b1, float b2,
+                                                float b3) {
     const float lo = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(b0, b1), fminf(b2, b3)));
     const float hi = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)));
     const float sum = a0 + a1 + a2 + a3 + b0 + b1 + b2 + b3;  // NaN iff a corner is NaN (or +inf and -inf meet)
     const unsigned any_bits = __float_as_uint(a0) | __float_as_uint(a1) | __float_as_uint(a2) | __float_as_uint(a3) |
                               __float_as_uint(b0) | __float_as_uint(b1) | __float_as_uint(b2) | __float_as_uint(b3);
-    const bool all_positive = (sum == sum) && lo > 0.f && hi < CUDART_INF_F;
-    const bool all_plus_zero = any_bits == 0u;
-    return all_positive || all_plus_zero;
+    const bool finite = (sum == sum) && hi < CUDART_INF_F && lo > -CUDART_INF_F;
+    if (finite && lo > 0.f) return 0;
+    if (any_bits == 0u) return 0;
+    // no sign bit anywhere: every corner is +0 or positive
+    if (finite && (any_bits & 0x80000000u) == 0u) return 1;
+    return 2;
 }
 
 // The four voxels (x0..x0+1, y0..y0+1) of layer z in ONE texture instruction: tld4 returns the
@@ -429,11 +436,25 @@ __device__ __forceinline__ float cube_sample_hot(const CubeView& c, float xi, fl
         const float high_y = lerp_nonneg(high_x1, high_x2, ty, oy);
         return lerp_nonneg(low_y, high_y, tz, oz);
     }
+    if (LERP == 3 && __float_as_int(s000) < 0) {
+        // sign-marked record (zeros next to positive corners, oct_record_class 1): the non-negative form of std::lerp,
+        // here in the hot loop -- a ray crosses the surface of a zero region at a step of its own, and a lane that left
+        // the loop for it would fall out of step with its warp
+        s000 = fabsf(s000);
+        const float ox = __fsub_rn(1.f, tx), oy = __fsub_rn(1.f, ty), oz = __fsub_rn(1.f, tz);
+        const float low_x1 = lerp_nonneg(s000, l001, tx, ox);
+        const float low_x2 = lerp_nonneg(l010, l011, tx, ox);
+        const float high_x1 = lerp_nonneg(l100, l101, tx, ox);
+        const float high_x2 = lerp_nonneg(l110, l111, tx, ox);
+        const float low_y = lerp_nonneg(low_x1, low_x2, ty, oy);
+        const float high_y = lerp_nonneg(high_x1, high_x2, ty, oy);
+        return lerp_nonneg(low_y, high_y, tz, oz);
+    }
     if (LERP == 1 || LERP == 3) {
         // LERP 3 (cubes outside the positive class, oct records with marks): a record whose corners are all positive
         // interpolates exactly as in a positive cube; one whose corners are all +0 gives 0 + t * (0 - 0) = +0, which is
-        // what std::lerp's sign branch t * 0 + (1 - t) * 0 gives; every other record carries a NaN in s000, so the
-        // sample is NaN and the caller's range test sends it to the literal sampler
+        // what std::lerp's sign branch t * 0 + (1 - t) * 0 gives; a NaN-marked record (oct_record_class 2) yields a NaN
+        // sample, and the caller's range test sends it to the literal sampler
         const float low_x1 = __fadd_rn(s000, __fmul_rn(tx, __fsub_rn(l001, s000)));
         const float low_x2 = __fadd_rn(l010, __fmul_rn(tx, __fsub_rn(l011, l010)));
         const float high_x1 = __fadd_rn(l100, __fmul_rn(tx, __fsub_rn(l101, l100)));
@@ -1024,11 +1045,28 @@ __device__ __forceinline__ float cmem_b1(const birp_cmem_params& P, float r, flo
     return __fmul_rn(__fmul_rn(P.A1, e), pw);
 }
 
+// 1 / c in fp64 to within an ulp or so: hardware seed (MUFU.RCP64H, ~20 bits) and three Newton steps, 7 instructions
+// where the IEEE division takes ~30 (seed, iterations, range fix-up).  Used where the quotient is rounded to fp32
+// right away: the fp32 result differs from the correctly rounded division's only when the fp64 value lies within an
+// ulp64 of an fp32 rounding boundary (about one sample in 2^27).
+__device__ __forceinline__ double rcp_newton(double c) {
+#ifdef __CUDACC__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(c));
+    y = fma(y, fma(-c, y, 1.0), y);
+    y = fma(y, fma(-c, y, 1.0), y);
+    return fma(y, fma(-c, y, 1.0), y);
+#else
+    return 1.0 / c;
+#endif
+}
+
 // b2 of src/Cmem.cpp:162-173: beyond the magnetosheath, computed in double from the fp32 quotient r/10
 __device__ __forceinline__ float cmem_b2(const birp_cmem_params& P, float r) {
     const double sd = (double)__fdiv_rn(r, 10.f);
     const double cube = __dmul_rn(__dmul_rn(sd, sd), sd);
-    return __double2float_rn(__dmul_rn((double)P.A2, __ddiv_rn(1.0, cube)));
+    // (r finite and non-zero here: the cube of an fp32 quotient widened to fp64 neither overflows nor underflows)
+    return __double2float_rn(__dmul_rn((double)P.A2, (cube > 0.0 && cube < 1e300) ? rcp_newton(cube) : __ddiv_rn(1.0, cube)));
 }
 
 // magnetopause (LinScaled, :188-222) and bow-shock (ShueModel, :280-288) radii in the sample's direction

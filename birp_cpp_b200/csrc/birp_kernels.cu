@@ -579,7 +579,11 @@ __global__ void __launch_bounds__(256) pack_octs_kernel(const float* __restrict_
         float4 lo = make_float4(__ldg(v + t), __ldg(v + t + dx), __ldg(v + t + dy), __ldg(v + t + dy + dx));
         const float4 hi = make_float4(__ldg(v + u), __ldg(v + u + dx), __ldg(v + u + dy), __ldg(v + u + dy + dx));
         // (CubeView::oct_marked) a record the three-operation lerp cannot interpolate exactly gets a NaN first corner
-        if (mark && !oct_record_is_clean(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w)) lo.x = __int_as_float(0x7fc00000);
+        if (mark) {
+            const int cls = oct_record_class(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w);
+            if (cls == 1) lo.x = -lo.x;
+            if (cls == 2) lo.x = __int_as_float(0x7fc00000);
+        }
         oct[2 * t] = lo;
         oct[2 * t + 1] = hi;
     }
@@ -601,9 +605,9 @@ __global__ void __launch_bounds__(256) verify_octs_kernel(const float* __restric
         float a0, a1, a2, a3, b0, b1, b2, b3;
         load_oct(oct + 8 * t, a0, a1, a2, a3, b0, b1, b2, b3);
         // the first corner of a record that must carry the mark is the quiet NaN, nothing else
-        const bool marked = mark && !oct_record_is_clean(v[t], v[t + dx], v[t + dy], v[t + dy + dx], v[u], v[u + dx],
-                                                         v[u + dy], v[u + dy + dx]);
-        const unsigned want0 = marked ? 0x7fc00000u : __float_as_uint(v[t]);
+        const int cls = mark ? oct_record_class(v[t], v[t + dx], v[t + dy], v[t + dy + dx], v[u], v[u + dx], v[u + dy],
+                                                v[u + dy + dx]) : 0;
+        const unsigned want0 = cls == 2 ? 0x7fc00000u : cls == 1 ? (__float_as_uint(v[t]) | 0x80000000u) : __float_as_uint(v[t]);
         ok &= __float_as_uint(a0) == want0 && __float_as_uint(a1) == __float_as_uint(v[t + dx]) &&
               __float_as_uint(a2) == __float_as_uint(v[t + dy]) && __float_as_uint(a3) == __float_as_uint(v[t + dy + dx]) &&
               __float_as_uint(b0) == __float_as_uint(v[u]) && __float_as_uint(b1) == __float_as_uint(v[u + dx]) &&

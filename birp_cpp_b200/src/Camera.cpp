@@ -39,9 +39,17 @@ void card(std::string& hdr, const std::string& key, const std::string& value, co
     hdr.append(buf, 80);
 }
 
-std::string fits_number(double x) {
-    char buf[40];
-    std::snprintf(buf, sizeof(buf), "%20.9G", x);
+// A float keyword value the way cfitsio writes a TFLOAT key (putkey.c: ffpkye with decim = -7 -> ffr2e): "%.7G" of
+// the value; an exponent form without a decimal point is redone as "%.1E"; a plain integer-looking result gets a
+// trailing '.' so that it reads back as a real; right-justified in columns 11-30.
+std::string fits_number(float x) {
+    char v[40];
+    std::snprintf(v, sizeof(v), "%.7G", (double)x);
+    if (!std::strchr(v, '.') && std::strchr(v, 'E')) std::snprintf(v, sizeof(v), "%.1E", (double)x);
+    if (!std::strchr(v, '.') && !std::strchr(v, 'E') && !std::strchr(v, 'N') && !std::strchr(v, 'I'))
+        std::strncat(v, ".", sizeof(v) - std::strlen(v) - 1);
+    char buf[48];
+    std::snprintf(buf, sizeof(buf), "%20s", v);
     return buf;
 }
 
@@ -49,6 +57,13 @@ std::string fits_int(long x) {
     char buf[40];
     std::snprintf(buf, sizeof(buf), "%20ld", x);
     return buf;
+}
+
+// COMMENT card: keyword, two blanks, text from column 11 (cfitsio ffpcom)
+void comment_card(std::string& hdr, const std::string& text) {
+    char buf[96];
+    std::snprintf(buf, sizeof(buf), "COMMENT   %-70.70s", text.c_str());
+    hdr.append(buf, 80);
 }
 
 void pad_to_block(std::string& s, char fill) { s.append((2880 - s.size() % 2880) % 2880, fill); }
@@ -167,12 +182,17 @@ int Camera::ToDat(std::string filename) {
 int Camera::ToFITS(std::string filename) {
     const int W = image_dimension_x, H = image_dimension_y;
     std::string hdr;
-    card(hdr, "SIMPLE", "                   T", "file conforms to FITS standard");
-    card(hdr, "BITPIX", fits_int(-32), "IEEE single precision floating point");
+    // the cards, in the order and with the comments cfitsio / EleFits give a single-image file written by
+    // src/Camera.cpp:252-307: the mandatory keywords of fits_create_img and its two COMMENT cards, the ten float
+    // records of header().writeSeq (unit in brackets: EleFits' raw comment), then the string record "rho"
+    card(hdr, "SIMPLE", "                   T", "file does conform to FITS standard");
+    card(hdr, "BITPIX", fits_int(-32), "number of bits per data pixel");
     card(hdr, "NAXIS", fits_int(2), "number of data axes");
-    card(hdr, "NAXIS1", fits_int(W), "image width (x fastest)");
-    card(hdr, "NAXIS2", fits_int(H), "image height");
-    card(hdr, "EXTEND", "                   T", "");
+    card(hdr, "NAXIS1", fits_int(W), "length of data axis 1");
+    card(hdr, "NAXIS2", fits_int(H), "length of data axis 2");
+    card(hdr, "EXTEND", "                   T", "FITS dataset may contain extensions");
+    comment_card(hdr, "FITS (Flexible Image Transport System) format is defined in 'Astronomy");
+    comment_card(hdr, "and Astrophysics', volume 376, page 359; bibcode: 2001A&A...376..359H");
     card(hdr, "CRVAL1", fits_number(-(fov_x / 2)), "[deg]");
     card(hdr, "CDELT1", fits_number(pixel_size_deg), "[deg]");
     card(hdr, "CRVAL2", fits_number(-(fov_y / 2)), "[deg]");
@@ -183,7 +203,7 @@ int Camera::ToFITS(std::string filename) {
     card(hdr, "AIM_X", fits_number(aim.x), "[float]");
     card(hdr, "AIM_Y", fits_number(aim.y), "[float]");
     card(hdr, "AIM_Z", fits_number(aim.z), "[float]");
-    card(hdr, "RHO", "'0       '", "[t] comment");
+    card(hdr, "RHO", "'0       '          ", "[t] comment");  // (a short string is padded to column 30, like a number)
     hdr.append("END");
     pad_to_block(hdr, ' ');
 

@@ -55,15 +55,24 @@ inline std::string card(const std::string& key, const std::string& value, const 
     std::snprintf(buf, sizeof(buf), "%-8.8s= %-70.70s", k.c_str(), v.c_str());
     return std::string(buf, 80);
 }
+// a TFLOAT keyword value as cfitsio formats it (putkey.c: ffpkye, decim = -7 -> ffr2e): "%.7G", an exponent form
+// without a decimal point redone as "%.1E", a '.' appended to an integer-looking result; right-justified to column 30
 inline std::string value_of(float x) {
-    char buf[40];
-    std::snprintf(buf, sizeof(buf), "%20.9G", (double)x);
+    char v[40];
+    std::snprintf(v, sizeof(v), "%.7G", (double)x);
+    if (!std::strchr(v, '.') && std::strchr(v, 'E')) std::snprintf(v, sizeof(v), "%.1E", (double)x);
+    if (!std::strchr(v, '.') && !std::strchr(v, 'E') && !std::strchr(v, 'N') && !std::strchr(v, 'I')) std::strcat(v, ".");
+    char buf[48];
+    std::snprintf(buf, sizeof(buf), "%20s", v);
     return buf;
 }
+// a string value (ffpkys): at least eight characters inside the quotes, padded to column 30 like a number
 inline std::string value_of(const std::string& s) {
     std::string q = "'" + s;
     while (q.size() < 9) q += ' ';
-    return q + "'";
+    q += "'";
+    while (q.size() < 20) q += ' ';
+    return q;
 }
 inline std::string value_of(long x) {
     char buf[40];
@@ -97,12 +106,22 @@ public:
     template <typename R, typename Raster>
     void write(const R& record, const Raster& raster) {
         using namespace shim_detail;
-        std::string hdr = card("SIMPLE", "                   T", "file conforms to FITS standard");
-        hdr += card("BITPIX", value_of(-32L), "IEEE single precision floating point");
+        // the mandatory keywords and the two COMMENT cards of cfitsio's fits_create_img
+        std::string hdr = card("SIMPLE", "                   T", "file does conform to FITS standard");
+        hdr += card("BITPIX", value_of(-32L), "number of bits per data pixel");
         hdr += card("NAXIS", value_of(2L), "number of data axes");
-        hdr += card("NAXIS1", value_of((long)raster.width), "image width (x fastest)");
-        hdr += card("NAXIS2", value_of((long)raster.height), "image height");
-        hdr += card("EXTEND", "                   T", "");
+        hdr += card("NAXIS1", value_of((long)raster.width), "length of data axis 1");
+        hdr += card("NAXIS2", value_of((long)raster.height), "length of data axis 2");
+        hdr += card("EXTEND", "                   T", "FITS dataset may contain extensions");
+        {
+            char buf[96];
+            std::snprintf(buf, sizeof(buf), "COMMENT   %-70.70s",
+                          "FITS (Flexible Image Transport System) format is defined in 'Astronomy");
+            hdr += std::string(buf, 80);
+            std::snprintf(buf, sizeof(buf), "COMMENT   %-70.70s",
+                          "and Astrophysics', volume 376, page 359; bibcode: 2001A&A...376..359H");
+            hdr += std::string(buf, 80);
+        }
         for (const auto& c : cards_) hdr += c;
         hdr += record_card(record);
         hdr += "END";

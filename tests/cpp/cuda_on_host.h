@@ -26,6 +26,11 @@ static inline float __int_as_float(int i) {  // (math_constants.h spells CUDART_
     std::memcpy(&f, &i, 4);
     return f;
 }
+static inline int __float_as_int(float f) {
+    int i;
+    std::memcpy(&i, &f, 4);
+    return i;
+}
 static inline unsigned __float_as_uint(float f) {
     unsigned u;
     std::memcpy(&u, &f, 4);

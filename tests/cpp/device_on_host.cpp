@@ -292,8 +292,9 @@ void* doh_cube_create(const float* zyx, int nx, int ny, int nz, const float orig
         h->oct_marked = h->oct;  // pack_octs_kernel with mark = 1
         for (size_t t = 0; t < n; ++t) {
             const float* r = &h->oct[8 * t];
-            if (!birp::oct_record_is_clean(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]))
-                h->oct_marked[8 * t] = __int_as_float(0x7fc00000);
+            const int cls = birp::oct_record_class(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+            if (cls == 1) h->oct_marked[8 * t] = -r[0];
+            if (cls == 2) h->oct_marked[8 * t] = __int_as_float(0x7fc00000);
         }
         h->poly.resize(8 * n);  // pack_poly_kernel
         for (size_t t = 0; t < n; ++t) {

@@ -239,6 +239,30 @@ int mir_render3(void* p, int kind, float px_deg, float fov_h, float fov_w, const
     return 0;
 }
 
+// Camera::ToFITS of a given image, no render (and no GPU): a Camera on a dummy Space whose image is filled by hand
+int mir_fits_of_image(float px_deg, float fov_h, float fov_w, const float* pos, const float* aim, const float* image,
+                      int* out_wh, const char* path) {
+    try {
+        struct Dummy : Space {
+            void Init() override {}
+            float GetSample(float, float, float) override { return 0.f; }
+        } dummy;
+        Camera cam(dummy, px_deg, fov_h, fov_w);
+        out_wh[0] = cam.Width();
+        out_wh[1] = cam.Height();
+        if (!image) return 0;
+        float x = pos[0], y = pos[1], z = pos[2];
+        cam.SetPosition(x, y, z);
+        cam.SetAim(aim[0], aim[1], aim[2]);
+        for (int j = 0; j < cam.Height(); ++j)
+            for (int i = 0; i < cam.Width(); ++i) cam.image[j][i] = image[(size_t)j * cam.Width() + i];
+        cam.ToFITS(path);
+    } catch (const std::exception& e) {
+        return fail(e);
+    }
+    return 0;
+}
+
 // RenderBatchDirectory; returns the number of cubes rendered, -1 on exception
 int mir_render_batch(const char* in_dir, const char* out_dir, float px_deg, float fov_h, float fov_w,
                      const float* pos, float aim_x, int trilinear, int threads, int* failed) {

@@ -58,6 +58,8 @@ def lib():
         L.mir_render3.restype = C.c_int
         L.mir_render3.argtypes = [_vp, C.c_int, C.c_float, C.c_float, C.c_float, _vp, _vp, C.c_int, C.c_int,
                                   C.c_int, _vp, _vp, C.c_char_p, C.c_char_p]
+        L.mir_fits_of_image.restype = C.c_int
+        L.mir_fits_of_image.argtypes = [C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp, C.c_char_p]
         L.mir_render_batch.restype = C.c_int
         L.mir_render_batch.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_float, _vp, C.c_float, C.c_int,
                                        C.c_int, _vp]
@@ -214,6 +216,20 @@ def render_aim(space, pos, aim, px_deg, fov_h, fov_w, nsamples=0, maxdist=0):
                          None, None):
         _raise()
     return img
+
+
+def fits_of_image(path, image, pos, aim, px_deg, fov_h, fov_w):
+    """Camera::ToFITS of a hand-filled image (no render, no GPU); writes <path>.fits; image None: (W, H) only"""
+    wh = np.zeros(2, np.int32)
+    p, a = _f32(pos, (3,)), _f32(aim, (3,))
+    if image is None:
+        if lib().mir_fits_of_image(px_deg, fov_h, fov_w, _p(p), _p(a), None, _p(wh), None):
+            _raise()
+        return int(wh[0]), int(wh[1])
+    img = _f32(image)
+    if lib().mir_fits_of_image(px_deg, fov_h, fov_w, _p(p), _p(a), _p(img), _p(wh), str(path).encode()):
+        _raise()
+    return int(wh[0]), int(wh[1])
 
 
 def render_sweep(space, positions, aim_x, px_deg, fov_h, fov_w):
