@@ -19,7 +19,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
 DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY, CMEM_LIBM64, CMEM_NO_FILTER = 8, 16, 32, 64, 128, 256, 512, 1024, 2048
-WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH, FAST_MARCH, NO_LEAN_MARCH = 4096, 8192, 16384, 32768, 65536
+WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH, FAST_MARCH, NO_LEAN_MARCH, CMEM_NO_TABLE, CMEM_LIBM32 = 4096, 8192, 16384, 32768, 65536, 131072, 262144
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -105,6 +105,7 @@ SIGNATURES = {
     "birp_check_device_status": (C.c_int, [_vp]),
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
     "birp_selftest_cmem_filter": (C.c_int, [_vp, C.c_long, _vp]),
+    "birp_selftest_cmem_table": (C.c_int, [_vp, C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
     "birp_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
 }
@@ -419,12 +420,17 @@ def render_sweep_multi(fields, poses, aim_x: float, fov_x_deg: float, fov_y_deg:
 
 
 def _cmem_mode(fast) -> int:
-    """fast: False = default (own fp64 blocks behind the region filter), True = fp32 libdevice calls,
-    "libm64" = CUDA fp64 library, "nofilter" = own fp64 blocks for every sample"""
+    """fast: False = default (own fp64 blocks behind the region table and filter), True = tolerance mode (fp32 values
+    behind the same decisions), "libm64" = CUDA fp64 library, "nofilter" = own fp64 blocks for every sample,
+    "notable" = default without the region table, "libm32" = CUDA fp32 library for every sample"""
     if fast == "libm64":
         return CMEM_LIBM64
     if fast == "nofilter":
         return CMEM_NO_FILTER
+    if fast == "notable":
+        return CMEM_NO_TABLE
+    if fast == "libm32":
+        return CMEM_LIBM32
     return CMEM_FAST if fast else 0
 
 
@@ -549,6 +555,13 @@ def selftest_cmem_filter(params: np.ndarray, n: int = 1 << 24) -> dict:
     out = np.zeros(3, dtype=np.float64)
     _check(lib().birp_selftest_cmem_filter(_ptr(params), n, _ptr(out)))
     return dict(zip(("margin_used_mp", "margin_used_bs", "trusted_fraction"), out.tolist()))
+
+
+def selftest_cmem_table(params: np.ndarray, n: int = 1 << 24) -> dict:
+    params = np.ascontiguousarray(params, dtype=CMEM_DTYPE)
+    out = np.zeros(3, dtype=np.float64)
+    _check(lib().birp_selftest_cmem_table(_ptr(params), n, _ptr(out)))
+    return dict(zip(("differing_samples", "decided_fraction", "table_in_use"), out.tolist()))
 
 
 def launch_count() -> int:

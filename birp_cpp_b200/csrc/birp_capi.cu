@@ -67,7 +67,10 @@ struct RayTable {
 struct DeviceCtx {
     int device = -1;
     cudaStream_t compute = nullptr;
+    cudaStream_t compute2 = nullptr;  // odd chunks of a host-buffer call: the next chunk's kernel fills the SMs the
+                                      // previous one's last CTAs leave idle
     cudaStream_t copy = nullptr;
+    cudaEvent_t frames_ready = nullptr;
     cudaEvent_t rendered[2] = {nullptr, nullptr};
     cudaEvent_t drained[2] = {nullptr, nullptr};
     std::map<std::pair<int, int>, RayTable> tables;
@@ -83,7 +86,12 @@ struct DeviceCtx {
     // spacing bits + limit bits -> cheapest exact div_spacing mode (0, 1, 2), proven on this device
     std::map<std::pair<unsigned, unsigned>, int> divmode_cache;
     // CMEM parameter record (raw bytes) -> may the region filter be used?  (self-test at first use, see cmem_flags)
-    std::map<std::string, bool> cmem_filter_ok;
+    struct CmemState {
+        bool filter_ok = false;       // the fp32 estimates stay within a quarter of their margin
+        float4* d_table = nullptr;    // region table (cmem_table_kernel), or nullptr when it failed its self-test
+        unsigned long long table_decided = 0, table_probes = 0;  // of the self-test's positions: how many the table decided
+    };
+    std::map<std::string, CmemState> cmem_state;
     int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
     int tile_swizzle = 0;     // BIRP_TILE_SWIZZLE override (experiments)
     int fast_variant = -1;    // BIRP_FAST_VARIANT override (experiments)
@@ -110,7 +118,9 @@ int get_ctx(DeviceCtx** out) {
     DeviceCtx* c = new DeviceCtx();
     c->device = dev;
     BIRP_CUDA(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+    BIRP_CUDA(cudaStreamCreateWithFlags(&c->compute2, cudaStreamNonBlocking));
     BIRP_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+    BIRP_CUDA(cudaEventCreateWithFlags(&c->frames_ready, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         BIRP_CUDA(cudaEventCreateWithFlags(&c->rendered[i], cudaEventDisableTiming));
         BIRP_CUDA(cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming));
@@ -214,20 +224,50 @@ int run_cmem_filter_selftest(DeviceCtx* c, const birp_cmem_params& params, long 
 // self-test runs here once, at first use (4M directions, a few ms, cached per device): if the estimates use
 // more than a quarter of the margin the filter is switched off for that set (BIRP_CMEM_NO_FILTER, same results,
 // slower) -- the CMEM counterpart of the division / texture / quad self-checks at cube upload.
-int cmem_flags(DeviceCtx* c, const birp_cmem_params& params, int flags, int* out_flags) {
+int cmem_flags(DeviceCtx* c, const birp_cmem_params& params, int flags, int* out_flags, const float4** d_table = nullptr) {
     *out_flags = flags;
-    if (flags & (BIRP_CMEM_FAST | BIRP_CMEM_LIBM64 | BIRP_CMEM_NO_FILTER)) return BIRP_OK;
+    if (d_table) *d_table = nullptr;
+    if (flags & (BIRP_CMEM_LIBM32 | BIRP_CMEM_LIBM64 | BIRP_CMEM_NO_FILTER)) return BIRP_OK;
     const std::string key(reinterpret_cast<const char*>(&params), sizeof(params));
     std::lock_guard<std::mutex> lk(c->mu);
-    auto it = c->cmem_filter_ok.find(key);
-    if (it == c->cmem_filter_ok.end()) {
+    auto it = c->cmem_state.find(key);
+    if (it == c->cmem_state.end()) {
+        DeviceCtx::CmemState st;
         double u[3];
         int rc = run_cmem_filter_selftest(c, params, 1L << 22, u);
         if (rc) return rc;
-        const bool ok = u[0] <= 0.25 && u[1] <= 0.25;  // (NaNs compare false: no filter)
-        it = c->cmem_filter_ok.emplace(key, ok).first;
+        st.filter_ok = u[0] <= 0.25 && u[1] <= 0.25;  // (NaNs compare false: no filter)
+        // The region table of this parameter set: built once (512 bins x 25 x 2049 exact evaluations, a few ms), then
+        // the march with it is compared with the unfiltered evaluation on 4M pseudo-random positions; a single
+        // differing sample and the table is dropped for this set.
+        if (st.filter_ok && !getenv("BIRP_DISABLE_CMEM_TABLE")) {
+            cudaError_t e = cudaMalloc(&st.d_table, sizeof(float4) * birp::kCmemTableBins);
+            if (e == cudaSuccess) e = birp::launch_cmem_table(params, st.d_table, c->compute);
+            unsigned long long h[2] = {1, 0};
+            const long n = 1L << 22;
+            if (e == cudaSuccess) {
+                rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
+                if (rc) return rc;
+                unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_scratch);
+                e = cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), c->compute);
+                if (e == cudaSuccess) e = birp::launch_cmem_table_selftest(params, st.d_table, n, d_out, c->compute);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->compute);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(c->compute);
+            }
+            if (e != cudaSuccess || h[0] != 0) {
+                cudaGetLastError();
+                if (st.d_table) cudaFree(st.d_table);
+                st.d_table = nullptr;
+            } else {
+                st.table_decided = h[1];
+                st.table_probes = (unsigned long long)n;
+            }
+        }
+        it = c->cmem_state.emplace(key, st).first;
     }
-    if (!it->second) *out_flags |= BIRP_CMEM_NO_FILTER;
+    if (!it->second.filter_ok) *out_flags |= (flags & BIRP_CMEM_FAST) ? BIRP_CMEM_LIBM32 : BIRP_CMEM_NO_FILTER;
+    if (!it->second.filter_ok) *out_flags &= ~BIRP_CMEM_FAST;
+    if (d_table && !(flags & BIRP_CMEM_NO_TABLE)) *d_table = it->second.d_table;
     return BIRP_OK;
 }
 
@@ -296,12 +336,16 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         DeviceCtx* c;
         ~DrainOnExit() {
             cudaStreamSynchronize(c->compute);
+            cudaStreamSynchronize(c->compute2);
             cudaStreamSynchronize(c->copy);
         }
     } drain{c};
-    if (!sweep && !plan.feed)
+    if (!sweep && !plan.feed) {
         BIRP_CUDA(cudaMemcpyAsync(c->d_frames, frames, sizeof(birp_frame) * nframes, cudaMemcpyHostToDevice,
                                   c->compute));
+        BIRP_CUDA(cudaEventRecord(c->frames_ready, c->compute));
+        BIRP_CUDA(cudaStreamWaitEvent(c->compute2, c->frames_ready, 0));
+    }
     const bool full_rows = (row_begin == 0 && row_end == H);
     const size_t frame_bytes = sizeof(float) * frame_px;
     // interleaved row bands: per frame, the own bands are `own_full` whole bands at a pitch of row_nphases bands
@@ -356,36 +400,38 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         }
         const int b = nchunks & 1;
         float* d_img = c->d_images[b];
+        cudaStream_t cs = b ? c->compute2 : c->compute;  // (chunks alternate between two compute streams)
         if (sweep) {
             // frame records of this chunk: host threads now (the GPU is busy with the previous chunk), then H2D
             int src = birp::host_frame_setup_batch(sweep->poses + 3 * f0, nf, sweep->aim_x, sweep->fov_x_deg,
                                                    sweep->fov_y_deg, W, H, sweep->frames_out + f0, plan.host_threads);
             if (src) {
                 cudaStreamSynchronize(c->compute);
+                cudaStreamSynchronize(c->compute2);
                 read_status(c, c->compute);  // (clears a status word set by the chunks already rendered)
                 if (src == BIRP_ERR_SINGULAR) return set_error(src, "Determinant is 0");
                 return src;
             }
             BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, sweep->frames_out + f0, sizeof(birp_frame) * nf,
-                                      cudaMemcpyHostToDevice, c->compute));
+                                      cudaMemcpyHostToDevice, cs));
         } else if (plan.feed) {
             BIRP_CUDA(cudaMemcpyAsync(c->d_frames + f0, frames + f0, sizeof(birp_frame) * nf, cudaMemcpyHostToDevice,
-                                      c->compute));
+                                      cs));
         }
         // caller's image slot of the chunk's first frame, and the distance between consecutive frames there
         float* h_first = images + (size_t)(plan.out_offset + (long long)f0 * plan.out_stride) * frame_px;
         const size_t h_pitch = (size_t)plan.out_stride * frame_bytes;
-        if (nchunks >= 2) BIRP_CUDA(cudaStreamWaitEvent(c->compute, c->drained[b], 0));
+        if (nchunks >= 2) BIRP_CUDA(cudaStreamWaitEvent(cs, c->drained[b], 0));
         if (flags & BIRP_ACCUMULATE) {
             if (interleaved) {
-                rc = copy_interleaved(true, d_img, h_first, h_pitch, nf, c->compute);
+                rc = copy_interleaved(true, d_img, h_first, h_pitch, nf, cs);
                 if (rc) return rc;
             } else if (full_rows) {
                 BIRP_CUDA(cudaMemcpy2DAsync(d_img, frame_bytes, h_first, h_pitch, frame_bytes, (size_t)nf,
-                                            cudaMemcpyHostToDevice, c->compute));
+                                            cudaMemcpyHostToDevice, cs));
             } else {
                 BIRP_CUDA(cudaMemcpy2DAsync(d_img + band_off, frame_bytes, h_first + band_off, h_pitch,
-                                            sizeof(float) * band_px, (size_t)nf, cudaMemcpyHostToDevice, c->compute));
+                                            sizeof(float) * band_px, (size_t)nf, cudaMemcpyHostToDevice, cs));
             }
         }
         birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
@@ -397,10 +443,10 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         g.fast_coop = c->fast_coop;
         g.fast_step = table.step;
         g.row_band = plan.row_band, g.row_phase = plan.row_phase, g.row_nphases = plan.row_nphases;
-        cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, c->compute);
+        cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, cs);
         if (e != cudaSuccess)
             return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-        BIRP_CUDA(cudaEventRecord(c->rendered[b], c->compute));
+        BIRP_CUDA(cudaEventRecord(c->rendered[b], cs));
         BIRP_CUDA(cudaStreamWaitEvent(c->copy, c->rendered[b], 0));
         if (interleaved) {
             rc = copy_interleaved(false, d_img, h_first, h_pitch, nf, c->copy);
@@ -419,7 +465,8 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
         }
         BIRP_CUDA(cudaEventRecord(c->drained[b], c->copy));
     }
-    BIRP_CUDA(cudaStreamSynchronize(c->copy));
+    BIRP_CUDA(cudaStreamSynchronize(c->copy));  // (the copy stream waited for every chunk's kernel)
+    BIRP_CUDA(cudaStreamSynchronize(c->compute2));
     return read_status(c, c->compute);
 }
 
@@ -938,12 +985,13 @@ int birp_render_cmem(const birp_cmem_params* params, const birp_frame* frames, i
     rc = get_ctx(&c);
     if (rc) return rc;
     const birp_cmem_params P = *params;
-    rc = cmem_flags(c, P, flags, &flags);
+    const float4* d_table = nullptr;
+    rc = cmem_flags(c, P, flags, &flags, &d_table);
     if (rc) return rc;
     return render_host(c, frames, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
                        [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
                            cudaStream_t s) {
-                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
+                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s, d_table);
                        });
 }
 
@@ -1005,12 +1053,13 @@ static int cmem_sweep_on_device(const birp_cmem_params* params, const float* pos
     rc = get_ctx(&c);
     if (rc) return rc;
     const birp_cmem_params P = *params;
-    rc = cmem_flags(c, P, flags, &flags);
+    const float4* d_table = nullptr;
+    rc = cmem_flags(c, P, flags, &flags, &d_table);
     if (rc) return rc;
     return render_host(c, sw.frames_out, nframes, W, H, row_begin, row_end, nsamples, maxdist, flags, images,
                        [&](const birp_frame* d_fr, const birp::RenderGeom& g, const float* d_dist, float* d_img,
                            cudaStream_t s) {
-                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s);
+                           return birp::launch_render_cmem(P, d_fr, g, d_dist, flags, d_img, nullptr, s, d_table);
                        },
                        &sw, plan);
 }
@@ -1221,7 +1270,8 @@ int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, i
     DeviceCtx* c;
     int rc = get_ctx(&c);
     if (rc) return rc;
-    rc = cmem_flags(c, *params, flags, &flags);
+    const float4* d_table = nullptr;
+    rc = cmem_flags(c, *params, flags, &flags, &d_table);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)n * 4);
@@ -1229,7 +1279,7 @@ int birp_sample_cmem(const birp_cmem_params* params, const float* xyz, long n, i
     float* d_xyz = c->d_scratch;
     float* d_out = c->d_scratch + (size_t)n * 3;
     BIRP_CUDA(cudaMemcpyAsync(d_xyz, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, c->compute));
-    cudaError_t e = birp::launch_sample_cmem(*params, d_xyz, n, flags, d_out, c->compute);
+    cudaError_t e = birp::launch_sample_cmem(*params, d_xyz, n, flags, d_out, c->compute, d_table);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     BIRP_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->compute));
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
@@ -1337,10 +1387,11 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
     g.fast_step = table.step;
     g.out_frame_offset = frame_offset;
     g.out_frame_stride = frame_stride;
-    rc = cmem_flags(c, *params, flags, &flags);  // (first use of a parameter set: a self-test on the library's stream)
+    const float4* d_table = nullptr;
+    rc = cmem_flags(c, *params, flags, &flags, &d_table);  // (first use of a parameter set: table + self-tests on the library's stream)
     if (rc) return rc;
     cudaError_t e = birp::launch_render_cmem(*params, d_frames, g, table.d_dist, flags, d_images,
-                                             d_valid_samples, (cudaStream_t)stream);
+                                             d_valid_samples, (cudaStream_t)stream, d_table);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return BIRP_OK;
 }
@@ -1420,6 +1471,33 @@ int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(c->mu);
     return run_cmem_filter_selftest(c, *params, n, out);
+}
+
+int birp_selftest_cmem_table(const birp_cmem_params* params, long n, double out[3]) {
+    if (!params || n <= 0 || !out) return set_error(BIRP_ERR_ARG, "bad arguments");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    int flags = 0;
+    const float4* d_table = nullptr;
+    rc = cmem_flags(c, *params, 0, &flags, &d_table);  // builds (and self-tests) the table at first use
+    if (rc) return rc;
+    out[0] = out[1] = 0.0;
+    out[2] = d_table ? 1.0 : 0.0;
+    if (!d_table) return BIRP_OK;
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
+    if (rc) return rc;
+    unsigned long long* d_out = reinterpret_cast<unsigned long long*>(c->d_scratch);
+    BIRP_CUDA(cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), c->compute));
+    cudaError_t e = birp::launch_cmem_table_selftest(*params, d_table, n, d_out, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    unsigned long long h[2];
+    BIRP_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    out[0] = (double)h[0];
+    out[1] = (double)h[1] / (double)n;
+    return BIRP_OK;
 }
 
 unsigned long long birp_launch_count(void) { return birp::launch_count(); }

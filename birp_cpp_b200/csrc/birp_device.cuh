@@ -912,7 +912,15 @@ struct CmemDev {
     float p3dn, p3ds;                      // p3 * dn, p3 * ds       (:217)
     int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
     int q_nonpositive;                     // p2 * charlie <= 0: the cusp term of LinScaled can only lower the radius
+    // Region table of this parameter set (cmem_table_kernel; nullptr: none): kCmemTableBins bins over cos(theta) in
+    // [-1, 1], each {mp_lo, mp_hi, bs_lo, bs_hi}: whatever phi, a sample of that bin with r < mp_lo is inside the
+    // magnetopause layer, with r > mp_hi outside it, with r < bs_lo inside the bow-shock layer, with r > bs_hi beyond
+    // it -- bounds over every direction of the bin and its two neighbours, layer half-thickness and estimate margins
+    // included, so that a comparison of the ESTIMATED r with them is safe
+    const float4* table;
 };
+
+constexpr int kCmemTableBins = 512;
 
 // Sample-independent CMEM terms, with the host libm the reference itself calls.
 inline CmemDev make_cmem_dev(const birp_cmem_params& P) {
@@ -929,6 +937,7 @@ inline CmemDev make_cmem_dev(const birp_cmem_params& P) {
     D.p3ds = p3ds;
     D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
     D.q_nonpositive = (p2c <= 0.f) ? 1 : 0;
+    D.table = nullptr;
     return D;
 }
 
@@ -1249,16 +1258,69 @@ __device__ __forceinline__ float cmem_estimate_stage2(const CmemDev& D, CmemEsti
 
 // The filter: true with the sample in `value` when its region is certain; false when the full evaluation
 // (cmem_sample_v4) has to decide.
+// The emissivity of a sample whose REGION is known.  FASTVAL = false: the fp64-then-round evaluation of the default
+// path (bit for bit what the unfiltered evaluation returns).  FASTVAL = true (BIRP_CMEM_FAST, tolerance mode): fp32
+// with the hardware approximations, ~1e-6 relative -- the estimated r and cos(theta) the filter already holds are
+// all it needs: sin^2(theta) = 1 - cos^2(theta), x^y = 2^(y log2 x), and exp(-B (theta/2)^4) is 1 to within 1e-7
+// unless B is far from what CMEM::Init leaves there (src/Cmem.cpp:310: |b| * 1e-9).
+template <bool FASTVAL>
+__device__ __forceinline__ float cmem_outside_value(const CmemDev& D, float x, float y, float z, float r_est) {
+    if (!FASTVAL) return cmem_b2(D.P, vec_len3(x, y, z));
+    const float sd = r_est * 0.1f;
+    return __fdividef(D.P.A2, sd * sd * sd);
+}
+
+template <bool FASTVAL>
+__device__ __forceinline__ float cmem_sheath_value(const CmemDev& D, float x, float y, float z, float r_est, float q_t) {
+    if (!FASTVAL) {
+        const float r_exact = vec_len3(x, y, z);
+        const cm::Angle T = cm::angle_from_cosine((x != 0.f) ? __fdiv_rn(x, r_exact) : 1.f);
+        return cmem_b1(D.P, r_exact, T.a, (float)T.s);
+    }
+    const birp_cmem_params& P = D.P;
+    const float sin2 = (1.f - q_t) * (1.f + q_t);
+    const float pw = exp2f((-P.alpha - P.beta * sin2) * __log2f(r_est * 0.1f));
+    float e = 1.f;
+    if (fabsf(P.B) > 1e-8f) {  // (theta <= pi: B (theta/2)^4 <= 6.1 B)
+        const float h = 0.5f * est_acos(q_t);
+        e = __expf(-P.B * (h * h) * (h * h));
+    }
+    return P.A1 * e * pw;
+}
+
+// The filter: true with the sample in `value` when its region is certain; false when the full evaluation has to decide.
+template <bool FASTVAL>
 __device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
     float r, q_t, q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
+    // Stage 0: the region table.  Most samples lie far from both boundaries WHATEVER phi is; for those one 16-byte
+    // load decides the region, and neither radius is estimated at all.
+    if (D.table) {
+        int bin = (int)((q_t + 1.f) * (0.5f * kCmemTableBins));
+        bin = bin < 0 ? 0 : (bin > kCmemTableBins - 1 ? kCmemTableBins - 1 : bin);
+        const float4 tb = __ldg(D.table + bin);  // {mp_lo, mp_hi, bs_lo, bs_hi}; NaN-free by construction
+        if (r < tb.x) {
+            value = 0.f;
+            return true;
+        }
+        if (r > tb.y) {
+            if (r > tb.w) {
+                value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+                return true;
+            }
+            if (r < tb.z) {
+                value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
+                return true;
+            }
+        }
+    }
     CmemEstimate e = cmem_estimate_stage1(D, q_t, q_p);
     const float ht = BIRP_CMEM_HALF_THICKNESS;
     const float m_bs = BIRP_CMEM_MARGIN(e.bs);
     // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
     if (D.q_nonpositive && e.trusted && r > e.bs + ht + m_bs && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper)) {
         // certainly r > bs_hi and r > mp_hi: neither sheath nor a layer
-        value = cmem_b2(D.P, vec_len3(x, y, z));
+        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
         return true;
     }
     const float mp = cmem_estimate_stage2(D, e);
@@ -1269,13 +1331,11 @@ __device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float
     }
     const bool above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
     if (above_mp && r > e.bs + ht + m_bs) {                 // (parameter sets with q > 0)
-        value = cmem_b2(D.P, vec_len3(x, y, z));
+        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
         return true;
     }
     if (above_mp && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
-        const float r_exact = vec_len3(x, y, z);
-        const cm::Angle T = cm::angle_from_cosine((x != 0.f) ? __fdiv_rn(x, r_exact) : 1.f);
-        value = cmem_b1(D.P, r_exact, T.a, (float)T.s);
+        value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
         return true;
     }
     return false;
@@ -1283,14 +1343,24 @@ __device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float
 
 __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
     float value;
-    if (cmem_try_filter(D, x, y, z, value)) return value;
+    if (cmem_try_filter<false>(D, x, y, z, value)) return value;
     return cmem_sample_v4(D, x, y, z);
 }
 
-// CMEM evaluation mode: 0 fp32 libdevice calls, 1 CUDA fp64 library rounded once, 2 own fp64 blocks,
-// 3 (default) own fp64 blocks behind the region filter
+// BIRP_CMEM_FAST (opt-in, tolerance mode): the same region decisions from the table and the fp32 estimates, values in
+// fp32; a sample next to a boundary is evaluated with the fp32 math library (region decided by fp32 radii, which
+// agree with the reference's on all but about one sample in 10^4 crossings)
+__device__ __forceinline__ float cmem_sample_fast(const CmemDev& D, float x, float y, float z) {
+    float value;
+    if (cmem_try_filter<true>(D, x, y, z, value)) return value;
+    return cmem_sample<false>(D, x, y, z);
+}
+
+// CMEM evaluation mode: 0 fp32 libdevice calls for every sample (diagnostic), 1 CUDA fp64 library rounded once, 2 own fp64
+// blocks, 3 (default) own fp64 blocks behind the region table and filter, 4 (BIRP_CMEM_FAST) fp32 values behind them
 template <int MODE>
 __device__ __forceinline__ float cmem_sample_mode(const CmemDev& D, float x, float y, float z) {
+    if (MODE == 4) return cmem_sample_fast(D, x, y, z);
     if (MODE == 3) return cmem_sample_v5(D, x, y, z);
     if (MODE == 2) return cmem_sample_v4(D, x, y, z);
     return cmem_sample<MODE == 1>(D, x, y, z);

@@ -36,15 +36,19 @@ struct RenderGeom {
 cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames, const RenderGeom& g,
                                const float* d_dist, int flags, float* d_images,
                                unsigned long long* d_valid, int* d_status, cudaStream_t stream);
+// d_table: the region table of this parameter set on this device (launch_cmem_table), or nullptr
 cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame* d_frames,
                                const RenderGeom& g, const float* d_dist, int flags, float* d_images,
-                               unsigned long long* d_valid, cudaStream_t stream);
+                               unsigned long long* d_valid, cudaStream_t stream, const float4* d_table = nullptr);
+cudaError_t launch_cmem_table(const birp_cmem_params& params, float4* d_table, cudaStream_t stream);
+cudaError_t launch_cmem_table_selftest(const birp_cmem_params& params, const float4* d_table, long n,
+                                       unsigned long long* d_out2, cudaStream_t stream);
 cudaError_t launch_accumulate(const float* d_samples, long nrays, int nsamples, float ray_width, int flags,
                               float* d_image, cudaStream_t stream);
 cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n, int flags, float* d_out,
                                int* d_status, cudaStream_t stream);
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
-                               float* d_out, cudaStream_t stream);
+                               float* d_out, cudaStream_t stream, const float4* d_table = nullptr);
 
 // per-frame setup / orbit poses on the device (k = {a, e, sqrt(1-e^2), u[3], w[3]})
 cudaError_t launch_frame_setup(const float* d_poses, int n, float aim_x, float tan_half_x, float tan_half_y,

@@ -62,8 +62,9 @@ struct MarchArgs {
     double fast_step;
 };
 
-template <int MODE>  // 0 fp32 libdevice, 1 CUDA fp64 library, 2 own fp64 blocks, 3 + region filter (cmem_sample_mode)
+template <int MODE>  // 0 fp32 libdevice, 1 CUDA fp64 library, 2 own fp64 blocks, 3 + table and filter, 4 fast (cmem_sample_mode)
 struct CmemField {
+    static constexpr bool kScaleOnce = true;
     CmemDev D;
     __device__ __forceinline__ float operator()(float x, float y, float z, bool&) const {
         return cmem_sample_mode<MODE>(D, x, y, z);
@@ -98,6 +99,9 @@ __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int
 }
 
 // Generic march: any Field functor (used for CMEM; the DataCube path has its own kernel below).
+// Field::kScaleOnce: the raw samples are summed in fp32 and the scale of src/Camera.cpp:201 is applied to the sum (the
+// analytic field is a tolerance path -- its transcendentals are not glibc's -- so the order of the roundings is free;
+// a ray still ends at its first negative sample, whose sign is that of its scaled value for the positive ray width).
 template <class Field>
 __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a, const Field field) {
     int f, i, j;
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
     pixel_direction(fr, i, j, (float)a.W, (float)a.H, dx, dy, dz);
 
     float* pix = a.images + ((size_t)(a.out_offset + f * a.out_stride) * a.H + j) * a.W + i;
-    float acc = a.accumulate ? *pix : 0.f;
+    float acc = (a.accumulate && !Field::kScaleOnce) ? *pix : 0.f;
     bool nan_index = false;
     unsigned nvalid = 0;
     const float ray_width = a.ray_width;
@@ -118,10 +122,14 @@ __global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a,
         const float y = __fadd_rn(__fmul_rn(dy, tk), fr.pos[1]);
         const float z = __fadd_rn(__fmul_rn(dz, tk), fr.pos[2]);
         float s = field(x, y, z, nan_index);
-        s = scale_sample(s, ray_width);
+        if (!Field::kScaleOnce) s = scale_sample(s, ray_width);
         if (s < 0.f) break;  // src/Camera.cpp:207-210: the rest of the ray is ignored
         acc = __fadd_rn(acc, s);
         ++nvalid;
+    }
+    if (Field::kScaleOnce) {
+        const float total = __double2float_rn(__dmul_rn((double)__fmul_rn(acc, ray_width), a.scale_k));
+        acc = a.accumulate ? __fadd_rn(*pix, total) : total;
     }
     *pix = acc;
     if (nan_index && a.status) atomicOr(a.status, kStatusNanIndex);
@@ -869,6 +877,114 @@ __global__ void __launch_bounds__(256) cmem_filter_selftest_kernel(const CmemDev
     atomicAdd(out + 2, 1ull);
 }
 
+
+// ---- CMEM region table (CmemDev::table) ---------------------------------------------------------------------
+// One block per bin of cos(theta).  The block evaluates the EXACT radii (cmem_radii_v4, what the march itself would
+// compute) on a dense grid of directions -- 25 values of cos(theta) across the bin and its two neighbours (a sample's
+// estimated cosine may land it in the bin next door) x 2049 values of phi in [0, pi] (the field is mirror-symmetric
+// in z) -- and keeps the extremes, widened by twice the largest difference between neighbouring grid points (what the
+// grid can miss between its points), by the layers' half thickness and by the margin the fp32 estimates of the
+// filter are allowed (the table is compared with the ESTIMATED r).  A bin in which a radius is not finite decides
+// nothing.  Whether the table ever disagrees with the exact evaluation is checked on millions of random positions
+// before it is used (cmem_table_selftest_kernel) and on 10^8 in the tests.
+__global__ void __launch_bounds__(256) cmem_table_kernel(const CmemDev D, float4* __restrict__ table) {
+    constexpr int NT = 24, NP = 2048, PER = NP / 256;  // thread t: phi samples t * PER .. t * PER + PER (one shared with t + 1)
+    const int bin = blockIdx.x;
+    const float w = 2.f / kCmemTableBins;
+    const float q_lo = fmaxf(-1.f, -1.f + (float)(bin - 1) * w), q_hi = fminf(1.f, -1.f + (float)(bin + 2) * w);
+    float mn[2] = {CUDART_INF_F, CUDART_INF_F}, mx[2] = {-CUDART_INF_F, -CUDART_INF_F}, dif[2] = {0.f, 0.f};
+    bool bad = false;
+    float prev_row[2][PER + 1];
+    for (int it = 0; it <= NT; ++it) {
+        const float q_t = q_lo + (q_hi - q_lo) * ((float)it / (float)NT);
+        float prev[2] = {0.f, 0.f};
+        for (int k = 0; k <= PER; ++k) {
+            const float phi = 3.14159265f * (float)(threadIdx.x * PER + k) / (float)NP;
+            const float q_p = fminf(1.f, fmaxf(-1.f, cosf(phi)));
+            float theta, sin_t, rad[2];
+            cmem_radii_v4(D, q_t, q_p, theta, sin_t, rad[0], rad[1]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const float v = rad[a];
+                if (!(fabsf(v) < CUDART_INF_F)) bad = true;
+                mn[a] = fminf(mn[a], v);
+                mx[a] = fmaxf(mx[a], v);
+                if (k > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev[a]));
+                if (it > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev_row[a][k]));
+                prev[a] = v;
+                prev_row[a][k] = v;
+            }
+        }
+    }
+    __shared__ float s_mn[2][8], s_mx[2][8], s_dif[2][8];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (bad) atomicOr(&s_bad, 1);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        float lo = mn[a], hi = mx[a], d = dif[a];
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+        }
+        if ((threadIdx.x & 31) == 0) s_mn[a][threadIdx.x >> 5] = lo, s_mx[a][threadIdx.x >> 5] = hi, s_dif[a][threadIdx.x >> 5] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float out[4];
+        for (int a = 0; a < 2; ++a) {
+            float lo = s_mn[a][0], hi = s_mx[a][0], d = s_dif[a][0];
+            for (int k = 1; k < 8; ++k) lo = fminf(lo, s_mn[a][k]), hi = fmaxf(hi, s_mx[a][k]), d = fmaxf(d, s_dif[a][k]);
+            const float slack = 2.f * d + 1e-4f * fabsf(hi);
+            out[2 * a] = lo - slack - BIRP_CMEM_HALF_THICKNESS - BIRP_CMEM_MARGIN(lo);
+            out[2 * a + 1] = hi + slack + BIRP_CMEM_HALF_THICKNESS + BIRP_CMEM_MARGIN(hi);
+        }
+        const bool usable = !s_bad && out[0] == out[0] && out[1] == out[1] && out[2] == out[2] && out[3] == out[3];
+        table[bin] = usable ? make_float4(out[0], out[1], out[2], out[3])
+                            : make_float4(-CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F);
+    }
+}
+
+// the march's sampler with the table (mode 3 with D.table) against the unfiltered evaluation (mode 2) on n pseudo-random
+// positions (the generator of cmem_filter_selftest_kernel): out[0] = samples that differ bitwise (must be 0),
+// out[1] = samples the table decided
+__global__ void __launch_bounds__(256) cmem_table_selftest_kernel(const CmemDev D, long n, unsigned long long* out) {
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    unsigned h = (unsigned)t * 2654435761u + 777u;
+    auto next01 = [&]() {
+        h ^= h >> 16;
+        h *= 0x85ebca6bu;
+        h ^= h >> 13;
+        h *= 0xc2b2ae35u;
+        h ^= h >> 16;
+        return (float)h * (1.0f / 4294967296.0f);
+    };
+    float x = (next01() - 0.5f) * 70.f, y = (next01() - 0.5f) * 70.f, z = (next01() - 0.5f) * 70.f;
+    const unsigned pick = h & 15u;
+    const float tiny = exp2f(-20.f * next01());
+    if (pick == 0) y *= tiny;
+    if (pick == 1) z *= tiny;
+    if (pick == 2) x *= tiny;
+    if (pick == 3) y *= tiny, z *= tiny;
+    if (pick == 4) x = -fabsf(x), y *= 0.2f * tiny, z *= 0.2f * tiny;
+    if (pick == 5) {  // on a ray through the origin region, at a radius near the table's bounds: scale towards 8 .. 16 RE
+        const float s = (8.f + 8.f * next01()) * rsqrtf(x * x + y * y + z * z);
+        x *= s, y *= s, z *= s;
+    }
+    const float a = cmem_sample_v5(D, x, y, z);
+    const float b = cmem_sample_v4(D, x, y, z);
+    if (__float_as_uint(a) != __float_as_uint(b)) atomicAdd(out + 0, 1ull);
+    float r, q_t, q_p;
+    cmem_cosines_estimate(x, y, z, r, q_t, q_p);
+    int bin = (int)((q_t + 1.f) * (0.5f * kCmemTableBins));
+    bin = bin < 0 ? 0 : (bin > kCmemTableBins - 1 ? kCmemTableBins - 1 : bin);
+    const float4 tb = D.table[bin];
+    if (r < tb.x || (r > tb.y && (r > tb.w || r < tb.z))) atomicAdd(out + 1, 1ull);
+}
+
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -1011,10 +1127,30 @@ cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2
     return cudaGetLastError();
 }
 
+cudaError_t launch_cmem_table(const birp_cmem_params& params, float4* d_table, cudaStream_t stream) {
+    cmem_table_kernel<<<kCmemTableBins, 256, 0, stream>>>(make_cmem_dev(params), d_table);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cmem_table_selftest(const birp_cmem_params& params, const float4* d_table, long n,
+                                       unsigned long long* d_out2, cudaStream_t stream) {
+    CmemDev D = make_cmem_dev(params);
+    D.table = d_table;
+    cmem_table_selftest_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(D, n, d_out2);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame* d_frames,
                                const RenderGeom& g, const float* d_dist, int flags, float* d_images,
-                               unsigned long long* d_valid, cudaStream_t stream) {
-    if (flags & BIRP_CMEM_FAST) {
+                               unsigned long long* d_valid, cudaStream_t stream, const float4* d_table) {
+    if (flags & BIRP_CMEM_FAST) {  // tolerance mode: fp32 values behind the table and the filter
+        CmemField<4> f{make_cmem_dev(params)};
+        f.D.table = (flags & BIRP_CMEM_NO_TABLE) ? nullptr : d_table;
+        return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
+    }
+    if (flags & BIRP_CMEM_LIBM32) {  // diagnostic: the fp32 math library for every sample, no filter
         CmemField<0> f{make_cmem_dev(params)};
         return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
     }
@@ -1027,6 +1163,7 @@ cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame*
         return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
     }
     CmemField<3> f{make_cmem_dev(params)};
+    f.D.table = (flags & BIRP_CMEM_NO_TABLE) ? nullptr : d_table;
     return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
 }
 
@@ -1087,10 +1224,13 @@ cudaError_t launch_sample_cube(const CubeView& cube, const float* d_xyz, long n,
 }
 
 cudaError_t launch_sample_cmem(const birp_cmem_params& params, const float* d_xyz, long n, int flags,
-                               float* d_out, cudaStream_t stream) {
+                               float* d_out, cudaStream_t stream, const float4* d_table) {
     if (n <= 0) return cudaSuccess;
-    const CmemDev D = make_cmem_dev(params);
+    CmemDev D = make_cmem_dev(params);
+    D.table = (flags & BIRP_CMEM_NO_TABLE) ? nullptr : d_table;
     if (flags & BIRP_CMEM_FAST)
+        sample_cmem_kernel<4><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
+    else if (flags & BIRP_CMEM_LIBM32)
         sample_cmem_kernel<0><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);
     else if (flags & BIRP_CMEM_LIBM64)
         sample_cmem_kernel<1><<<blocks_for(n, 256), 256, 0, stream>>>(D, d_xyz, n, d_out);

@@ -105,6 +105,11 @@ public:
 
     // ---- additions (not in the reference) -----------------------------------------------
     bool IsTrilinear() const { return trilinear; }
+    // Tolerance mode of the trilinear march (BIRP_FAST_MARCH): sample values with fused arithmetic, ~1e-6 relative per
+    // pixel against the reference instead of bit-identical images, 1.5x - 1.9x the frame rate; where rays end stays
+    // exact.  Off by default.
+    void SetFastMarch(bool on) { fast_march = on; }
+    bool FastMarch() const { return fast_march; }
     // Load with an explicit number of text -> float worker threads (0 = choose: up to 16, or BIRP_LOAD_THREADS);
     // callers that load several cubes at once (RenderBatchDirectory) divide the cores among them.
     void LoadParallel(const std::string& filename, bool debug, int nthreads);
@@ -142,6 +147,7 @@ private:
     bool TryLoadCache(const std::string& filename, long long src_size, long long src_mtime_ns);
     void WriteCache(const std::string& filename, long long src_size, long long src_mtime_ns) const;
     bool trilinear = false;  // the reference leaves this uninitialised until SetTrilinear
+    bool fast_march = false;
     birp_cube* device_cube = nullptr;
     std::vector<birp_cube*> replicas;  // ResidentOn: copies on other devices
     // the grid as Load() parsed it: flat[(z * ny + y) * nx + x]; valid until somebody touches `slices`

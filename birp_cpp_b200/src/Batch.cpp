@@ -154,7 +154,7 @@ std::vector<float> RenderSweep(Space& space, const std::vector<float>& positions
     if (devices <= 0) devices = BirpDeviceCount();
     if (n < 64 * devices) devices = 1;  // too few frames to be worth a second GPU
     if (auto* cube = dynamic_cast<DataCube*>(&space)) {
-        const int flags = cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST;
+        const int flags = (cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST) | (cube->FastMarch() ? BIRP_FAST_MARCH : 0);
         if (devices > 1) {
             std::vector<const birp_cube*> cubes(devices);
             for (int d = 0; d < devices; ++d) cubes[d] = cube->ResidentOn(d);

@@ -126,7 +126,7 @@ void Camera::Render() {
     const int acc = nonzero ? BIRP_ACCUMULATE : 0;
 
     if (DataCube* cube = dynamic_cast<DataCube*>(dataCube)) {
-        const int flags = (cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST) | acc;
+        const int flags = (cube->IsTrilinear() ? BIRP_TRILINEAR : BIRP_NEAREST) | (cube->FastMarch() ? BIRP_FAST_MARCH : 0) | acc;
         rc = birp_render_cube(cube->Resident(), &frame, 1, W, H, 0, H, ray_samples, ray_max_distance, flags,
                               flat.data());
         if (rc != BIRP_OK) raise(rc, "Camera::Render(DataCube)");

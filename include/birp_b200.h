@@ -51,8 +51,12 @@ enum {
     BIRP_ACCUMULATE = 2,     /* start each pixel from the value already in `images`
                                 (the reference never clears Camera::image, src/Camera.cpp:223);
                                 without it pixels start from 0 and `images` is overwritten */
-    BIRP_CMEM_FAST = 4,      /* CMEM only: evaluate the transcendental calls in fp32 libdevice
-                                instead of fp64-then-round */
+    BIRP_CMEM_FAST = 4,      /* CMEM only, opt-in: tolerance mode.  The region of a sample is decided like in the default
+                                path (region table, fp32 radius estimates with margins); its VALUE is computed in fp32
+                                with the hardware approximations (~1e-6 relative) instead of fp64-then-round, and a
+                                sample next to a boundary goes through the fp32 math library.  >= 99.9 % of pixels
+                                within 1e-5 of the reference; the default path reproduces the reference's samples bit
+                                for bit in 99 % of the cases */
     /* diagnostics: force the slower, equally exact kernel variants (see DESIGN.md "variants") */
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
@@ -80,6 +84,12 @@ enum {
                                    [2^-120, 2^120) computes the cell index in fp32 and drops the range / midpoint tests of the
                                    scale shortcut, which that range makes redundant (identical results, four instructions
                                    fewer per sample, measured +1.9 %); this flag keeps the general loop as the cross-check */
+    BIRP_CMEM_LIBM32 = 262144,   /* CMEM only, diagnostic: the CUDA fp32 math library for every sample, no table, no filter
+                                    (round 1's BIRP_CMEM_FAST; slower than the default) */
+    BIRP_CMEM_NO_TABLE = 131072, /* CMEM only: do not use the region table of the parameter set (per bin of cos(theta), bounds
+                                    of both radii over every phi: a sample far from both boundaries is classified by one
+                                    16-byte load instead of the fp32 radius estimates); identical results, kept as the
+                                    cross-check */
     BIRP_FAST_MARCH = 32768,    /* DataCube, trilinear, opt-in: tolerance mode.  The default march is bit-identical to the
                                    reference Camera; with this flag the VALUE of an in-bounds sample is computed with fused
                                    arithmetic (one FFMA per coordinate, the cell's interpolant as a polynomial from one
@@ -311,6 +321,12 @@ int birp_selftest_cmem_math(long n, double max_err[6]);
    the fp32 estimate of the magnetopause / bow-shock radius was off by, over n pseudo-random sample positions
    (must stay far below 1), out[2] = fraction of the positions whose direction the filter trusts */
 int birp_selftest_cmem_filter(const birp_cmem_params* params, long n, double out[3]);
+
+/* diagnostics of the CMEM region table of a parameter set (built at first use on the calling thread's device): the
+   march's sampler with the table against the unfiltered evaluation on n pseudo-random positions; out[0] = samples that
+   differ bitwise (must be 0), out[1] = fraction of the positions the table decided, out[2] = 1 when the table is in use
+   (0: it failed its self-test at first use, or BIRP_DISABLE_CMEM_TABLE is set) */
+int birp_selftest_cmem_table(const birp_cmem_params* params, long n, double out[3]);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long birp_launch_count(void);

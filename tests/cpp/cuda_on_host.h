@@ -75,6 +75,7 @@ static inline int atomicOr(int* p, int v) {
 #define __expf expf
 #define __log2f log2f
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+static inline float __fdividef(float a, float b) { return a / b; }
 
 // provided by the harness (device_on_host.cpp): the staged ray table at a byte offset, and the texture gather
 float birp_host_table_entry(unsigned sdist);

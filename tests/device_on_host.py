@@ -37,6 +37,8 @@ def lib():
         L.doh_scale_exhaustive.argtypes = [C.c_int, C.c_uint, C.c_int, _vp]
         L.doh_sample_cmem.argtypes = [_vp, _vp, C.c_long, C.c_int, _vp]
         L.doh_cmem_filter_decides.argtypes = [_vp, _vp, C.c_long, _vp]
+        L.doh_cmem_table.argtypes = [_vp, _vp]
+        L.doh_sample_cmem_table.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp]
         L.doh_render_cmem.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
         _lib = L
     return _lib
@@ -167,6 +169,25 @@ def cmem_filter_decides(params, xyz):
     params = np.ascontiguousarray(params)
     lib().doh_cmem_filter_decides(_p(params), _p(xyz), len(xyz), _p(out))
     return out.astype(bool)
+
+
+def cmem_table(params):
+    """the region table of a parameter set (cmem_table_kernel restated on the host): (bins, 4) floats"""
+    params = np.ascontiguousarray(params)
+    out = np.zeros((512, 4), np.float32)
+    lib().doh_cmem_table(_p(params), _p(out))
+    return out
+
+
+def sample_cmem_table(params, table, xyz):
+    """(CMEM samples with the region table in front of the filter, which samples the table decided)"""
+    xyz = _f32(xyz).reshape(-1, 3)
+    params = np.ascontiguousarray(params)
+    table = np.ascontiguousarray(table, dtype=np.float32)
+    out = np.zeros(len(xyz), np.float32)
+    dec = np.zeros(len(xyz), np.uint8)
+    lib().doh_sample_cmem_table(_p(params), _p(table), _p(xyz), len(xyz), _p(out), _p(dec))
+    return out, dec.astype(bool)
 
 
 def render_cmem(params, frames, W, H, mode=3, nsamples=200, maxdist=44):

@@ -491,3 +491,37 @@ def test_marked_oct_records_march_equals_oracle(kind):
         assert st == 0 and gvalid == wvalid
         assert_bit_exact(got, want, f"{kind}, n={nsamples}")
     c.free()
+
+
+# ------------------------------------------------------------------ CMEM region table and tolerance mode
+@pytest.mark.parametrize("kw", [{}, O.CMEM_CLI, dict(dipole=0.5, p0=2.0, bs=20.0, A1=1e-5, ay_bs=1.5, az_bs=0.4)])
+def test_cmem_region_table_on_host_is_invisible(kw):
+    """the region table (cmem_table_kernel, restated for the host over the same grid of directions) in front of the
+    filter: nine samples in ten are decided by one table entry, and every sample equals the unfiltered evaluation bit
+    for bit -- random positions and rays sampled every 0.04 RE across both boundaries"""
+    P = capi.cmem_init(**kw)
+    tab = D.cmem_table(P)
+    assert tab.shape == (512, 4) and not np.isnan(tab).any()
+    assert np.isfinite(tab).all(axis=1).mean() > 0.9  # (the bins next to the -x axis decide nothing)
+    rng = np.random.default_rng(5)
+    pts = [rng.uniform(-35, 35, size=(300000, 3))]
+    d = rng.normal(size=(300, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:30, 2] *= 1e-4
+    t = np.linspace(2.0, 40.0, 1000)
+    pts.append((d[:, None, :] * t[None, :, None]).reshape(-1, 3))
+    pts = np.concatenate(pts).astype(np.float32)
+    got, decided = D.sample_cmem_table(P, tab, pts)
+    assert_bit_exact(got, D.sample_cmem(P, pts, mode=2), "the table changed a sample")
+    assert decided.mean() > 0.8
+
+
+def test_cmem_fast_mode_on_host_within_tolerance():
+    """BIRP_CMEM_FAST (fp32 values behind the same region decisions) against the oracle: SURVEY 8(d) tolerance at 99.9 %"""
+    poses = S.orbit_poses(10000)[::1250]
+    P = capi.cmem_init()
+    fp, fo = frames_pair(poses, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    want = O.orc_render_cmem(O.orc_cmem_init(), fo, W, H)
+    got = D.render_cmem(P, fp, W, H, mode=4)
+    for g, w in zip(got, want):
+        assert assert_image_parity(g, w, "cmem fast", min_fraction=0.999) >= 0.999

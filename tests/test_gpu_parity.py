@@ -795,23 +795,36 @@ def test_cmem_filter_is_invisible(gpu, kw):
     pts = np.concatenate(pts).astype(np.float32)
     a = capi.sample_cmem(P, pts)
     b = capi.sample_cmem(P, pts, fast="nofilter")
-    assert_bit_exact(a, b, "region filter changed a sample")
+    assert_bit_exact(a, b, "region table / filter changed a sample")
+    assert_bit_exact(capi.sample_cmem(P, pts, fast="notable"), b, "region filter (without the table) changed a sample")
 
 
-@pytest.mark.parametrize("fast", [False, True, "libm64"])
+@pytest.mark.parametrize("kw", CMEM_KW + [dict(dipole=0.5, p0=2.0, bs=20.0, A1=1e-5, ay_bs=1.5, az_bs=0.4),
+                                          dict(dipole=-0.4, p3=1, bs=6.0, alpha=0.5, beta=3.0)])
+def test_cmem_region_table_never_disagrees(gpu, kw):
+    """the region table (per bin of cos(theta): bounds of both radii over every phi) decides nine samples in ten with
+    one 16-byte load -- and never differently from the exact evaluation: 10^8 pseudo-random positions"""
+    out = capi.selftest_cmem_table(capi.cmem_init(**kw), 100_000_000)
+    print(out)
+    assert out["differing_samples"] == 0
+    if out["table_in_use"]:
+        assert out["decided_fraction"] > 0.5
+
+
+@pytest.mark.parametrize("fast", [False, True, "libm64", "libm32"])
 @pytest.mark.parametrize("kw,answers", [({}, KA_DEFAULT), (O.CMEM_TEST2, KA_TEST2)])
 def test_cmem_known_answers_on_device(gpu, kw, answers, fast):
     """the reference's own CMEM tests (tests/CMEM_test.cpp), evaluated by the device sampler"""
     P = capi.cmem_init(**kw)
     got = capi.sample_cmem(P, [p for p, _ in answers], fast=fast)
     want = np.array([v for _, v in answers], np.float32)
-    np.testing.assert_allclose(got, want, rtol=(2e-6 if fast is True else 3e-7), atol=0)
+    np.testing.assert_allclose(got, want, rtol=(3e-6 if fast in (True, "libm32") else 3e-7), atol=0)
     assert got[3] == got[4] == got[5]  # mirror symmetry in y and z
-    if fast is not True:
+    if fast not in (True, "libm32"):
         assert_bit_exact(got, want, "precise mode reproduces the known answers bitwise")
 
 
-@pytest.mark.parametrize("fast", [False, True, "libm64"])
+@pytest.mark.parametrize("fast", [False, True, "libm64", "libm32"])
 @pytest.mark.parametrize("kw", [{}, O.CMEM_CLI, O.CMEM_TEST2, dict(dipole=0.2, b=(1, -2, -6), v=(450, 10, -20))])
 def test_cmem_samples_vs_oracle(gpu, kw, fast):
     P = capi.cmem_init(**kw)
@@ -824,7 +837,7 @@ def test_cmem_samples_vs_oracle(gpu, kw, fast):
     rel[(got == 0) & (want == 0)] = 0
     # region flips at the layer boundaries change a sample discontinuously; they must be rare
     assert np.mean(rel <= 1e-5) > 0.9995, np.mean(rel <= 1e-5)
-    if fast is not True:
+    if fast not in (True, "libm32"):
         assert np.mean(got.view(np.uint32) == want.view(np.uint32)) > 0.90
     if fast is False:
         assert_bit_exact(got, capi.sample_cmem(P, pts, fast="nofilter"), "region filter changed a sample")
@@ -835,7 +848,7 @@ def test_cmem_samples_vs_oracle(gpu, kw, fast):
         assert same > 0.9999
 
 
-@pytest.mark.parametrize("fast", [False, True, "libm64"])
+@pytest.mark.parametrize("fast", [False, True, "libm64", "libm32"])
 @pytest.mark.parametrize("name,kw", [("default", {}), ("cli", O.CMEM_CLI), ("test2", O.CMEM_TEST2)])
 def test_cmem_render_vs_oracle_and_golden(gpu, golden, name, kw, fast):
     P = capi.cmem_init(**kw)

@@ -31,11 +31,12 @@ for grid in (zyx, zyx0):
     got = capi.render_sweep(c, poses, S.DEFAULT_AIM_X, 27., 16., W, H)
     c.free()
 P = capi.cmem_init()
-for mode in (False, True, "libm64", "nofilter"):
+for mode in (False, True, "libm64", "nofilter", "notable", "libm32"):
     capi.render_cmem(P, fp, W, H, fast=mode)
     capi.sample_cmem(P, np.random.rand(1000, 3) * 20 - 10, fast=mode)
 capi.selftest_cmem_math(1 << 12)
 capi.selftest_cmem_filter(P, 1 << 12)
+capi.selftest_cmem_table(P, 1 << 12)
 capi.accumulate(np.random.rand(500, 200).astype(np.float32), 0.22)
 capi.ray_directions(fp[:1], W, H)
 try:
