@@ -53,15 +53,9 @@ EXTRA_FLAGS = 0
 
 
 def cmem_mode():
-    """--extra-flags -> the `fast` argument of the capi CMEM calls (False = default: own fp64 blocks + region filter)"""
-    from birp_cpp_b200 import capi
-    if EXTRA_FLAGS & capi.CMEM_FAST:
-        return True
-    if EXTRA_FLAGS & capi.CMEM_LIBM64:
-        return "libm64"
-    if EXTRA_FLAGS & capi.CMEM_NO_FILTER:
-        return "nofilter"
-    return False
+    """--extra-flags -> the `fast` argument of the capi CMEM calls (False = default: own fp64 blocks behind the region
+    table and filter; otherwise the raw BIRP_CMEM_* flags)"""
+    return int(EXTRA_FLAGS) if EXTRA_FLAGS else False
 
 WORKLOADS = {
     # name: (description, cube n, W, H, fov_w, fov_h, nsamples, frames, field)
@@ -167,7 +161,7 @@ def issue_roofline(entry, live_samples, kernel_ms, sm_mhz):
 def kernel_name(field, trilinear, extra_flags):
     from birp_cpp_b200 import capi
     if field != "cube":
-        return "march_kernel<CmemField>"
+        return "march_kernel<CmemField, tolerance mode>" if (extra_flags & capi.CMEM_FAST) else "march_kernel<CmemField>"
     if not trilinear:
         return "march_cube_kernel<nearest>"
     return "march_cube_fast_kernel<trilinear>" if (extra_flags & capi.FAST_MARCH) else "march_cube_kernel<trilinear>"
@@ -838,12 +832,13 @@ def run_b200(args, wl, name):
                                             max(want.sum(dtype=np.float64), 1e-300)),
                       "against": "unmodified reference (oracle/_ref)" if nframes > 1 else "oracle restatement"}
             # the gate: DataCube path bit-exact (tolerance-mode kernels: SURVEY 8(d) tolerance at 99.9 %), CMEM 95 %
-            tolerance_mode = field == "cube" and (EXTRA_FLAGS & capi.FAST_MARCH)
+            tolerance_mode = (field == "cube" and (EXTRA_FLAGS & capi.FAST_MARCH)) or \
+                             (field == "cmem" and (EXTRA_FLAGS & capi.CMEM_FAST))
             if field == "cube" and not tolerance_mode:
                 if not parity["bit_exact"]:
                     failed.append("DataCube images are not bit-exact against the reference")
             else:
-                need = 0.999 if field == "cube" else 0.95
+                need = 0.999 if tolerance_mode else 0.95
                 if parity["pixels_within_1e-5"] < need:
                     failed.append(f"only {parity['pixels_within_1e-5']:.4%} of pixels within 1e-5 (need {need:.1%})")
                 if parity["flux_rel_err"] > 1e-4:

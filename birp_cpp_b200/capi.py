@@ -423,6 +423,8 @@ def _cmem_mode(fast) -> int:
     """fast: False = default (own fp64 blocks behind the region table and filter), True = tolerance mode (fp32 values
     behind the same decisions), "libm64" = CUDA fp64 library, "nofilter" = own fp64 blocks for every sample,
     "notable" = default without the region table, "libm32" = CUDA fp32 library for every sample"""
+    if isinstance(fast, int) and not isinstance(fast, bool):
+        return fast  # raw BIRP_CMEM_* flags
     if fast == "libm64":
         return CMEM_LIBM64
     if fast == "nofilter":

@@ -237,11 +237,11 @@ int cmem_flags(DeviceCtx* c, const birp_cmem_params& params, int flags, int* out
         int rc = run_cmem_filter_selftest(c, params, 1L << 22, u);
         if (rc) return rc;
         st.filter_ok = u[0] <= 0.25 && u[1] <= 0.25;  // (NaNs compare false: no filter)
-        // The region table of this parameter set: built once (512 bins x 25 x 2049 exact evaluations, a few ms), then
+        // The region table of this parameter set: built once (256 x 64 cells x 169 exact evaluations, a few ms), then
         // the march with it is compared with the unfiltered evaluation on 4M pseudo-random positions; a single
         // differing sample and the table is dropped for this set.
         if (st.filter_ok && !getenv("BIRP_DISABLE_CMEM_TABLE")) {
-            cudaError_t e = cudaMalloc(&st.d_table, sizeof(float4) * birp::kCmemTableBins);
+            cudaError_t e = cudaMalloc(&st.d_table, sizeof(float4) * birp::kCmemTableT * birp::kCmemTableP);
             if (e == cudaSuccess) e = birp::launch_cmem_table(params, st.d_table, c->compute);
             unsigned long long h[2] = {1, 0};
             const long n = 1L << 22;
@@ -434,34 +434,46 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
                                             sizeof(float) * band_px, (size_t)nf, cudaMemcpyHostToDevice, cs));
             }
         }
-        birp::RenderGeom g{nf, W, H, row_begin, row_end, nsamples, table.ray_width};
-        g.monotone_table = table.monotone;
-        g.tile_w_log2 = c->tile_w_log2;
-        g.fast_variant = c->fast_variant;
-        g.tile_swizzle = c->tile_swizzle;
-        g.fast_kstep = c->fast_kstep;
-        g.fast_coop = c->fast_coop;
-        g.fast_step = table.step;
-        g.row_band = plan.row_band, g.row_phase = plan.row_phase, g.row_nphases = plan.row_nphases;
-        cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, cs);
-        if (e != cudaSuccess)
-            return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-        BIRP_CUDA(cudaEventRecord(c->rendered[b], cs));
-        BIRP_CUDA(cudaStreamWaitEvent(c->copy, c->rendered[b], 0));
-        if (interleaved) {
-            rc = copy_interleaved(false, d_img, h_first, h_pitch, nf, c->copy);
-            if (rc) return rc;
-        } else if (full_rows) {
-            if (plan.out_stride == 1) {
-                BIRP_CUDA(cudaMemcpyAsync(h_first, d_img, frame_bytes * nf, cudaMemcpyDeviceToHost, c->copy));
+        // A chunk of one or two LARGE frames (a 4096 x 4096 image is 64 MiB) is rendered and drained in row pieces:
+        // the copy of piece p overlaps the render of piece p + 1 instead of following the whole frame.
+        int npieces = 1;
+        if (!interleaved && nf <= 2 && band_px >= (size_t(4) << 20) && (row_end - row_begin) >= 64) npieces = 4;
+        for (int piece = 0; piece < npieces; ++piece) {
+            // piece boundaries on multiples of 8 rows (the warp's pixel tile is 4 x 8 or 8 x 4)
+            const int rows_all = row_end - row_begin;
+            const int r0 = row_begin + (int)(((long long)rows_all * piece / npieces) / 8 * 8);
+            const int r1 = (piece + 1 == npieces) ? row_end : row_begin + (int)(((long long)rows_all * (piece + 1) / npieces) / 8 * 8);
+            if (r1 <= r0) continue;
+            birp::RenderGeom g{nf, W, H, r0, r1, nsamples, table.ray_width};
+            g.monotone_table = table.monotone;
+            g.tile_w_log2 = c->tile_w_log2;
+            g.fast_variant = c->fast_variant;
+            g.tile_swizzle = c->tile_swizzle;
+            g.fast_kstep = c->fast_kstep;
+            g.fast_coop = c->fast_coop;
+            g.fast_step = table.step;
+            g.row_band = plan.row_band, g.row_phase = plan.row_phase, g.row_nphases = plan.row_nphases;
+            cudaError_t e = launch(c->d_frames + f0, g, table.d_dist, d_img, cs);
+            if (e != cudaSuccess)
+                return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+            BIRP_CUDA(cudaEventRecord(c->rendered[b], cs));
+            BIRP_CUDA(cudaStreamWaitEvent(c->copy, c->rendered[b], 0));
+            const size_t p_off = (size_t)W * r0, p_px = (size_t)W * (r1 - r0);
+            if (interleaved) {
+                rc = copy_interleaved(false, d_img, h_first, h_pitch, nf, c->copy);
+                if (rc) return rc;
+            } else if (r0 == 0 && r1 == H) {
+                if (plan.out_stride == 1) {
+                    BIRP_CUDA(cudaMemcpyAsync(h_first, d_img, frame_bytes * nf, cudaMemcpyDeviceToHost, c->copy));
+                } else {
+                    BIRP_CUDA(cudaMemcpy2DAsync(h_first, h_pitch, d_img, frame_bytes, frame_bytes, (size_t)nf,
+                                                cudaMemcpyDeviceToHost, c->copy));
+                }
             } else {
-                BIRP_CUDA(cudaMemcpy2DAsync(h_first, h_pitch, d_img, frame_bytes, frame_bytes, (size_t)nf,
-                                            cudaMemcpyDeviceToHost, c->copy));
+                // the rows of this piece / band in every frame: rows of p_px floats, one per frame
+                BIRP_CUDA(cudaMemcpy2DAsync(h_first + p_off, h_pitch, d_img + p_off, frame_bytes, sizeof(float) * p_px,
+                                            (size_t)nf, cudaMemcpyDeviceToHost, c->copy));
             }
-        } else {
-            // the band of every frame: rows of band_px floats, one per frame
-            BIRP_CUDA(cudaMemcpy2DAsync(h_first + band_off, h_pitch, d_img + band_off, frame_bytes,
-                                        sizeof(float) * band_px, (size_t)nf, cudaMemcpyDeviceToHost, c->copy));
         }
         BIRP_CUDA(cudaEventRecord(c->drained[b], c->copy));
     }

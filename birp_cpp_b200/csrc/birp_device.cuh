@@ -912,15 +912,25 @@ struct CmemDev {
     float p3dn, p3ds;                      // p3 * dn, p3 * ds       (:217)
     int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
     int q_nonpositive;                     // p2 * charlie <= 0: the cusp term of LinScaled can only lower the radius
-    // Region table of this parameter set (cmem_table_kernel; nullptr: none): kCmemTableBins bins over cos(theta) in
-    // [-1, 1], each {mp_lo, mp_hi, bs_lo, bs_hi}: whatever phi, a sample of that bin with r < mp_lo is inside the
-    // magnetopause layer, with r > mp_hi outside it, with r < bs_lo inside the bow-shock layer, with r > bs_hi beyond
-    // it -- bounds over every direction of the bin and its two neighbours, layer half-thickness and estimate margins
-    // included, so that a comparison of the ESTIMATED r with them is safe
+    // Region table of this parameter set (cmem_table_cell; nullptr: none): kCmemTableT bins over cos(theta) x
+    // kCmemTableP bins over cos(phi), each {mp_lo, mp_hi, bs_lo, bs_hi}: a sample whose direction falls into the cell
+    // and whose r is < mp_lo lies inside the magnetopause layer, with r > mp_hi outside it, with r < bs_lo inside the
+    // bow-shock layer, with r > bs_hi beyond it -- bounds over the cell and its eight neighbours, layer half-thickness
+    // and estimate margins included, so that a comparison of the ESTIMATED r with them is safe.  A cell near which
+    // the fp32 estimates are not trusted (next to a cusp axis, where the Lin radius has a needle; next to the -x
+    // axis) bounds nothing.
     const float4* table;
 };
 
-constexpr int kCmemTableBins = 512;
+constexpr int kCmemTableT = 256, kCmemTableP = 64;
+
+__device__ __forceinline__ int cmem_table_index(float q_t, float q_p) {
+    int bt = (int)((q_t + 1.f) * (0.5f * kCmemTableT));
+    int bp = (int)((q_p + 1.f) * (0.5f * kCmemTableP));
+    bt = bt < 0 ? 0 : (bt > kCmemTableT - 1 ? kCmemTableT - 1 : bt);
+    bp = bp < 0 ? 0 : (bp > kCmemTableP - 1 ? kCmemTableP - 1 : bp);
+    return bt * kCmemTableP + bp;
+}
 
 // Sample-independent CMEM terms, with the host libm the reference itself calls.
 inline CmemDev make_cmem_dev(const birp_cmem_params& P) {
@@ -1167,8 +1177,8 @@ __device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float
 // the cost.  Everything else -- within the margin of a boundary, directions where the estimate is
 // ill-conditioned (near the -x axis, near a cusp), NaNs -- takes the full evaluation.
 // ---------------------------------------------------------------------------------
-#define BIRP_CMEM_MARGIN_REL 5e-3f
-#define BIRP_CMEM_MARGIN_ABS 5e-3f
+#define BIRP_CMEM_MARGIN_REL 2e-3f
+#define BIRP_CMEM_MARGIN_ABS 2e-3f
 
 // hardware approximations for the estimate (MUFU.SQRT / MUFU.RCP, ~2^-22 relative)
 __device__ __forceinline__ float est_sqrt(float x) {
@@ -1293,12 +1303,10 @@ template <bool FASTVAL>
 __device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
     float r, q_t, q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
-    // Stage 0: the region table.  Most samples lie far from both boundaries WHATEVER phi is; for those one 16-byte
-    // load decides the region, and neither radius is estimated at all.
+    // Stage 0: the region table.  Most samples lie far from both boundaries of their direction's cell; for those one
+    // 16-byte load decides the region, and neither radius is estimated at all.
     if (D.table) {
-        int bin = (int)((q_t + 1.f) * (0.5f * kCmemTableBins));
-        bin = bin < 0 ? 0 : (bin > kCmemTableBins - 1 ? kCmemTableBins - 1 : bin);
-        const float4 tb = __ldg(D.table + bin);  // {mp_lo, mp_hi, bs_lo, bs_hi}; NaN-free by construction
+        const float4 tb = __ldg(D.table + cmem_table_index(q_t, q_p));  // {mp_lo, mp_hi, bs_lo, bs_hi}; never NaN
         if (r < tb.x) {
             value = 0.f;
             return true;
@@ -1354,6 +1362,59 @@ __device__ __forceinline__ float cmem_sample_fast(const CmemDev& D, float x, flo
     float value;
     if (cmem_try_filter<true>(D, x, y, z, value)) return value;
     return cmem_sample<false>(D, x, y, z);
+}
+
+// One cell of the region table (cmem_table_kernel; tests/cpp/device_on_host.cpp runs the same function on the host).
+// The EXACT radii (cmem_radii_v4, what the march itself computes) on a 13 x 13 grid of directions across the cell and
+// its eight neighbours (a sample's estimated cosines may land it next door), the extremes widened by twice the
+// largest difference between neighbouring grid points (what the grid can miss between its points) and a quarter of
+// their range, by the layers' half thickness and by the margin the filter allows its fp32 estimates (the table is
+// compared with the ESTIMATED r).  Where the fp32 estimates are not trusted the exact radius is not smooth either --
+// within 2 degrees of a cusp axis the Lin radius has a needle no grid resolves, towards the -x axis both radii blow
+// up -- so a cell with an untrusted grid point bounds nothing; nor does a cell with a non-finite radius.  The first
+// and the last row (directions along the x axis, where cos(phi) is ill-defined) hold the bounds of the whole row.
+__device__ __forceinline__ void cmem_table_cell(const CmemDev& D, int bt, int bp, float out[4]) {
+    constexpr int NS = 12;
+    const float wt = 2.f / kCmemTableT, wp = 2.f / kCmemTableP;
+    const bool polar = (bt == 0 || bt == kCmemTableT - 1);
+    const float t_lo = fmaxf(-1.f, -1.f + (float)(bt - 1) * wt), t_hi = fminf(1.f, -1.f + (float)(bt + 2) * wt);
+    const float p_lo = polar ? -1.f : fmaxf(-1.f, -1.f + (float)(bp - 1) * wp);
+    const float p_hi = polar ? 1.f : fminf(1.f, -1.f + (float)(bp + 2) * wp);
+    const int np = polar ? 16 * NS : NS;
+    float mn[2] = {CUDART_INF_F, CUDART_INF_F}, mx[2] = {-CUDART_INF_F, -CUDART_INF_F}, dif[2] = {0.f, 0.f};
+    bool usable[2] = {true, true};
+    float prev_row[2][16 * NS + 1];
+    for (int it = 0; it <= NS; ++it) {
+        const float q_t = t_lo + (t_hi - t_lo) * ((float)it / (float)NS);
+        float prev[2] = {0.f, 0.f};
+        for (int ip = 0; ip <= np; ++ip) {
+            const float q_p = p_lo + (p_hi - p_lo) * ((float)ip / (float)np);
+            float theta, sin_t, rad[2];
+            cmem_radii_v4(D, q_t, q_p, theta, sin_t, rad[0], rad[1]);
+            CmemEstimate e = cmem_estimate_stage1(D, q_t, q_p);
+            if (!e.trusted) usable[0] = usable[1] = false;
+            (void)cmem_estimate_stage2(D, e);
+            if (!e.trusted) usable[0] = false;  // (next to a cusp axis: only the magnetopause has the needle)
+            for (int a = 0; a < 2; ++a) {
+                const float v = rad[a];
+                if (!(fabsf(v) < CUDART_INF_F)) usable[a] = false;
+                mn[a] = fminf(mn[a], v);
+                mx[a] = fmaxf(mx[a], v);
+                if (ip > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev[a]));
+                if (it > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev_row[a][ip]));
+                prev[a] = v;
+                prev_row[a][ip] = v;
+            }
+        }
+    }
+    for (int a = 0; a < 2; ++a) {
+        const float slack = 2.f * dif[a] + 0.25f * (mx[a] - mn[a]) + 1e-4f * fabsf(mx[a]);
+        float lo = mn[a] - slack - BIRP_CMEM_HALF_THICKNESS - BIRP_CMEM_MARGIN(mn[a]);
+        float hi = mx[a] + slack + BIRP_CMEM_HALF_THICKNESS + BIRP_CMEM_MARGIN(mx[a]);
+        if (!usable[a] || !(lo == lo) || !(hi == hi)) lo = -CUDART_INF_F, hi = CUDART_INF_F;
+        out[2 * a] = lo;
+        out[2 * a + 1] = hi;
+    }
 }
 
 // CMEM evaluation mode: 0 fp32 libdevice calls for every sample (diagnostic), 1 CUDA fp64 library rounded once, 2 own fp64

@@ -878,73 +878,13 @@ __global__ void __launch_bounds__(256) cmem_filter_selftest_kernel(const CmemDev
 }
 
 
-// ---- CMEM region table (CmemDev::table) ---------------------------------------------------------------------
-// One block per bin of cos(theta).  The block evaluates the EXACT radii (cmem_radii_v4, what the march itself would
-// compute) on a dense grid of directions -- 25 values of cos(theta) across the bin and its two neighbours (a sample's
-// estimated cosine may land it in the bin next door) x 2049 values of phi in [0, pi] (the field is mirror-symmetric
-// in z) -- and keeps the extremes, widened by twice the largest difference between neighbouring grid points (what the
-// grid can miss between its points), by the layers' half thickness and by the margin the fp32 estimates of the
-// filter are allowed (the table is compared with the ESTIMATED r).  A bin in which a radius is not finite decides
-// nothing.  Whether the table ever disagrees with the exact evaluation is checked on millions of random positions
-// before it is used (cmem_table_selftest_kernel) and on 10^8 in the tests.
-__global__ void __launch_bounds__(256) cmem_table_kernel(const CmemDev D, float4* __restrict__ table) {
-    constexpr int NT = 24, NP = 2048, PER = NP / 256;  // thread t: phi samples t * PER .. t * PER + PER (one shared with t + 1)
-    const int bin = blockIdx.x;
-    const float w = 2.f / kCmemTableBins;
-    const float q_lo = fmaxf(-1.f, -1.f + (float)(bin - 1) * w), q_hi = fminf(1.f, -1.f + (float)(bin + 2) * w);
-    float mn[2] = {CUDART_INF_F, CUDART_INF_F}, mx[2] = {-CUDART_INF_F, -CUDART_INF_F}, dif[2] = {0.f, 0.f};
-    bool bad = false;
-    float prev_row[2][PER + 1];
-    for (int it = 0; it <= NT; ++it) {
-        const float q_t = q_lo + (q_hi - q_lo) * ((float)it / (float)NT);
-        float prev[2] = {0.f, 0.f};
-        for (int k = 0; k <= PER; ++k) {
-            const float phi = 3.14159265f * (float)(threadIdx.x * PER + k) / (float)NP;
-            const float q_p = fminf(1.f, fmaxf(-1.f, cosf(phi)));
-            float theta, sin_t, rad[2];
-            cmem_radii_v4(D, q_t, q_p, theta, sin_t, rad[0], rad[1]);
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const float v = rad[a];
-                if (!(fabsf(v) < CUDART_INF_F)) bad = true;
-                mn[a] = fminf(mn[a], v);
-                mx[a] = fmaxf(mx[a], v);
-                if (k > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev[a]));
-                if (it > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev_row[a][k]));
-                prev[a] = v;
-                prev_row[a][k] = v;
-            }
-        }
-    }
-    __shared__ float s_mn[2][8], s_mx[2][8], s_dif[2][8];
-    __shared__ int s_bad;
-    if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
-    if (bad) atomicOr(&s_bad, 1);
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        float lo = mn[a], hi = mx[a], d = dif[a];
-        for (int o = 16; o > 0; o >>= 1) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
-        }
-        if ((threadIdx.x & 31) == 0) s_mn[a][threadIdx.x >> 5] = lo, s_mx[a][threadIdx.x >> 5] = hi, s_dif[a][threadIdx.x >> 5] = d;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float out[4];
-        for (int a = 0; a < 2; ++a) {
-            float lo = s_mn[a][0], hi = s_mx[a][0], d = s_dif[a][0];
-            for (int k = 1; k < 8; ++k) lo = fminf(lo, s_mn[a][k]), hi = fmaxf(hi, s_mx[a][k]), d = fmaxf(d, s_dif[a][k]);
-            const float slack = 2.f * d + 1e-4f * fabsf(hi);
-            out[2 * a] = lo - slack - BIRP_CMEM_HALF_THICKNESS - BIRP_CMEM_MARGIN(lo);
-            out[2 * a + 1] = hi + slack + BIRP_CMEM_HALF_THICKNESS + BIRP_CMEM_MARGIN(hi);
-        }
-        const bool usable = !s_bad && out[0] == out[0] && out[1] == out[1] && out[2] == out[2] && out[3] == out[3];
-        table[bin] = usable ? make_float4(out[0], out[1], out[2], out[3])
-                            : make_float4(-CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F);
-    }
+// ---- CMEM region table (CmemDev::table): one thread per cell (cmem_table_cell, birp_device.cuh) -----------------
+__global__ void __launch_bounds__(128) cmem_table_kernel(const CmemDev D, float4* __restrict__ table) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= kCmemTableT * kCmemTableP) return;
+    float out[4];
+    cmem_table_cell(D, cell / kCmemTableP, cell % kCmemTableP, out);
+    table[cell] = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // the march's sampler with the table (mode 3 with D.table) against the unfiltered evaluation (mode 2) on n pseudo-random
@@ -979,9 +919,7 @@ __global__ void __launch_bounds__(256) cmem_table_selftest_kernel(const CmemDev 
     if (__float_as_uint(a) != __float_as_uint(b)) atomicAdd(out + 0, 1ull);
     float r, q_t, q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
-    int bin = (int)((q_t + 1.f) * (0.5f * kCmemTableBins));
-    bin = bin < 0 ? 0 : (bin > kCmemTableBins - 1 ? kCmemTableBins - 1 : bin);
-    const float4 tb = D.table[bin];
+    const float4 tb = D.table[cmem_table_index(q_t, q_p)];
     if (r < tb.x || (r > tb.y && (r > tb.w || r < tb.z))) atomicAdd(out + 1, 1ull);
 }
 
@@ -1128,7 +1066,7 @@ cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2
 }
 
 cudaError_t launch_cmem_table(const birp_cmem_params& params, float4* d_table, cudaStream_t stream) {
-    cmem_table_kernel<<<kCmemTableBins, 256, 0, stream>>>(make_cmem_dev(params), d_table);
+    cmem_table_kernel<<<(kCmemTableT * kCmemTableP + 127) / 128, 128, 0, stream>>>(make_cmem_dev(params), d_table);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -559,51 +559,17 @@ void doh_render_cmem(const birp_cmem_params* params, int mode, const birp_frame*
     for (auto& th : pool) th.join();
 }
 
-// cmem_table_kernel restated for the host (the kernel's reductions are warp shuffles): the same grid of directions,
-// the same widening.  table: kCmemTableBins x {mp_lo, mp_hi, bs_lo, bs_hi}.
+// cmem_table_kernel on the host: the same per-cell function (cmem_table_cell), over all cells.
+// table: kCmemTableT * kCmemTableP x {mp_lo, mp_hi, bs_lo, bs_hi}.
 void doh_cmem_table(const birp_cmem_params* params, float* table) {
     const birp::CmemDev D = birp::make_cmem_dev(*params);
-    constexpr int NT = 24, NP = 2048, N = birp::kCmemTableBins;
+    const int ncell = birp::kCmemTableT * birp::kCmemTableP;
     const int nthreads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<std::thread> pool;
     for (int t = 0; t < nthreads; ++t)
         pool.emplace_back([&, t] {
-            std::vector<float> prev_row(2 * (NP + 1));
-            for (int bin = t; bin < N; bin += nthreads) {
-                const float w = 2.f / N;
-                const float q_lo = fmaxf(-1.f, -1.f + (float)(bin - 1) * w), q_hi = fminf(1.f, -1.f + (float)(bin + 2) * w);
-                float mn[2] = {CUDART_INF_F, CUDART_INF_F}, mx[2] = {-CUDART_INF_F, -CUDART_INF_F}, dif[2] = {0.f, 0.f};
-                bool bad = false;
-                for (int it = 0; it <= NT; ++it) {
-                    const float q_t = q_lo + (q_hi - q_lo) * ((float)it / (float)NT);
-                    float prev[2] = {0.f, 0.f};
-                    for (int k = 0; k <= NP; ++k) {
-                        const float phi = 3.14159265f * (float)k / (float)NP;
-                        const float q_p = fminf(1.f, fmaxf(-1.f, cosf(phi)));
-                        float theta, sin_t, rad[2];
-                        birp::cmem_radii_v4(D, q_t, q_p, theta, sin_t, rad[0], rad[1]);
-                        for (int a = 0; a < 2; ++a) {
-                            const float v = rad[a];
-                            if (!(fabsf(v) < CUDART_INF_F)) bad = true;
-                            mn[a] = fminf(mn[a], v);
-                            mx[a] = fmaxf(mx[a], v);
-                            if (k > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev[a]));
-                            if (it > 0) dif[a] = fmaxf(dif[a], fabsf(v - prev_row[2 * k + a]));
-                            prev[a] = v;
-                            prev_row[2 * k + a] = v;
-                        }
-                    }
-                }
-                float out[4];
-                for (int a = 0; a < 2; ++a) {
-                    const float slack = 2.f * dif[a] + 1e-4f * fabsf(mx[a]);
-                    out[2 * a] = mn[a] - slack - BIRP_CMEM_HALF_THICKNESS - BIRP_CMEM_MARGIN(mn[a]);
-                    out[2 * a + 1] = mx[a] + slack + BIRP_CMEM_HALF_THICKNESS + BIRP_CMEM_MARGIN(mx[a]);
-                }
-                const bool usable = !bad && out[0] == out[0] && out[1] == out[1] && out[2] == out[2] && out[3] == out[3];
-                const float none[4] = {-CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, CUDART_INF_F};
-                std::memcpy(table + 4 * bin, usable ? out : none, sizeof(out));
-            }
+            for (int cell = t; cell < ncell; cell += nthreads)
+                birp::cmem_table_cell(D, cell / birp::kCmemTableP, cell % birp::kCmemTableP, table + 4 * cell);
         });
     for (auto& th : pool) th.join();
 }
@@ -618,9 +584,7 @@ void doh_sample_cmem_table(const birp_cmem_params* params, const float* table, c
         out[p] = birp::cmem_sample_mode<3>(D, x, y, z);
         float r, q_t, q_p;
         birp::cmem_cosines_estimate(x, y, z, r, q_t, q_p);
-        int bin = (int)((q_t + 1.f) * (0.5f * birp::kCmemTableBins));
-        bin = bin < 0 ? 0 : (bin > birp::kCmemTableBins - 1 ? birp::kCmemTableBins - 1 : bin);
-        const float* tb = table + 4 * bin;
+        const float* tb = table + 4 * birp::cmem_table_index(q_t, q_p);
         decided[p] = (r < tb[0] || (r > tb[1] && (r > tb[3] || r < tb[2]))) ? 1 : 0;
     }
 }

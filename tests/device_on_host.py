@@ -172,9 +172,9 @@ def cmem_filter_decides(params, xyz):
 
 
 def cmem_table(params):
-    """the region table of a parameter set (cmem_table_kernel restated on the host): (bins, 4) floats"""
+    """the region table of a parameter set (cmem_table_cell over all cells, on the host): (256 * 64, 4) floats"""
     params = np.ascontiguousarray(params)
-    out = np.zeros((512, 4), np.float32)
+    out = np.zeros((256 * 64, 4), np.float32)
     lib().doh_cmem_table(_p(params), _p(out))
     return out
 

@@ -770,11 +770,12 @@ CMEM_KW = [{}, O.CMEM_CLI, O.CMEM_TEST2, dict(dipole=0.2, b=(1, -2, -6), v=(450,
 
 @pytest.mark.parametrize("kw", CMEM_KW)
 def test_cmem_filter_margin(gpu, kw):
-    """the fp32 radius estimates of the region filter stay within a twentieth of the margin the filter allows
-    them, over 10^8 sample positions (incl. positions squeezed towards the degenerate planes and axes)"""
+    """the fp32 radius estimates of the region filter stay within an eighth of the margin the filter allows them
+    (2e-3 R + 2e-3 RE), over 10^8 sample positions (incl. positions squeezed towards the degenerate planes and axes);
+    the library itself refuses the filter for a parameter set that uses more than a quarter"""
     out = capi.selftest_cmem_filter(capi.cmem_init(**kw), 100_000_000)
     print(out)
-    assert out["margin_used_mp"] <= 0.05 and out["margin_used_bs"] <= 0.05, out
+    assert out["margin_used_mp"] <= 0.125 and out["margin_used_bs"] <= 0.125, out
     assert out["trusted_fraction"] > 0.9
 
 
