@@ -363,6 +363,8 @@ def run_b200(args, wl, name):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    # the ranks of one box share its cores: each makes its frame records on its share of them
+    os.environ.setdefault("BIRP_HOST_THREADS", str(max(1, min(16, len(os.sched_getaffinity(0)) // world))))
     torch.cuda.set_device(local)
     capi.set_device(local)
     dev = torch.device("cuda", local)
@@ -414,8 +416,7 @@ def run_b200(args, wl, name):
             # one image over the GPUs in INTERLEAVED bands of 32 rows (rank r: bands r, r + N, ...): every rank gets the
             # same mix of cheap rows (rays that leave the cube early) and expensive ones
             interleave = (ROW_BAND, rank, world)
-            own = ((np.arange(H) // ROW_BAND) % world) == rank
-            my_rows = int(own.sum())
+            my_rows = sum(r1 - r0 for r0, r1 in sharding.interleaved_row_bands(H, ROW_BAND, world, rank))
             rows = (0, H)
     nmine = len(my_frames)
 
@@ -630,22 +631,10 @@ def run_b200(args, wl, name):
     h_frames = capi.PinnedArray((nmine,), capi.FRAME_DTYPE)
     h_frames.array[:] = my_frames
     frames_total_n = nframes if nframes > 1 else 1
-    shm = None
+    shared = None
     if world > 1:
-        from multiprocessing import shared_memory
-        shm_name = [None]
-        if rank == 0:
-            shm = shared_memory.SharedMemory(create=True, size=frames_total_n * H * W * 4)
-            shm_name[0] = shm.name
-        dist.broadcast_object_list(shm_name, src=0)
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=shm_name[0])
-        h_all = np.ndarray((frames_total_n, H, W), dtype=np.float32, buffer=shm.buf)
-        if rank == 0:
-            h_all[:] = 0
-        dist.barrier()
-        capi.host_register(h_all)
-        shm_addr = h_all.ctypes.data
+        shared = sharding.SharedHostResult((frames_total_n, H, W), rank, world)
+        h_all = shared.array
         h_images = None
     else:
         h_images = capi.PinnedArray((nmine, H, W), np.float32)
@@ -889,17 +878,9 @@ def run_b200(args, wl, name):
     h_frames.free()
     if h_images is not None:
         h_images.free()
-    if shm is not None:
-        import ctypes
+    if shared is not None:
         e2e_images = h_all = got = None  # (views of the segment must be gone before it is closed)
-        dist.barrier()
-        capi.lib().birp_host_unregister(ctypes.c_void_p(shm_addr))
-        try:
-            shm.close()
-        except BufferError:
-            pass
-        if rank == 0:
-            shm.unlink()
+        shared.close()
     if peer is not None:
         peer.close()
     if world > 1:

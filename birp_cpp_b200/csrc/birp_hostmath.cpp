@@ -15,6 +15,7 @@
 //   birp_cmem_init    <- CMEM::Init and helpers       reference src/Cmem.cpp:38-115,250-325
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -67,7 +68,12 @@ int host_frame_setup_batch(const float* poses, int n, float aim_x, float fov_x_d
                            birp_frame* out, int nthreads) {
     if (n <= 0) return BIRP_OK;
     unsigned hw = std::thread::hardware_concurrency();
-    if (nthreads <= 0) nthreads = (int)(hw ? (hw < 16 ? hw : 16) : 4);
+    if (nthreads <= 0) {
+        // BIRP_HOST_THREADS: processes that share a box (one per GPU) divide the cores between them
+        const char* env = std::getenv("BIRP_HOST_THREADS");
+        const int want = env ? std::atoi(env) : 0;
+        nthreads = want > 0 ? want : (int)(hw ? (hw < 16 ? hw : 16) : 4);
+    }
     if (nthreads > (n + 255) / 256) nthreads = (n + 255) / 256;
     std::atomic<int> status{BIRP_OK};
     auto work = [&](int begin, int end) {

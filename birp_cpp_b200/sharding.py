@@ -28,6 +28,68 @@ def row_band(height: int, world: int, rank: int) -> Tuple[int, int]:
     return block_range(height, world, rank)
 
 
+def interleaved_row_bands(height: int, band_rows: int, world: int, rank: int) -> List[Tuple[int, int]]:
+    """single large image in INTERLEAVED bands (birp_render_cube_rows / birp_render_cube_device_rows): of the bands of
+    `band_rows` rows counted from the top, `rank` renders those with index = rank (mod world); the last band of the
+    image may be short.  Returns the [begin, end) row ranges in image order."""
+    out = []
+    nbands = (height + band_rows - 1) // band_rows
+    for b in range(rank, nbands, world):
+        out.append((b * band_rows, min(height, (b + 1) * band_rows)))
+    return out
+
+
+class SharedHostResult:
+    """ONE host buffer for the result of a job that several processes of a box render (rank 0 owns a POSIX
+    shared-memory segment, every rank maps it): each rank's sweep / row-band call writes its share straight into it
+    (birp_render_*_sweep_strided, birp_render_cube_rows), every GPU over its own PCIe link.  `register` page-locks
+    the mapping with the CUDA driver (birp_host_register); on CPU-only ranks (tests) it is left out."""
+
+    def __init__(self, shape, rank: int, world: int, register: bool = True):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        self.rank, self.world = rank, world
+        nbytes = int(np.prod(shape)) * 4
+        name = [None]
+        self.shm = None
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(create=True, size=max(nbytes, 4))
+            name[0] = self.shm.name
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name[0])
+        self.array = np.ndarray(shape, dtype=np.float32, buffer=self.shm.buf)
+        if rank == 0:
+            self.array[...] = 0
+        if world > 1:
+            dist.barrier()
+        self._addr = self.array.ctypes.data
+        self._registered = False
+        if register:
+            from . import capi
+            capi.host_register(self.array)
+            self._registered = True
+
+    def close(self):
+        import ctypes
+        import torch.distributed as dist
+        self.array = None
+        if self.world > 1:
+            dist.barrier()  # nobody unmaps while a peer may still be writing
+        if self._registered:
+            from . import capi
+            capi.lib().birp_host_unregister(ctypes.c_void_p(self._addr))
+            self._registered = False
+        try:
+            self.shm.close()
+        except BufferError:
+            pass
+        if self.rank == 0:
+            self.shm.unlink()
+
+
 def broadcast_cube(cube_tensor, geom_tensor, src: int = 0):
     """replicate the grid and its origin/spacing from `src` to every rank (one-time)"""
     import torch.distributed as dist

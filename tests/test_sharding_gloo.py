@@ -24,6 +24,12 @@ def test_block_partition_properties():
     assert sharding.frame_block(10000, 8, 3) == (3750, 5000)
     assert sharding.row_band(1024, 8, 7) == (896, 1024)
     assert sharding.row_band(64, 3, 0) == (0, 22)
+    # interleaved row bands: the ranks' bands partition the image, a short last band included
+    for height, band, world in ((64, 8, 4), (70, 16, 3), (4096, 32, 8), (24, 8, 5)):
+        rows = sorted(r for rank in range(world) for b in sharding.interleaved_row_bands(height, band, world, rank)
+                      for r in range(*b))
+        assert rows == list(range(height))
+    assert sharding.interleaved_row_bands(70, 16, 3, 1) == [(16, 32), (64, 70)]
 
 
 def _free_port():
@@ -88,11 +94,27 @@ def _worker(rank, world, port, out_path):
         r0, r1 = sh.row_band(H, world, rank)
         img = O.orc_render_cube(zyx, org, sp, True, frames[:1], W, H, rows=(r0, r1), nthreads=1)
         whole = sh.gather_row_bands(torch.from_numpy(img[0, r0:r1].copy()), bands)
+        # (c) the end-to-end layout of bench.py at N > 1: ONE host buffer on rank 0 (shared memory) that every rank
+        # writes its share into -- a sweep interleaved frame by frame, then one image in interleaved row bands
+        shared = sh.SharedHostResult((8, H, W), rank, world, register=False)
+        for j, f in enumerate(idx):
+            shared.array[f] = mine8[j].numpy()
+        dist.barrier()
+        shared_sweep = shared.array.copy() if rank == 0 else None
+        shared.close()
+        one = sh.SharedHostResult((1, H, W), rank, world, register=False)
+        my_bands = sh.interleaved_row_bands(H, 4, world, rank)
+        for r0b, r1b in my_bands:
+            one.array[0, r0b:r1b] = O.orc_render_cube(zyx, org, sp, True, frames[:1], W, H, rows=(r0b, r1b), nthreads=1)[0, r0b:r1b]
+        dist.barrier()
+        shared_image = one.array.copy() if rank == 0 else None
+        one.close()
         if rank == 0:
             want = O.orc_render_cube(zyx, org, sp, True, frames, W, H, nthreads=1)
             want8 = O.orc_render_cube(zyx, org, sp, True, frames8, W, H, nthreads=1)
             np.savez(out_path, full=full.numpy(), want=want, whole=whole.numpy(),
-                     inter=inter.reshape(8, H, W).numpy(), want8=want8, blocks7=blocks7.numpy())
+                     inter=inter.reshape(8, H, W).numpy(), want8=want8, blocks7=blocks7.numpy(),
+                     shared_sweep=shared_sweep, shared_image=shared_image)
         else:
             assert full is None and whole is None and inter is None and blocks7 is None
         dist.barrier()
@@ -110,4 +132,6 @@ def test_two_rank_gather_equals_unsharded(tmp_path):
     assert np.array_equal(d["whole"].view(np.uint32), d["want"][0].view(np.uint32))
     assert np.array_equal(d["inter"].view(np.uint32), d["want8"].view(np.uint32))
     assert np.array_equal(d["blocks7"].view(np.uint32), d["want"].view(np.uint32))
+    assert np.array_equal(d["shared_sweep"].view(np.uint32), d["want8"].view(np.uint32))
+    assert np.array_equal(d["shared_image"][0].view(np.uint32), d["want"][0].view(np.uint32))
     assert d["want"].max() > 0

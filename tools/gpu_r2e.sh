@@ -4,9 +4,9 @@ tag=${1:-r2e}
 N=${2:-2}
 mkdir -p gpurun_out
 nvidia-smi -L
-timeout 600 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${tag}_pytest_${N}gpu.log 2>&1
+timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/${tag}_pytest_${N}gpu.log 2>&1
 tail -6 gpurun_out/${tag}_pytest_${N}gpu.log
-for spec in "orbit:0" "orbit-zeros:0" "orbit-neg:0" "hires512x4k:0" "cmem:0"; do
+for spec in "orbit:0" "hires512x4k:0" "cmem:0" "orbit:32768" "cmem:4"; do
 w=${spec%%:*}; fl=${spec#*:}
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $w --extra-flags $fl > gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.json 2> gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.err; echo "bench $w $fl rc=$?"
 python - <<PY
