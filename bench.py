@@ -48,7 +48,7 @@ if str(ROOT) not in sys.path:
 from birp_cpp_b200 import synthetic as S  # noqa: E402
 
 NSAMPLES, MAXDIST = 200, 44
-ROW_BAND = 32  # rows per interleaved band when one image is split over the ranks (a multiple of the 8-row warp tile)
+ROW_BAND = 128  # rows per interleaved band when one image is split over the ranks (a multiple of the 8-row warp tile)
 EXTRA_FLAGS = 0
 
 
@@ -671,9 +671,9 @@ def run_b200(args, wl, name):
     e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        e2e_step()
-        if world > 1:
-            dist.barrier()  # a step of the job ends when every rank's share is in rank 0's buffer
+        e2e_step()  # (synchronous on return: this rank's share of the sweep is in rank 0's host buffer)
+    if world > 1:
+        dist.barrier()  # the K steps end when every rank's last share is in that buffer
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -683,8 +683,8 @@ def run_b200(args, wl, name):
     e2e_images = h_all if world > 1 else h_images.array
     if world > 1:
         e2e_note = ("every rank writes its share straight into ONE host buffer owned by rank 0 (POSIX shared memory, "
-                    "page-locked by each rank): bytes are per rank, each GPU drains over its own PCIe link; a step ends "
-                    "with a barrier, when the whole sweep is in that buffer")
+                    "page-locked by each rank): bytes are per rank, each GPU drains over its own PCIe link; the K steps are "
+                    "bracketed by barriers")
         # rank 0 holds the whole result on the host: probe frames / rows of OTHER ranks' shares against rank 0's own render
         if rank == 0:
             if nframes > 1:
@@ -849,7 +849,7 @@ def run_b200(args, wl, name):
             "run": {"cube_analysis": cube.info() if cube is not None else None, "extra_flags": EXTRA_FLAGS,
                     "gather": {"none": "none (1 GPU)",
                                "peer": "render kernels store their pixels into rank 0's buffer over NVLink (CUDA IPC), "
-                                       "one all-reduce fence; inside the timed region",
+                                       "completion flags in rank 0's memory as the fence; inside the timed region",
                                }.get(gather_mode, "NCCL grouped send/recv to rank 0, inside the timed region")},
             "rays_per_sec": value * W * H,
             "samples_per_sec": valid_total / (total_ms / args.steps / 1e3),

@@ -19,7 +19,7 @@ HEADER_PATH = _HERE.parent / "include" / "birp_b200.h"
 BIRP_OK, BIRP_ERR_CUDA, BIRP_ERR_ARG, BIRP_ERR_SINGULAR, BIRP_ERR_RANGE, BIRP_ERR_NOMEM = range(6)
 NEAREST, TRILINEAR, ACCUMULATE, CMEM_FAST = 0, 1, 2, 4
 DIV_TWO_STEP, DIV_IEEE, GENERAL_LERP, NO_TEXTURE, TEXTURE_ONLY, NO_QUADS, QUADS_ONLY, CMEM_LIBM64, CMEM_NO_FILTER = 8, 16, 32, 64, 128, 256, 512, 1024, 2048
-WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH, FAST_MARCH, NO_LEAN_MARCH, CMEM_NO_TABLE, CMEM_LIBM32 = 4096, 8192, 16384, 32768, 65536, 131072, 262144
+WINDOW_PER_STEP, NO_OCTS, LEAN_MARCH, FAST_MARCH, NO_LEAN_MARCH, CMEM_NO_TABLE, CMEM_LIBM32, DIV_ONE_STEP = 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288
 
 FRAME_DTYPE = np.dtype(
     [("pos", "<f4", (3,)), ("rinv", "<f4", (9,)), ("tan_half_x", "<f4"), ("tan_half_y", "<f4"),
@@ -102,6 +102,8 @@ SIGNATURES = {
     "birp_ipc_export": (C.c_int, [_vp, _vp]),
     "birp_ipc_import": (C.c_int, [_vp, C.POINTER(_vp)]),
     "birp_ipc_close": (C.c_int, [_vp]),
+    "birp_peer_signal": (C.c_int, [_vp, C.c_uint, _vp]),
+    "birp_peer_wait": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
     "birp_check_device_status": (C.c_int, [_vp]),
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
     "birp_selftest_cmem_filter": (C.c_int, [_vp, C.c_long, _vp]),
@@ -540,6 +542,14 @@ class DeviceBuffer:
         if self._p:
             (lib().birp_ipc_close if self._imported else lib().birp_device_free)(self._p)
             self._p = _vp()
+
+
+def peer_signal(d_flag: int, value: int, stream: int = 0) -> None:
+    _check(lib().birp_peer_signal(_vp(d_flag), int(value) & 0xffffffff, _vp(stream)))
+
+
+def peer_wait(d_flags: int, n: int, value: int, stream: int = 0) -> None:
+    _check(lib().birp_peer_wait(_vp(d_flags), int(n), int(value) & 0xffffffff, _vp(stream)))
 
 
 def check_device_status(stream: int = 0) -> None:

@@ -194,6 +194,8 @@ int read_status(DeviceCtx* c, cudaStream_t stream) {
     if (st) {
         BIRP_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), stream));
         BIRP_CUDA(cudaStreamSynchronize(stream));
+        if (st & birp::kStatusPeerTimeout)
+            return set_error(BIRP_ERR_CUDA, "birp_peer_wait: a rank did not signal within the time limit");
         if (st & birp::kStatusSingular) return set_error(BIRP_ERR_SINGULAR, "Determinant is 0");
         if (st & birp::kStatusNanIndex)
             return set_error(BIRP_ERR_RANGE,
@@ -648,9 +650,10 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
             BIRP_CUDA(cudaMemsetAsync(c->d_flags, 0, 4 * sizeof(int), c->compute));
             cudaError_t e = birp::launch_verify_div(sp[a], rcp[a], lbits, c->d_flags, c->compute);
             if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "verify_div launch: %s", cudaGetErrorString(e));
-            BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
+            BIRP_CUDA(cudaMemcpyAsync(c->h_status, c->d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->compute));
             BIRP_CUDA(cudaStreamSynchronize(c->compute));
-            m = (c->h_status[0] == 0) ? 0 : (c->h_status[1] == 0) ? 1 : 2;
+            // cost rank of the cheapest exact form: 0 the multiply alone, 1 one correction step, 2 two, 3 IEEE division
+            m = (c->h_status[2] == 0) ? 0 : (c->h_status[0] == 0) ? 1 : (c->h_status[1] == 0) ? 2 : 3;
             c->divmode_cache[key] = m;
         }
         if (m > mode) mode = m;
@@ -775,7 +778,9 @@ static int finish_cube(DeviceCtx* c, birp_cube* cube) {
     v.lx = lim[0];
     v.ly = lim[1];
     v.lz = lim[2];
-    v.divmode = mode;
+    // (cost rank -> div_spacing<MODE>: 3 multiply only, 0 one step, 1 two steps, 2 IEEE)
+    static const int kModeOfRank[4] = {3, 0, 1, 2};
+    v.divmode = kModeOfRank[mode];
     return BIRP_OK;
 }
 
@@ -1448,6 +1453,26 @@ int birp_ipc_import(const unsigned char handle[64], void** d_ptr) {
 
 int birp_ipc_close(void* d_ptr) {
     if (d_ptr) BIRP_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return BIRP_OK;
+}
+
+int birp_peer_signal(unsigned* d_flag, unsigned value, void* stream) {
+    if (!d_flag) return set_error(BIRP_ERR_ARG, "null flag");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    cudaError_t e = birp::launch_peer_signal(d_flag, value, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return BIRP_OK;
+}
+
+int birp_peer_wait(const unsigned* d_flags, int n, unsigned value, void* stream) {
+    if (!d_flags || n < 1 || n > 32) return set_error(BIRP_ERR_ARG, "bad flag array");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    cudaError_t e = birp::launch_peer_wait(d_flags, n, value, c->d_status, (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return BIRP_OK;
 }
 

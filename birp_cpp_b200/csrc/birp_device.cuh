@@ -137,7 +137,9 @@ __device__ __forceinline__ void gather4(cudaTextureObject_t tex, int layer, floa
 // ingress / spacing, correctly rounded.
 //   MODE 2: IEEE division.
 //   MODE 0/1: multiply by the correctly rounded reciprocal, then one / two residual corrections.
-// MODE 0 and 1 are only selected for a cube after an EXHAUSTIVE device-side comparison with
+//   MODE 3: the multiply alone -- exact when the spacing is a power of two (0.5 R_E in the reference's own cubes):
+//           the reciprocal is exact and scaling by a power of two rounds nothing in the normal range.
+// MODE 0, 1 and 3 are only selected for a cube after an EXHAUSTIVE device-side comparison with
 // __fdiv_rn over every fp32 ingress of the hot window (2^-100 <= a < limit), for each
 // axis spacing (verify_div_kernel), so the quotient -- and with it the voxel index and the
 // interpolation weight -- is bit-identical to the reference's `x_ingress / spacing[0]`.
@@ -145,6 +147,7 @@ template <int MODE>
 __device__ __forceinline__ float div_spacing(float a, float s, float r) {
     if (MODE == 2) return __fdiv_rn(a, s);
     float q = __fmul_rn(a, r);
+    if (MODE == 3) return q;
     float e = __fmaf_rn(-q, s, a);
     q = __fmaf_rn(e, r, q);
     if (MODE == 1) {
@@ -489,6 +492,7 @@ constexpr int kSmemDist = 2048;  // ray-table entries kept in shared memory by t
 // bits in the device status word
 constexpr int kStatusNanIndex = 1;  // BIRP_ERR_RANGE
 constexpr int kStatusSingular = 2;  // BIRP_ERR_SINGULAR (device frame setup)
+constexpr int kStatusPeerTimeout = 4;  // birp_peer_wait gave up (BIRP_ERR_CUDA)
 
 // entry of the staged ray table at 32-bit shared-window address `sdist` (one LDS; the host build reads its own
 // copy of the table at that byte offset)

@@ -71,6 +71,10 @@ cudaError_t launch_pack_poly(const CubeView& cube, float* d_poly, cudaStream_t s
 cudaError_t launch_verify_gather(const CubeView& cube, int ncells, int* d_bad, cudaStream_t stream);
 cudaError_t launch_verify_div(float s, float r, unsigned limit_bits, int* d_bad2, cudaStream_t stream);
 
+// completion flags between the GPUs of a box (see signal_kernel / wait_kernel)
+cudaError_t launch_peer_signal(unsigned* d_flag, unsigned value, cudaStream_t stream);
+cudaError_t launch_peer_wait(const unsigned* d_flags, int n, unsigned value, int* d_status, cudaStream_t stream);
+
 unsigned long long launch_count();
 
 }  // namespace birp

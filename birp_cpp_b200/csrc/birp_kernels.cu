@@ -670,10 +670,10 @@ __global__ void __launch_bounds__(256) scan_positive_kernel(const float* __restr
 
 // Exhaustive proof for one spacing: for EVERY fp32 ingress a of the hot window,
 // 2^-100 <= a < limit (all bit patterns in [bits(2^-100), limit_bits)), do the cheap quotients
-// equal the IEEE one?  bad[0] / bad[1] are set when div_spacing<0> / div_spacing<1> ever differs
-// from __fdiv_rn.
+// equal the IEEE one?  bad[0] / bad[1] / bad[2] are set when div_spacing<0> / <1> / <3> (the multiply alone) ever
+// differs from __fdiv_rn.
 __global__ void __launch_bounds__(256) verify_div_kernel(float s, float r, unsigned limit_bits, int* bad) {
-    bool b0 = false, b1 = false;
+    bool b0 = false, b1 = false, b3 = false;
     const unsigned long long first = __float_as_uint(BIRP_TINY_INGRESS);
     for (unsigned long long u = first + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < limit_bits;
          u += (unsigned long long)gridDim.x * blockDim.x) {
@@ -681,9 +681,11 @@ __global__ void __launch_bounds__(256) verify_div_kernel(float s, float r, unsig
         const unsigned want = __float_as_uint(__fdiv_rn(a, s));
         b0 |= __float_as_uint(div_spacing<0>(a, s, r)) != want;
         b1 |= __float_as_uint(div_spacing<1>(a, s, r)) != want;
+        b3 |= __float_as_uint(div_spacing<3>(a, s, r)) != want;
     }
     if (__any_sync(0xffffffffu, b0) && (threadIdx.x & 31) == 0) atomicOr(bad + 0, 1);
     if (__any_sync(0xffffffffu, b1) && (threadIdx.x & 31) == 0) atomicOr(bad + 1, 1);
+    if (__any_sync(0xffffffffu, b3) && (threadIdx.x & 31) == 0) atomicOr(bad + 2, 1);
 }
 
 // ---- per-frame setup on the device ----------------------------------------------
@@ -923,6 +925,33 @@ __global__ void __launch_bounds__(256) cmem_table_selftest_kernel(const CmemDev 
     if (r < tb.x || (r > tb.y && (r > tb.w || r < tb.z))) atomicAdd(out + 1, 1ull);
 }
 
+// ---- completion flags between the GPUs of a box (one process per GPU, results in one GPU's memory) -----------------
+// A rank's render kernel stores its pixels into the gathering rank's buffer over NVLink; "all ranks are done" used to be
+// a 4-byte NCCL all-reduce (30-40 us: 4 % of a 0.9 ms step).  Now each rank's stream ends a step with signal_kernel --
+// one store of the step number into its slot of a flag array in the gathering rank's memory, ordered after the render
+// kernel's stores by the stream and a system-scope fence -- and the gathering rank's stream waits in wait_kernel until
+// every slot holds the step number.  The wait gives up after ~2 s of clock (a rank died): the status word says so.
+__global__ void signal_kernel(volatile unsigned* flag, unsigned value) {
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+
+__global__ void wait_kernel(const volatile unsigned* flags, int n, unsigned value, int* status) {
+    const int t = threadIdx.x;
+    if (t < n) {
+        const long long t0 = clock64();
+        while ((int)(flags[t] - value) < 0) {  // (wrap-safe: a slot may already hold a LATER step)
+            __nanosleep(200);
+            if (clock64() - t0 > 4000000000LL) {
+                if (status) atomicOr(status, kStatusPeerTimeout);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 inline unsigned blocks_for(long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -939,8 +968,9 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     if (a.total_tiles <= 0) return cudaSuccess;
     const bool tri = (flags & BIRP_TRILINEAR) != 0;
     const int lerp = (flags & BIRP_GENERAL_LERP) ? 0 : cube.positive;
-    int divmode = cube.divmode;
-    if ((flags & BIRP_DIV_TWO_STEP) && divmode < 1) divmode = 1;
+    int divmode = cube.divmode;  // 3 multiply only (power-of-two spacings), 0 one correction step, 1 two, 2 IEEE
+    if ((flags & BIRP_DIV_TWO_STEP) && (divmode == 3 || divmode == 0)) divmode = 1;
+    if (flags & BIRP_DIV_ONE_STEP && divmode == 3) divmode = 0;
     if (flags & BIRP_DIV_IEEE) divmode = 2;
     // corner fetch of the trilinear kernel (cube_sample_hot): what the cube has, minus what the flags forbid
     const bool has_tex = cube.tex != 0 && !(flags & BIRP_NO_TEXTURE);
@@ -1017,6 +1047,7 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
     switch (divmode) {
         case 0: e = launch_cube_div<0>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
         case 1: e = launch_cube_div<1>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
+        case 3: e = launch_cube_div<3>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
         default: e = launch_cube_div<2>(a, view, blocks, tri, lerp, fetch, span, lean, stream); break;
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1103,6 +1134,18 @@ cudaError_t launch_render_cmem(const birp_cmem_params& params, const birp_frame*
     CmemField<3> f{make_cmem_dev(params)};
     f.D.table = (flags & BIRP_CMEM_NO_TABLE) ? nullptr : d_table;
     return launch_march(f, d_frames, g, d_dist, flags, d_images, d_valid, nullptr, stream);
+}
+
+cudaError_t launch_peer_signal(unsigned* d_flag, unsigned value, cudaStream_t stream) {
+    signal_kernel<<<1, 1, 0, stream>>>(d_flag, value);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(const unsigned* d_flags, int n, unsigned value, int* d_status, cudaStream_t stream) {
+    wait_kernel<<<1, 32, 0, stream>>>(d_flags, n, value, d_status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_accumulate(const float* d_samples, long nrays, int nsamples, float ray_width, int flags,

@@ -59,6 +59,8 @@ enum {
                                 for bit in 99 % of the cases */
     /* diagnostics: force the slower, equally exact kernel variants (see DESIGN.md "variants") */
     BIRP_DIV_TWO_STEP = 8,   /* two residual corrections in the division by the spacing */
+    BIRP_DIV_ONE_STEP = 524288, /* one residual correction even where the multiply by the reciprocal alone is exact (a
+                                   cube whose spacings are powers of two) */
     BIRP_DIV_IEEE = 16,      /* plain IEEE division by the spacing */
     BIRP_GENERAL_LERP = 32,  /* full std::lerp semantics even for an all-positive cube */
     /* corner fetch of the trilinear kernel; default: one 32-byte load per sample from the oct copy of
@@ -197,7 +199,7 @@ void birp_cube_free(birp_cube* cube);
 int birp_cube_replicate(const birp_cube* src, int device, birp_cube** out);
 int birp_cube_device(const birp_cube* cube, int* device);
 /* what the upload-time analysis found: info[0] = division variant proven exact for this cube's
-   spacings (0 one-step, 1 two-step, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0, 2 when
+   spacings (3 the multiply by the reciprocal alone: power-of-two spacings; 0 one correction step, 1 two, 2 IEEE only), info[1] = 1 when every voxel is finite and > 0, 2 when
    finite and > 0 or +0 (each class has its own exact form of std::lerp), 0 otherwise,
    info[2] = 1 when the layered-texture copy exists and passed its gather self-check,
    info[3] = 1 when the quad copy (16-byte corner fetch) exists and passed its self-check */
@@ -307,6 +309,15 @@ int birp_device_free(void* d_ptr);
 int birp_ipc_export(const void* d_ptr, unsigned char handle[64]);
 int birp_ipc_import(const unsigned char handle[64], void** d_ptr);
 int birp_ipc_close(void* d_ptr);
+
+/* Completion flags for results that several processes' kernels store into ONE GPU's memory (birp_*_device_strided with
+   an imported pointer): birp_peer_signal enqueues, after the caller's render on `stream`, one store of `value` (the
+   step number) into *d_flag -- the caller's slot of a flag array in the gathering GPU's memory, mapped like the
+   result buffer; birp_peer_wait makes the gathering GPU's `stream` wait until all n slots hold `value` (or a later
+   one).  A 5 us replacement for a one-element all-reduce; the wait gives up after ~2 s and raises the device status
+   (birp_check_device_status returns BIRP_ERR_CUDA). */
+int birp_peer_signal(unsigned* d_flag, unsigned value, void* stream);
+int birp_peer_wait(const unsigned* d_flags, int n, unsigned value, void* stream);
 
 /* device error word of the calling thread's device (BIRP_ERR_RANGE / BIRP_ERR_SINGULAR conditions raised
    by *_device launches); synchronises `stream`, returns BIRP_OK or the error and clears it */

@@ -177,6 +177,7 @@ bool render_div(RenderJob& job, int div, int lerp, int fetch, int span) {
         case 0: return render_lerp<TRI, 0>(job, lerp, fetch, span);
         case 1: return render_lerp<TRI, 1>(job, lerp, fetch, span);
         case 2: return render_lerp<TRI, 2>(job, lerp, fetch, span);
+        case 3: return render_lerp<TRI, 3>(job, lerp, fetch, span);
     }
     return false;
 }
@@ -328,9 +329,9 @@ void doh_cube_window(const void* cube, float lo[3], float hi[3]) {
     hi[0] = v.lx, hi[1] = v.ly, hi[2] = v.lz;
 }
 
-// verify_div_kernel on every `stride`-th fp32 ingress of the hot window of one axis: bad[m] = 1 when
-// div_spacing<m> ever differs from IEEE division
-void doh_verify_div(float s, int n, unsigned stride, int bad[2]) {
+// verify_div_kernel on every `stride`-th fp32 ingress of the hot window of one axis: bad[0] / bad[1] / bad[2] = 1 when
+// div_spacing<0> / <1> / <3> (the multiply alone) ever differs from IEEE division
+void doh_verify_div(float s, int n, unsigned stride, int bad[3]) {
     const volatile float rv = 1.0f / s;
     const float r = rv;
     const float limit = birp::host_bounds_limit(s, n);
@@ -338,7 +339,7 @@ void doh_verify_div(float s, int n, unsigned stride, int bad[2]) {
     const float tiny = BIRP_TINY_INGRESS;
     std::memcpy(&first, &tiny, 4);
     std::memcpy(&last, &limit, 4);
-    bad[0] = bad[1] = 0;
+    bad[0] = bad[1] = bad[2] = 0;
     for (uint64_t u = first; u < last; u += stride) {
         const uint32_t b = (uint32_t)u;
         float a;
@@ -346,6 +347,7 @@ void doh_verify_div(float s, int n, unsigned stride, int bad[2]) {
         const float want = a / s;
         if (birp::div_spacing<0>(a, s, r) != want) bad[0] = 1;
         if (birp::div_spacing<1>(a, s, r) != want) bad[1] = 1;
+        if (birp::div_spacing<3>(a, s, r) != want) bad[2] = 1;
     }
 }
 
@@ -388,6 +390,7 @@ int doh_sample_cube(const void* cube, int trilinear, int lerp, int fetch, const 
     switch (c.divmode) {                         \
         case 0: DOH_HOT_LERP(TRI, 0); break;     \
         case 1: DOH_HOT_LERP(TRI, 1); break;     \
+        case 3: DOH_HOT_LERP(TRI, 3); break;     \
         default: DOH_HOT_LERP(TRI, 2); break;    \
     }
         if (trilinear) { DOH_HOT_DIV(true) } else { DOH_HOT_DIV(false) }

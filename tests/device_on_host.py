@@ -55,11 +55,12 @@ def _p(a):
     return a.ctypes.data_as(_vp)
 
 
-def verify_div(spacing: float, n: int, stride: int = 1) -> tuple[bool, bool]:
-    """(one-step division exact, two-step division exact) over every `stride`-th ingress of the hot window"""
-    bad = (C.c_int * 2)()
+def verify_div(spacing: float, n: int, stride: int = 1, with_multiply: bool = False):
+    """(one-step division exact, two-step division exact[, the multiply by the reciprocal alone exact]) over every
+    `stride`-th ingress of the hot window"""
+    bad = (C.c_int * 3)()
     lib().doh_verify_div(float(spacing), int(n), int(stride), bad)
-    return bad[0] == 0, bad[1] == 0
+    return (bad[0] == 0, bad[1] == 0, bad[2] == 0) if with_multiply else (bad[0] == 0, bad[1] == 0)
 
 
 class HostCube:

@@ -261,6 +261,24 @@ def test_march_on_host_random_grids_and_marches(seed):
         c.free()
 
 
+def test_power_of_two_spacing_divides_by_one_multiply(cube1):
+    """div_spacing<3>: for a spacing that is a power of two (the reference's own cubes: 0.5 R_E) the multiply by the
+    reciprocal IS the division for every ingress of the window, and for no other spacing; the march with it (config-1
+    cube, lean and general, nearest too) equals the oracle"""
+    for sp, want in ((0.5, True), (0.25, True), (2.0, True), (0.3137255, False), (0.1, False), (1.0 / 3.0, False)):
+        assert D.verify_div(np.float32(sp), 161, stride=61, with_multiply=True)[2] == want, sp
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    c = D.HostCube(zyx, org, sp, divmode=3)
+    for tri in (True, False):
+        want = O.orc_render_cube(zyx, org, sp, tri, fo, W, H)
+        for span in ((2, 1, 0) if tri else (1, 0)):
+            got, _, st = c.render(fp, W, H, trilinear=tri, fetch=5, span=span)
+            assert st == 0
+            assert_bit_exact(got, want, f"divmode 3, tri={tri}, span={span}")
+    c.free()
+
+
 def test_lean_march_on_host_equals_oracle(cube1):
     """BIRP_LEAN_MARCH (opt-in): fp32 cell index and no range test in the scale, on a positive cube whose values scale
     well inside the normal fp32 range -- same images bit for bit, on the reference test cube's shape and on a grid with

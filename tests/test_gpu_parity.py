@@ -88,7 +88,7 @@ def test_render_config1_bit_exact(dev_cube1, dev_cube1_neg, cube1, cube1_neg, tr
 # (flags 0 = the lean span march on a positive cube of at most 2^24 voxels, NO_LEAN_MARCH = the general span march)
 _FETCH = [0, capi.NO_LEAN_MARCH, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.TEXTURE_ONLY,
           capi.NO_QUADS | capi.NO_TEXTURE]
-_DIV = [0, capi.DIV_TWO_STEP, capi.DIV_IEEE]
+_DIV = [0, capi.DIV_ONE_STEP, capi.DIV_TWO_STEP, capi.DIV_IEEE]  # (cube1's spacing is 0.5: default = the multiply alone)
 _LERP = [0, capi.GENERAL_LERP]
 
 
@@ -111,7 +111,7 @@ def test_upload_analysis(dev_cube1, dev_cube1_neg, gpu):
     assert a["texture"] and b["texture"], "layered-texture copy missing or failed its gather self-check"
     assert a["quads"] and b["quads"], "quad copy missing or failed its self-check"
     assert a["octs"] and b["octs"], "oct copy missing or failed its self-check"
-    assert a["divmode"] in (0, 1, 2) and a["divmode"] == b["divmode"]
+    assert a["divmode"] == 3 == b["divmode"], "spacing 0.5: the multiply by the exact reciprocal is the division"
     print("division variant proven exact for spacing 0.5:", a["divmode"])
     # awkward spacings: whatever variant is chosen, the renders must stay bit-exact
     rng = np.random.default_rng(9)

@@ -17,15 +17,36 @@ fp = capi.frames_for_poses(poses, S.DEFAULT_AIM_X, 27., 16., W, H)
 fo = O.orc_frames(poses, S.DEFAULT_AIM_X, 27., 16., W, H)
 zyx, org, sp = S.make_cube(41, 37, 45, negative_slab=False)
 zyx0 = zyx.copy()
-zyx0[10:20] = 0.0  # a non-negative cube (lerp_nonneg)
-for grid in (zyx, zyx0):
+zyx0[10:20] = 0.0  # a non-negative cube (sign-marked oct records, lerp_nonneg)
+zyxn = S.make_cube(41, 37, 45, negative_slab=True)[0]  # negative voxels (NaN-marked records, marked poly cells)
+for grid in (zyx, zyx0, zyxn):
     c = capi.Cube(grid, org, sp)
     for tri in (False, True):
         for fl in (0, capi.NO_LEAN_MARCH, capi.NO_OCTS, capi.WINDOW_PER_STEP, capi.NO_QUADS, capi.NO_QUADS | capi.NO_TEXTURE, capi.TEXTURE_ONLY,
-                   capi.GENERAL_LERP, capi.DIV_IEEE):
+                   capi.GENERAL_LERP, capi.DIV_IEEE, capi.DIV_ONE_STEP, capi.DIV_TWO_STEP):
             got = c.render(fp, W, H, trilinear=tri, extra_flags=fl)
             want = O.orc_render_cube(grid, org, sp, tri, fo, W, H)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (tri, fl)
+    # the tolerance-mode march: every index-rounding variant, computed and table-read step distances, the warp-per-ray
+    # experiment, lanes in 2x2 blocks
+    for v in (0, 1, 2, 3, 4):
+        for ks in (1, 0):
+            capi.set_tuning("fast_variant", v)
+            capi.set_tuning("fast_kstep", ks)
+            c.render(fp, W, H, trilinear=True, extra_flags=capi.FAST_MARCH)
+    capi.set_tuning("fast_variant", -1)
+    capi.set_tuning("fast_kstep", 1)
+    for knob in ("fast_coop", "tile_swizzle"):
+        capi.set_tuning(knob, 1)
+        c.render(fp, W, H, trilinear=True, extra_flags=capi.FAST_MARCH)
+        c.render(fp, W, H, trilinear=True)
+        capi.set_tuning(knob, 0)
+    c.render(fp, W, H, nsamples=3000, trilinear=True, extra_flags=capi.FAST_MARCH)
+    for ph in range(3):  # interleaved row bands, strided sweep output
+        capi.render_cube_rows(c, fp, W, H, 8, ph, 3)
+    both = np.zeros((len(poses), H, W), np.float32)
+    for r in range(2):
+        capi.render_sweep(c, poses[r::2], S.DEFAULT_AIM_X, 27., 16., W, H, out=both, frame_offset=r, frame_stride=2)
     c.render(fp, W, H, nsamples=3000, trilinear=True)  # march longer than the staged ray table
     c.sample(np.random.rand(1000, 3) * 80 - 40, True)
     got = capi.render_sweep(c, poses, S.DEFAULT_AIM_X, 27., 16., W, H)
