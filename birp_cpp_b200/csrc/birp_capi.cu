@@ -322,9 +322,11 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
     if (plan.feed && plan.feed_chunk) chunk = plan.feed_chunk < chunk ? plan.feed_chunk : chunk;
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)nframes) chunk = nframes;
-    // a sweep: a small first chunk, so that the GPU starts after the host set-up of a few frames instead of a quarter
-    // of the sweep (what stays exposed end to end is the first chunk's set-up + H2D and the last chunk's D2H)
-    const size_t first_chunk = (sweep && !plan.feed && chunk >= 512) ? chunk / 8 : chunk;
+    // a batch of many frames: a small FIRST chunk, so that the GPU starts after the host set-up / H2D of a few frames
+    // instead of a quarter of the batch, and a small LAST one, whose D2H is the piece nothing overlaps -- at 8 GPUs the
+    // last chunks of all ranks drain at the same time through the box's ~94 GB/s of aggregate D2H bandwidth
+    // (tools/d2h_aggregate.py), so a quarter of the sweep there was 0.7 ms of a 3.5 ms step
+    const size_t first_chunk = (!plan.feed && chunk >= 128) ? (chunk / 8 > 32 ? chunk / 8 : 32) : chunk;
     rc = ensure(&c->d_frames, &c->frames_cap, (size_t)nframes);
     if (rc) return rc;
     for (int b = 0; b < 2; ++b) {
@@ -1137,9 +1139,10 @@ static int sweep_multi(int ndevices, const int* devices, int nframes, int W, int
     std::atomic<long long> feed{0};
     HostPlan plan;
     plan.feed = &feed;
-    // a chunk per grab: about four grabs per device (balance against kernel tails), at least 64 frames
-    size_t chunk = ((size_t)nframes + (size_t)ndevices * 4 - 1) / ((size_t)ndevices * 4);
-    if (chunk < 64) chunk = 64;
+    // a chunk per grab: about eight grabs per device (dynamic balance, and a short last chunk per device: the last
+    // chunks of all devices drain together through the box's aggregate D2H bandwidth), at least 32 frames
+    size_t chunk = ((size_t)nframes + (size_t)ndevices * 8 - 1) / ((size_t)ndevices * 8);
+    if (chunk < 32) chunk = 32;
     plan.feed_chunk = chunk;
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 4;

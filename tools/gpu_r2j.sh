@@ -7,7 +7,7 @@ timeout 300 python -m pytest tests/test_multi_gpu.py -m gpu -x -q > gpurun_out/$
 tail -3 gpurun_out/${tag}_pytest_${N}gpu.log
 timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/d2h_aggregate.py > gpurun_out/${tag}_d2h_aggregate_${N}gpu.json 2> gpurun_out/${tag}_d2h_aggregate_${N}gpu.err
 cat gpurun_out/${tag}_d2h_aggregate_${N}gpu.json; tail -2 gpurun_out/${tag}_d2h_aggregate_${N}gpu.err
-for spec in "orbit:0" "hires512x4k:0" "cmem:0"; do
+for spec in "orbit:0" "hires512x4k:0" "orbit:32768"; do
 w=${spec%%:*}; fl=${spec#*:}
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --workload $w --extra-flags $fl > gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.json 2> gpurun_out/${tag}_bench_${w}_flags${fl}_${N}gpu.err; echo "bench $w $fl rc=$?"
 python - <<PY
