@@ -413,7 +413,7 @@ def run_b200(args, wl, name):
         my_rows = rows[1] - rows[0]
         counts = [1] * world
         if world > 1 and os.environ.get("BIRP_GATHER", "peer") == "peer":
-            # one image over the GPUs in INTERLEAVED bands of 32 rows (rank r: bands r, r + N, ...): every rank gets the
+            # one image over the GPUs in INTERLEAVED bands of ROW_BAND rows (rank r: bands r, r + N, ...): every rank gets the
             # same mix of cheap rows (rays that leave the cube early) and expensive ones
             interleave = (ROW_BAND, rank, world)
             my_rows = sum(r1 - r0 for r0, r1 in sharding.interleaved_row_bands(H, ROW_BAND, world, rank))
