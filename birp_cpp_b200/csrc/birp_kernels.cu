@@ -31,7 +31,10 @@ namespace {
 
 std::atomic<unsigned long long> g_launches{0};
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef BIRP_WARPS_PER_BLOCK
+#define BIRP_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = BIRP_WARPS_PER_BLOCK;  // A/B builds only (tools/scratch): 4 and 2 measured no faster
 constexpr int kFastVariantDefault = 2;  // fast_sample<VARIANT> of the tolerance-mode march (see birp_device.cuh)
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
