@@ -93,6 +93,7 @@ struct DeviceCtx {
     };
     std::map<std::string, CmemState> cmem_state;
     int tile_w_log2 = -1;     // BIRP_TILE_W_LOG2 override (experiments)
+    int cta_warps = 0;        // warps per CTA, 0 = by frame size (experiments: birp_set_tuning("cta_warps", 2 | 4 | 8))
     int tile_swizzle = 0;     // BIRP_TILE_SWIZZLE override (experiments)
     int fast_variant = -1;    // BIRP_FAST_VARIANT override (experiments)
     int fast_coop = 0;        // experiment: warp-per-ray tolerance-mode march
@@ -453,6 +454,7 @@ int render_host(DeviceCtx* c, const birp_frame* frames, int nframes, int W, int 
             g.tile_w_log2 = c->tile_w_log2;
             g.fast_variant = c->fast_variant;
             g.tile_swizzle = c->tile_swizzle;
+            g.cta_warps = c->cta_warps;
             g.fast_kstep = c->fast_kstep;
             g.fast_coop = c->fast_coop;
             g.fast_step = table.step;
@@ -1361,6 +1363,7 @@ static int cube_device_launch(const birp_cube* cube, const birp_frame* d_frames,
     g.tile_w_log2 = c->tile_w_log2;
     g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
+    g.cta_warps = c->cta_warps;
     g.fast_kstep = c->fast_kstep;
     g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
@@ -1402,6 +1405,7 @@ int birp_render_cmem_device_strided(const birp_cmem_params* params, const birp_f
     g.tile_w_log2 = c->tile_w_log2;
     g.fast_variant = c->fast_variant;
     g.tile_swizzle = c->tile_swizzle;
+    g.cta_warps = c->cta_warps;
     g.fast_kstep = c->fast_kstep;
     g.fast_coop = c->fast_coop;
     g.fast_step = table.step;
@@ -1551,6 +1555,7 @@ int birp_set_tuning(const char* name, int value) {
     const std::string n(name);
     if (n == "tile_w_log2") c->tile_w_log2 = value;
     else if (n == "tile_swizzle") c->tile_swizzle = value;
+    else if (n == "cta_warps") c->cta_warps = value;
     else if (n == "fast_variant") c->fast_variant = value;
     else if (n == "fast_kstep") c->fast_kstep = value;
     else if (n == "fast_coop") c->fast_coop = value;

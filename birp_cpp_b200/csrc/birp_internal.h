@@ -23,6 +23,7 @@ struct RenderGeom {
     // index = row_phase (mod row_nphases) are rendered (row_band = 0 or row_nphases = 1: all rows)
     int row_band = 0, row_phase = 0, row_nphases = 1;
     int tile_swizzle = 0;  // lanes in 2x2 pixel blocks (MarchArgs::swizzle)
+    int cta_warps = 0;     // warps per CTA: 2, 4 or 8; 0 = chosen from the frame size (pick_cta_warps)
     // maxdist / nsamples when the ray table is the uniform one of Camera::GenerateRayDistWidth (else 0): the
     // tolerance-mode march may then compute the distance of a step instead of reading it; fast_kstep = 0 forbids that
     double fast_step = 0.0;

@@ -31,10 +31,8 @@ namespace {
 
 std::atomic<unsigned long long> g_launches{0};
 
-#ifndef BIRP_WARPS_PER_BLOCK
-#define BIRP_WARPS_PER_BLOCK 8
-#endif
-constexpr int kWarpsPerBlock = BIRP_WARPS_PER_BLOCK;  // A/B builds only (tools/scratch): 4 and 2 measured no faster
+// The LARGEST CTA (the launch bound).  A launch uses 8 warps per CTA, 4 for very large images (pick_cta_warps).
+constexpr int kWarpsPerBlock = 8;
 constexpr int kFastVariantDefault = 2;  // fast_sample<VARIANT> of the tolerance-mode march (see birp_device.cuh)
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 
@@ -51,6 +49,7 @@ struct MarchArgs {
     // [row_begin, row_end).  `rows` counts the rows of this launch's own bands, row_end bounds the last one.
     int row_band, row_phase, row_nphases, row_end;
     int nsamples;
+    int cta_warps;    // warps per CTA of this launch (blockDim.x / 32)
     int tile_w_log2;  // a warp's 32 rays form a (1 << tile_w_log2) x (32 >> tile_w_log2) pixel tile
     int swizzle;      // lanes 4n .. 4n+3 own a 2x2 pixel block of the tile instead of four pixels of one row
     int tiles_x, tiles_per_frame;
@@ -77,7 +76,7 @@ struct CmemField {
 // Which ray this lane owns; false when the lane falls outside the image / row band.
 __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int& j) {
     const int lane = threadIdx.x & 31;
-    const long long tile = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long tile = (long long)blockIdx.x * a.cta_warps + (threadIdx.x >> 5);
     if (tile >= a.total_tiles) return false;
     f = (int)(tile / a.tiles_per_frame);
     const int t = (int)(tile - (long long)f * a.tiles_per_frame);
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     __shared__ float s_dist[kSmemDist + 1];  // + the look-ahead padding entry
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
     const int first_chunk = min(kSmemDist, a.nsamples);
-    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    for (int k = threadIdx.x; k < first_chunk; k += blockDim.x) s_dist[k] = __ldg(a.dist + k);
     if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
     __syncthreads();
     CubeView cc = c;
@@ -237,7 +236,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_CUBE_MIN_BLOCKS) march_cub
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
         __syncthreads();
-        for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
+        for (int k = threadIdx.x; k < chunk; k += blockDim.x) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
             nlive4 += (SPAN ? march_steps_span<TRILINEAR, DIVMODE, LERP, FETCH, SPAN == 2>(cc, r, s_base, s_base + 4u * chunk,
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
     __shared__ float s_dist[kSmemDist + 1];
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
     const int first_chunk = min(kSmemDist, a.nsamples);
-    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    for (int k = threadIdx.x; k < first_chunk; k += blockDim.x) s_dist[k] = __ldg(a.dist + k);
     if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
     __syncthreads();
     CubeView cc = c;
@@ -301,7 +300,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
     for (int base = kSmemDist; base < a.nsamples; base += kSmemDist) {
         const int chunk = min(kSmemDist, a.nsamples - base);
         __syncthreads();
-        for (int k = threadIdx.x; k < chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + base + k);
+        for (int k = threadIdx.x; k < chunk; k += blockDim.x) s_dist[k] = __ldg(a.dist + base + k);
         __syncthreads();
         if (alive)
             nlive4 += march_steps_fast<SIGNS, VARIANT, KSTEP>(cc, r, q, s_base, s_base + 4u * chunk, ray_width, a.status, alive,
@@ -327,7 +326,7 @@ __global__ void __launch_bounds__(kBlockThreads, BIRP_FAST_MIN_BLOCKS) march_cub
     __shared__ float s_dist[kSmemDist + 1];
     const unsigned s_base = (unsigned)__cvta_generic_to_shared(s_dist);
     const int first_chunk = min(kSmemDist, a.nsamples);
-    for (int k = threadIdx.x; k < first_chunk; k += kBlockThreads) s_dist[k] = __ldg(a.dist + k);
+    for (int k = threadIdx.x; k < first_chunk; k += blockDim.x) s_dist[k] = __ldg(a.dist + k);
     if (threadIdx.x == 0) s_dist[kSmemDist] = 0.f;
     __syncthreads();
     CubeView cc = c;
@@ -414,6 +413,16 @@ __global__ void __launch_bounds__(256) pack_poly_kernel(const float* __restrict_
 // Tile shape: split the warp's 32 rays so that the tile is as square as possible in ANGLE
 // (the SXI pixel is 1.7x wider than tall once the reference's extra aspect factor is applied):
 // compact ray bundles touch fewer cache lines per corner load.
+// Warps per CTA.  Measured with tools/ab_rows.py (profiles/r2m_ab_rows_*.json: separate builds; profiles/r2n_ab_rows_*.json:
+// this launch-time choice), 8 / 4 / 2 warps: one 4096^2 image of the 512^3 cube 7.09 / 7.09 / 7.21 ms (separate builds:
+// 7.13 / 6.99 / 7.09), one rank's eighth of it 0.924 / 0.918 / 0.940 ms (tolerance mode 0.510 / 0.502 / 0.574); a 512^2
+// image 0.158 / 0.164 / 0.173 ms; the orbit sweep of 64 x 108 frames 27.57 / 27.67 / 27.79 ms.  So: 4 warps for frames of
+// half a million rays and more (a CTA's slot is refilled only when its slowest warp is done), 8 otherwise -- a 1-2 % matter.
+int pick_cta_warps(const RenderGeom& g, int tiles_per_frame) {
+    if (g.cta_warps == 2 || g.cta_warps == 4 || g.cta_warps == 8) return g.cta_warps;
+    return tiles_per_frame >= 16384 ? 4 : kWarpsPerBlock;  // >= 2^19 rays of one frame in this launch
+}
+
 int pick_tile_w_log2(const RenderGeom& g) {
     if (g.tile_w_log2 >= 0 && g.tile_w_log2 <= 5) return g.tile_w_log2;
     // default: the reference ties the image size to the field of view (W ~ fov_w / px,
@@ -467,7 +476,8 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.fast_step = 0.0;
     a.out_offset = g.out_frame_offset;
     a.out_stride = g.out_frame_stride;
-    const long long nb = (a.total_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    a.cta_warps = pick_cta_warps(g, a.tiles_per_frame);
+    const long long nb = (a.total_tiles + a.cta_warps - 1) / a.cta_warps;
     *blocks = (unsigned)nb;
     return nb <= 0x7fffffffLL;
 }
@@ -481,14 +491,14 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
     if (!fill_args(a, d_frames, g, d_dist, flags, d_images, d_valid, d_status, &blocks))
         return cudaErrorInvalidConfiguration;
     if (a.total_tiles <= 0) return cudaSuccess;
-    march_kernel<Field><<<blocks, kBlockThreads, 0, stream>>>(a, field);
+    march_kernel<Field><<<blocks, a.cta_warps * 32, 0, stream>>>(a, field);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 
 template <bool TRI, int DIV, int LERP, int FETCH, int SPAN>
 cudaError_t launch_cube_variant(const MarchArgs& a, const CubeView& c, unsigned blocks, cudaStream_t stream) {
-    march_cube_kernel<TRI, DIV, LERP, FETCH, SPAN><<<blocks, kBlockThreads, 0, stream>>>(a, c);
+    march_cube_kernel<TRI, DIV, LERP, FETCH, SPAN><<<blocks, a.cta_warps * 32, 0, stream>>>(a, c);
     return cudaGetLastError();
 }
 
@@ -1004,13 +1014,13 @@ cudaError_t launch_render_cube(const CubeView& cube, const birp_frame* d_frames,
         const bool kstep = g.fast_step > 0.0 && g.fast_kstep != 0;
         a.fast_step = kstep ? g.fast_step : 0.0;
         if (g.fast_coop && kstep && !signs && variant != 0 && a.nsamples <= kSmemDist) {  // (experiment, see the kernel)
-            march_cube_fast_coop_kernel<2><<<blocks, kBlockThreads, 0, stream>>>(a, cube);
+            march_cube_fast_coop_kernel<2><<<blocks, a.cta_warps * 32, 0, stream>>>(a, cube);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             return cudaGetLastError();
         }
 #define BIRP_FAST_LAUNCH(S, V)                                                                       \
-    if (kstep) march_cube_fast_kernel<S, V, true><<<blocks, kBlockThreads, 0, stream>>>(a, cube);   \
-    else march_cube_fast_kernel<S, V, false><<<blocks, kBlockThreads, 0, stream>>>(a, cube)
+    if (kstep) march_cube_fast_kernel<S, V, true><<<blocks, a.cta_warps * 32, 0, stream>>>(a, cube);   \
+    else march_cube_fast_kernel<S, V, false><<<blocks, a.cta_warps * 32, 0, stream>>>(a, cube)
 #define BIRP_FAST_VARIANTS(S)                       \
     switch (variant) {                              \
         case 0: BIRP_FAST_LAUNCH(S, 0); break;      \

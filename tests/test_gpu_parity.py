@@ -497,8 +497,50 @@ def assert_fast_parity(got, want, what):
 def tuning(gpu):
     """birp_set_tuning with the defaults restored afterwards"""
     yield capi.set_tuning
-    for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0)):
+    for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0),
+                 ("cta_warps", 0)):
         capi.set_tuning(k, v)
+
+
+@pytest.mark.parametrize("warps", [2, 4, 8])
+def test_cta_size_does_not_change_a_bit(dev_cube1, cube1, tuning, warps):
+    """the launch picks 8 warps per CTA for many small frames and 4 for large images (pick_cta_warps): every size
+    renders the same bits -- trilinear, nearest, tolerance mode, interleaved row bands, and CMEM"""
+    zyx, org, sp = cube1
+    fp, fo = frames_pair(POSES, S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    tuning("cta_warps", 0)
+    auto = {tri: dev_cube1.render(fp, W, H, trilinear=tri) for tri in (True, False)}
+    auto_fast = dev_cube1.render(fp, W, H, trilinear=True, extra_flags=FAST)
+    P = capi.cmem_init()
+    auto_cmem = capi.render_cmem(P, fp, W, H)
+    tuning("cta_warps", warps)
+    for tri in (True, False):
+        got = dev_cube1.render(fp, W, H, trilinear=tri)
+        assert_bit_exact(got, O.orc_render_cube(zyx, org, sp, tri, fo, W, H))
+        assert_bit_exact(got, auto[tri])
+    assert_bit_exact(dev_cube1.render(fp, W, H, trilinear=True, extra_flags=FAST), auto_fast)
+    assert_bit_exact(capi.render_cmem(P, fp, W, H), auto_cmem)
+    bands = np.full_like(auto[True], -7.0)
+    for ph in range(3):
+        capi.render_cube_rows(dev_cube1, fp, W, H, 8, ph, 3, out=bands)
+    assert_bit_exact(bands, auto[True])
+
+
+def test_large_image_takes_the_small_cta_and_stays_bit_exact(gpu, tuning):
+    """a 1024 x 576 image is above the frame size where the launch switches to 4 warps per CTA: compared with the oracle
+    and with the forced 8-warp launch"""
+    zyx, org, sp = S.make_cube(48, 40, 44)
+    poses = np.array([S.DEFAULT_POS], np.float32)
+    Wl, Hl = 1024, 576
+    fp, fo = frames_pair(poses, 36.0, 20.25, Wl, Hl)
+    dev = capi.Cube(zyx, org, sp)
+    try:
+        got = dev.render(fp, Wl, Hl, trilinear=True)
+        assert_bit_exact(got, O.orc_render_cube(zyx, org, sp, True, fo, Wl, Hl))
+        tuning("cta_warps", 8)
+        assert_bit_exact(dev.render(fp, Wl, Hl, trilinear=True), got)
+    finally:
+        dev.free()
 
 
 @pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4])

@@ -90,7 +90,7 @@ def main():
     ref = None
     img = np.empty((len(poses), H, W), np.float32)
     def tune(knobs):
-        for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0)):
+        for k, v in (("fast_variant", -1), ("fast_kstep", 1), ("tile_swizzle", 0), ("tile_w_log2", -1), ("fast_coop", 0), ("cta_warps", 0)):
             capi.set_tuning(k, v)
         for k, v in knobs:
             capi.set_tuning(k, v)

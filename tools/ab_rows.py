@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--cube", type=int, default=512)
     ap.add_argument("--image", type=int, default=4096)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--nsamples", type=int, default=200)
+    ap.add_argument("--warps", type=int, default=0, help="birp_set_tuning('cta_warps'): 2, 4, 8; 0 = the library's choice")
     args = ap.parse_args()
     t0 = time.perf_counter()
     from ab_quick import cudart
@@ -40,6 +42,7 @@ def main():
     rt.cudaMemset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
     capi.lib()
     capi.set_device(0)
+    capi.set_tuning("cta_warps", args.warps)
     n, W = args.cube, args.image
     H = W
     zyx, org, sp = S.make_cube(n, n, n)
@@ -75,18 +78,20 @@ def main():
         capi.check_device_status(0)
         return {"ms_min": round(min(ms), 4), "ms_mean": round(float(np.mean(ms)), 4)}
 
-    out = {"lib": str(capi.LIB_PATH), "cube": n, "image": W, "nphases": args.nphases, "flags": args.flags}
+    out = {"lib": str(capi.LIB_PATH), "cube": n, "image": W, "nphases": args.nphases, "flags": args.flags,
+           "nsamples": args.nsamples, "cta_warps": args.warps}
     whole = np.empty((H, W), np.float32)
     out["whole"] = timed(lambda: capi.render_cube_device(cube, d_frames.ptr, 1, W, H, d_img.ptr, trilinear=True, stream=0,
-                                                         extra_flags=args.flags))
+                                                         extra_flags=args.flags, nsamples=args.nsamples))
     ck(rt.cudaMemcpy(whole.ctypes.data, d_img.ptr, whole.nbytes, 2), "D2H")
     for band in [int(b) for b in args.bands.split(",")]:
         ck(rt.cudaMemset(d_img.ptr, 0, whole.nbytes), "clear")
         r = timed(lambda: capi.render_cube_device_rows(cube, d_frames.ptr, 1, W, H, d_img.ptr, band, 0, args.nphases,
-                                                       trilinear=True, stream=0, extra_flags=args.flags))
+                                                       trilinear=True, stream=0, extra_flags=args.flags,
+                                                       nsamples=args.nsamples))
         for ph in range(1, args.nphases):
             capi.render_cube_device_rows(cube, d_frames.ptr, 1, W, H, d_img.ptr, band, ph, args.nphases, trilinear=True,
-                                         stream=0, extra_flags=args.flags)
+                                         stream=0, extra_flags=args.flags, nsamples=args.nsamples)
         got = np.empty_like(whole)
         ck(rt.cudaMemcpy(got.ctypes.data, d_img.ptr, got.nbytes, 2), "D2H")
         r["shares_equal_whole"] = bool(np.array_equal(got.view(np.uint32), whole.view(np.uint32)))

@@ -36,6 +36,12 @@ for grid in (zyx, zyx0, zyxn):
             c.render(fp, W, H, trilinear=True, extra_flags=capi.FAST_MARCH)
     capi.set_tuning("fast_variant", -1)
     capi.set_tuning("fast_kstep", 1)
+    for warps in (2, 4):  # CTA sizes (8 is the default for frames of this size)
+        capi.set_tuning("cta_warps", warps)
+        c.render(fp, W, H, trilinear=True, extra_flags=capi.FAST_MARCH)
+        c.render(fp, W, H, trilinear=True)
+        c.render(fp, W, H, trilinear=False)
+    capi.set_tuning("cta_warps", 0)
     for knob in ("fast_coop", "tile_swizzle"):
         capi.set_tuning(knob, 1)
         c.render(fp, W, H, trilinear=True, extra_flags=capi.FAST_MARCH)
