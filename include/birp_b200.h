@@ -346,8 +346,10 @@ unsigned long long birp_launch_count(void);
    every code variant (results never depend on them beyond what the flags document): "tile_w_log2" (-1 = choose; a
    warp's 32 rays form a 2^v x 2^(5-v) pixel tile), "tile_swizzle" (1: four consecutive lanes own a 2x2 pixel block),
    "fast_variant" (-1 = default; 0..4: how the tolerance-mode march rounds its cell index, see fast_sample),
-   "fast_kstep" (0: the tolerance-mode march reads the ray table instead of computing step distances).  The same
-   knobs are read from the environment (BIRP_TILE_W_LOG2, BIRP_TILE_SWIZZLE, BIRP_FAST_VARIANT, BIRP_FAST_KSTEP)
+   "fast_kstep" (0: the tolerance-mode march reads the ray table instead of computing step distances), "fast_coop" (1:
+   the warp-per-ray experiment), "cta_warps" (0 = choose: 4 warps per CTA for frames of 2^19 rays and more, else 8;
+   2 | 4 | 8 force it).  The first four
+   knobs are also read from the environment (BIRP_TILE_W_LOG2, BIRP_TILE_SWIZZLE, BIRP_FAST_VARIANT, BIRP_FAST_KSTEP)
    when the device context is created. */
 int birp_set_tuning(const char* name, int value);
 
