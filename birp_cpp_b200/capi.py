@@ -106,6 +106,7 @@ SIGNATURES = {
     "birp_peer_wait": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
     "birp_check_device_status": (C.c_int, [_vp]),
     "birp_selftest_cmem_math": (C.c_int, [C.c_long, _vp]),
+    "birp_selftest_div10": (C.c_int, [_vp]),
     "birp_selftest_cmem_filter": (C.c_int, [_vp, C.c_long, _vp]),
     "birp_selftest_cmem_table": (C.c_int, [_vp, C.c_long, _vp]),
     "birp_launch_count": (C.c_ulonglong, []),
@@ -560,6 +561,13 @@ def selftest_cmem_math(n: int = 1 << 22) -> dict:
     out = np.zeros(6, dtype=np.float64)
     _check(lib().birp_selftest_cmem_math(n, _ptr(out)))
     return dict(zip(("exp2", "log2", "pow", "exp", "acos", "angle"), out.tolist()))
+
+
+def selftest_div10() -> tuple[int, int]:
+    """(patterns where the kernel's r / 10 differs from the IEEE division, patterns where the bare multiplication form would)"""
+    out = np.zeros(2, dtype=np.uint64)
+    _check(lib().birp_selftest_div10(_ptr(out)))
+    return int(out[0]), int(out[1])
 
 
 def selftest_cmem_filter(params: np.ndarray, n: int = 1 << 24) -> dict:

@@ -134,6 +134,7 @@ int get_ctx(DeviceCtx** out) {
     if (const char* t = getenv("BIRP_TILE_SWIZZLE")) c->tile_swizzle = atoi(t);
     if (const char* t = getenv("BIRP_FAST_VARIANT")) c->fast_variant = atoi(t);
     if (const char* t = getenv("BIRP_FAST_KSTEP")) c->fast_kstep = atoi(t);
+    if (const char* t = getenv("BIRP_CTA_WARPS")) c->cta_warps = atoi(t);
     g_ctx[dev] = c;
     *out = c;
     return BIRP_OK;
@@ -1504,6 +1505,23 @@ int birp_selftest_cmem_math(long n, double max_err[6]) {
     cudaError_t e = birp::launch_cmem_math_selftest(n, d_err, c->compute);
     if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     BIRP_CUDA(cudaMemcpyAsync(max_err, d_err, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->compute));
+    BIRP_CUDA(cudaStreamSynchronize(c->compute));
+    return BIRP_OK;
+}
+
+int birp_selftest_div10(unsigned long long mismatches[2]) {
+    if (!mismatches) return set_error(BIRP_ERR_ARG, "bad arguments");
+    DeviceCtx* c;
+    int rc = get_ctx(&c);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure(&c->d_scratch, &c->scratch_cap, (size_t)16);
+    if (rc) return rc;
+    unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->d_scratch);
+    BIRP_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), c->compute));
+    cudaError_t e = birp::launch_div10_selftest(d_bad, c->compute);
+    if (e != cudaSuccess) return set_error(BIRP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    BIRP_CUDA(cudaMemcpyAsync(mismatches, d_bad, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->compute));
     BIRP_CUDA(cudaStreamSynchronize(c->compute));
     return BIRP_OK;
 }

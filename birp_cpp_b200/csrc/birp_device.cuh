@@ -916,6 +916,7 @@ struct CmemDev {
     float p3dn, p3ds;                      // p3 * dn, p3 * ds       (:217)
     int same_flare;                        // ay_bs == az_bs: ShueModel's two powf calls coincide
     int q_nonpositive;                     // p2 * charlie <= 0: the cusp term of LinScaled can only lower the radius
+    int e_one;                             // expf(-B (theta/2)^4) rounds to 1.0f for EVERY theta in [0, pi] (see cmem_b1)
     // Region table of this parameter set (cmem_table_cell; nullptr: none): kCmemTableT bins over cos(theta) x
     // kCmemTableP bins over cos(phi), each {mp_lo, mp_hi, bs_lo, bs_hi}: a sample whose direction falls into the cell
     // and whose r is < mp_lo lies inside the magnetopause layer, with r > mp_hi outside it, with r < bs_lo inside the
@@ -951,6 +952,9 @@ inline CmemDev make_cmem_dev(const birp_cmem_params& P) {
     D.p3ds = p3ds;
     D.same_flare = (P.ay_bs == P.az_bs) ? 1 : 0;
     D.q_nonpositive = (p2c <= 0.f) ? 1 : 0;
+    // theta = RN32(acos q) <= RN32(pi), so (theta/2)^4 with its three roundings stays below 6.0881: when |B| * 6.0882 is
+    // below 2^-26 the argument of the expf of src/Cmem.cpp:157 is too, for every sample, and the exponential is 1.0f
+    D.e_one = ((double)fabsf(P.B) * 6.0882 < 1.4901161e-08) ? 1 : 0;
     D.table = nullptr;
     return D;
 }
@@ -1056,16 +1060,17 @@ __device__ __forceinline__ void cmem_cosines(float x, float y, float z, float& r
     q_p = (y != 0.f) ? __fdiv_rn(y, __fsqrt_rn(__fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z)))) : 1.f;
 }
 
-// b1 of src/Cmem.cpp:155-160: the magnetosheath emissivity, from the rounded theta and its fp32 sine
-__device__ __forceinline__ float cmem_b1(const birp_cmem_params& P, float r, float theta, float sin_t) {
-    const float h = __fdiv_rn(theta, 2.f);
-    const float h4 = __fmul_rn(__fmul_rn(__fmul_rn(h, h), h), h);
-    // expf(-B h^4): CMEM::Init overwrites B with |b| * 1e-9 (src/Cmem.cpp:310), so the argument is ~ -1e-8 and the
-    // correctly rounded result is 1.0f whenever |argument| < 2^-26 (e^x is then within a quarter ulp of 1)
-    const float ea = __fmul_rn(-P.B, h4);
-    const float e = (fabsf(ea) < 1.4901161e-08f) ? 1.0f : (float)cm::exp_d((double)ea);
-    const float pw = pow32(__fdiv_rn(r, 10.f), __fsub_rn(-P.alpha, __fmul_rn(P.beta, __fmul_rn(sin_t, sin_t))));
-    return __fmul_rn(__fmul_rn(P.A1, e), pw);
+// r / 10.f (src/Cmem.cpp:158,165) without the division: q0 = r * RN(1/10), the exact remainder r - 10 q0 (one FMA), one
+// correction step.  Compared with r / 10.f for EVERY fp32 r (birp_selftest_div10 on the device, and on the CPU):
+// identical for all r >= 2^-125 -- the 419 431 failures all lie in [2^-126, 2^-125), where the quotient is subnormal;
+// cmem_r_is_ordinary keeps it to [2^-100, 2^100).
+__device__ __forceinline__ float div10(float r) {
+    const float q0 = __fmul_rn(r, 0.1f);
+    return __fmaf_rn(__fmaf_rn(-q0, 10.f, r), 0.1f, q0);
+}
+// 2^-100 <= r < 2^100 (false for zero, negative, infinite, NaN): one integer compare
+__device__ __forceinline__ bool cmem_r_is_ordinary(float r) {
+    return (__float_as_uint(r) - 0x0D800000u) < 0x64000000u;
 }
 
 // 1 / c in fp64 to within an ulp or so: hardware seed (MUFU.RCP64H, ~20 bits) and three Newton steps, 7 instructions
@@ -1084,12 +1089,50 @@ __device__ __forceinline__ double rcp_newton(double c) {
 #endif
 }
 
+// expf(-B h^4) of src/Cmem.cpp:157.  CMEM::Init overwrites B with |b| * 1e-9 (:310), so the argument is ~ -1e-8 and the
+// correctly rounded result is 1.0f whenever |argument| < 2^-26 (e^x is then within a quarter ulp of 1).
+__device__ __forceinline__ float cmem_b1_exp(float B, float theta) {
+    const float h = __fdiv_rn(theta, 2.f);
+    const float h4 = __fmul_rn(__fmul_rn(__fmul_rn(h, h), h), h);
+    const float ea = __fmul_rn(-B, h4);
+    return (fabsf(ea) < 1.4901161e-08f) ? 1.0f : (float)cm::exp_d((double)ea);
+}
+
+// b1 and b2 (src/Cmem.cpp:155-173) for an r that is zero, tiny, huge, infinite or NaN: the literal forms, out of line
+// (no sample of a real render comes here; scalars by value, so that the parameter block need not be copied to the stack)
+#ifdef __CUDACC__
+#define BIRP_NOINLINE __noinline__
+#else
+#define BIRP_NOINLINE
+#endif
+static __device__ BIRP_NOINLINE float cmem_b1_odd_r(float A1, float B, float alpha, float beta, float r, float theta,
+                                                    float sin_t) {
+    const float pw = pow32(__fdiv_rn(r, 10.f), __fsub_rn(-alpha, __fmul_rn(beta, __fmul_rn(sin_t, sin_t))));
+    return __fmul_rn(__fmul_rn(A1, cmem_b1_exp(B, theta)), pw);
+}
+static __device__ BIRP_NOINLINE float cmem_b2_odd_r(float A2, float r) {
+    const double sd = (double)__fdiv_rn(r, 10.f);
+    return __double2float_rn(__dmul_rn((double)A2, __ddiv_rn(1.0, __dmul_rn(__dmul_rn(sd, sd), sd))));
+}
+
+// b1 of src/Cmem.cpp:155-160: the magnetosheath emissivity, from the rounded theta and its fp32 sine
+__device__ __forceinline__ float cmem_b1(const CmemDev& D, float r, float theta, float sin_t) {
+    const birp_cmem_params& P = D.P;
+    if (!cmem_r_is_ordinary(r)) return cmem_b1_odd_r(P.A1, P.B, P.alpha, P.beta, r, theta, sin_t);
+    // D.e_one: the exponential is 1.0f for every theta (known once per parameter set); a NaN theta reaches the result
+    // through sin_t all the same
+    const float e = D.e_one ? 1.0f : cmem_b1_exp(P.B, theta);
+    const float ex = __fsub_rn(-P.alpha, __fmul_rn(P.beta, __fmul_rn(sin_t, sin_t)));
+    // (r / 10 of an ordinary r is finite and positive: none of powf's special cases)
+    const float pw = (float)cm::pow_pos_d((double)div10(r), (double)ex);
+    return __fmul_rn(__fmul_rn(P.A1, e), pw);
+}
+
 // b2 of src/Cmem.cpp:162-173: beyond the magnetosheath, computed in double from the fp32 quotient r/10
 __device__ __forceinline__ float cmem_b2(const birp_cmem_params& P, float r) {
-    const double sd = (double)__fdiv_rn(r, 10.f);
-    const double cube = __dmul_rn(__dmul_rn(sd, sd), sd);
-    // (r finite and non-zero here: the cube of an fp32 quotient widened to fp64 neither overflows nor underflows)
-    return __double2float_rn(__dmul_rn((double)P.A2, (cube > 0.0 && cube < 1e300) ? rcp_newton(cube) : __ddiv_rn(1.0, cube)));
+    if (!cmem_r_is_ordinary(r)) return cmem_b2_odd_r(P.A2, r);
+    const double sd = (double)div10(r);  // (its cube neither overflows nor underflows in fp64)
+    return __double2float_rn(__dmul_rn((double)P.A2, rcp_newton(__dmul_rn(__dmul_rn(sd, sd), sd))));
 }
 
 // magnetopause (LinScaled, :188-222) and bow-shock (ShueModel, :280-288) radii in the sample's direction
@@ -1135,8 +1178,9 @@ __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float
 #define BIRP_CMEM_HALF_THICKNESS 0.025f /* 0.05f / 2, src/Cmem.cpp:133 */
 
 // the five regions of CMEM::GetSample (:135-176) for known radii
-__device__ __forceinline__ float cmem_regions(const birp_cmem_params& P, float r, float theta, float sin_t,
+__device__ __forceinline__ float cmem_regions(const CmemDev& D, float r, float theta, float sin_t,
                                               float radius_mp, float radius_bs) {
+    const birp_cmem_params& P = D.P;
     const float half_thickness = BIRP_CMEM_HALF_THICKNESS;
     const float mp_lo = __fsub_rn(radius_mp, half_thickness), mp_hi = __fadd_rn(radius_mp, half_thickness);
     const float bs_lo = __fsub_rn(radius_bs, half_thickness), bs_hi = __fadd_rn(radius_bs, half_thickness);
@@ -1148,7 +1192,7 @@ __device__ __forceinline__ float cmem_regions(const birp_cmem_params& P, float r
     const bool in_bs_layer = (r >= bs_lo && r <= bs_hi);
 
     float b1 = 0.f;
-    if (in_mp_layer || in_sheath || in_bs_layer) b1 = cmem_b1(P, r, theta, sin_t);
+    if (in_mp_layer || in_sheath || in_bs_layer) b1 = cmem_b1(D, r, theta, sin_t);
     if (in_mp_layer) {
         const float shue_norm = __fdiv_rn(__fsub_rn(r, mp_lo), mp_hi);
         return lerp_ref(0.f, b1, shue_norm);
@@ -1166,7 +1210,7 @@ __device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float
     float r, q_t, q_p, theta, sin_t, radius_mp, radius_bs;
     cmem_cosines(x, y, z, r, q_t, q_p);
     cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
-    return cmem_regions(D.P, r, theta, sin_t, radius_mp, radius_bs);
+    return cmem_regions(D, r, theta, sin_t, radius_mp, radius_bs);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1289,7 +1333,7 @@ __device__ __forceinline__ float cmem_sheath_value(const CmemDev& D, float x, fl
     if (!FASTVAL) {
         const float r_exact = vec_len3(x, y, z);
         const cm::Angle T = cm::angle_from_cosine((x != 0.f) ? __fdiv_rn(x, r_exact) : 1.f);
-        return cmem_b1(D.P, r_exact, T.a, (float)T.s);
+        return cmem_b1(D, r_exact, T.a, (float)T.s);
     }
     const birp_cmem_params& P = D.P;
     const float sin2 = (1.f - q_t) * (1.f + q_t);

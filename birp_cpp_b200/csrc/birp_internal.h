@@ -56,6 +56,7 @@ cudaError_t launch_frame_setup(const float* d_poses, int n, float aim_x, float t
                                float aspect, birp_frame* d_frames, int* d_status, cudaStream_t stream);
 cudaError_t launch_orbit_poses(int n, const double k[9], float* d_poses, cudaStream_t stream);
 cudaError_t launch_cmem_math_selftest(long n, unsigned long long* d_err6, cudaStream_t stream);
+cudaError_t launch_div10_selftest(unsigned long long* d_bad2, cudaStream_t stream);
 cudaError_t launch_cmem_filter_selftest(const birp_cmem_params& params, long n, unsigned long long* d_out3,
                                         cudaStream_t stream);
 cudaError_t launch_ray_directions(const birp_frame* d_frame, int W, int H, float* d_dirs, cudaStream_t stream);

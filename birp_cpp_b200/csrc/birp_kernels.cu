@@ -104,8 +104,15 @@ __device__ __forceinline__ bool lane_ray(const MarchArgs& a, int& f, int& i, int
 // Field::kScaleOnce: the raw samples are summed in fp32 and the scale of src/Camera.cpp:201 is applied to the sum (the
 // analytic field is a tolerance path -- its transcendentals are not glibc's -- so the order of the roundings is free;
 // a ray still ends at its first negative sample, whose sign is that of its scaled value for the positive ray width).
+// (no minimum of resident CTAs: ptxas then settles on 64 registers = 4 CTAs of 8 warps; A/B builds set BIRP_CMEM_MIN_BLOCKS
+// to 5 or 6, which caps the registers at 48 / 40 -- see profiles/README.md for what that measured)
+#ifdef BIRP_CMEM_MIN_BLOCKS
+#define BIRP_CMEM_LAUNCH_BOUNDS __launch_bounds__(kBlockThreads, BIRP_CMEM_MIN_BLOCKS)
+#else
+#define BIRP_CMEM_LAUNCH_BOUNDS __launch_bounds__(kBlockThreads)
+#endif
 template <class Field>
-__global__ void __launch_bounds__(kBlockThreads) march_kernel(const MarchArgs a, const Field field) {
+__global__ void BIRP_CMEM_LAUNCH_BOUNDS march_kernel(const MarchArgs a, const Field field) {
     int f, i, j;
     if (!lane_ray(a, f, i, j)) return;
     const birp_frame fr = a.frames[f];
@@ -1183,6 +1190,30 @@ cudaError_t launch_orbit_poses(int n, const double k[9], float* d_poses, cudaStr
     if (n <= 0) return cudaSuccess;
     orbit_poses_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(n, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7],
                                                               k[8], d_poses);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// div10 (birp_device.cuh) against the IEEE division for EVERY fp32 bit pattern: bad[0] counts the patterns where the form
+// the CMEM kernel uses -- div10 for an ordinary r, the division otherwise -- differs from r / 10.f, bad[1] the positive
+// normal r where div10 alone would (the subnormal quotients the range test keeps away from it)
+__global__ void __launch_bounds__(256) div10_selftest_kernel(unsigned long long* bad) {
+    unsigned long long n0 = 0, n1 = 0;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; u < (1ull << 32);
+         u += (unsigned long long)gridDim.x * blockDim.x) {
+        const float r = __uint_as_float((unsigned)u);
+        const unsigned want = __float_as_uint(__fdiv_rn(r, 10.f));
+        const unsigned fast = __float_as_uint(div10(r));
+        const bool nan_both = (r != r);  // any NaN payload is a NaN
+        if (!nan_both && (cmem_r_is_ordinary(r) ? fast : want) != want) ++n0;
+        if (u >= 0x00800000ull && u < 0x7f800000ull && fast != want) ++n1;  // positive normal r
+    }
+    if (n0) atomicAdd(bad + 0, n0);
+    if (n1) atomicAdd(bad + 1, n1);
+}
+
+cudaError_t launch_div10_selftest(unsigned long long* d_bad2, cudaStream_t stream) {
+    div10_selftest_kernel<<<148 * 16, 256, 0, stream>>>(d_bad2);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -328,6 +328,12 @@ int birp_check_device_status(void* stream);
    math library on n pseudo-random arguments */
 int birp_selftest_cmem_math(long n, double max_err[6]);
 
+/* diagnostics: the CMEM kernel takes r / 10 (src/Cmem.cpp:158,165) as a multiplication by RN(1/10) with one exact
+   correction step where r is in [2^-100, 2^100), and as the division elsewhere.  Compares that with the IEEE division
+   for EVERY fp32 bit pattern on the device: mismatches[0] = patterns where the kernel's form differs (must be 0),
+   mismatches[1] = positive normal r where the multiplication form alone would (419 431: the subnormal quotients) */
+int birp_selftest_div10(unsigned long long mismatches[2]);
+
 /* diagnostics of the CMEM region filter: out[0] / out[1] = the largest fraction of the filter's margin that
    the fp32 estimate of the magnetopause / bow-shock radius was off by, over n pseudo-random sample positions
    (must stay far below 1), out[2] = fraction of the positions whose direction the filter trusts */
@@ -348,8 +354,9 @@ unsigned long long birp_launch_count(void);
    "fast_variant" (-1 = default; 0..4: how the tolerance-mode march rounds its cell index, see fast_sample),
    "fast_kstep" (0: the tolerance-mode march reads the ray table instead of computing step distances), "fast_coop" (1:
    the warp-per-ray experiment), "cta_warps" (0 = choose: 4 warps per CTA for frames of 2^19 rays and more, else 8;
-   2 | 4 | 8 force it).  The first four
-   knobs are also read from the environment (BIRP_TILE_W_LOG2, BIRP_TILE_SWIZZLE, BIRP_FAST_VARIANT, BIRP_FAST_KSTEP)
+   2 | 4 | 8 force it).  Most of these
+   knobs are also read from the environment (BIRP_TILE_W_LOG2, BIRP_TILE_SWIZZLE, BIRP_FAST_VARIANT, BIRP_FAST_KSTEP,
+   BIRP_CTA_WARPS)
    when the device context is created. */
 int birp_set_tuning(const char* name, int value);
 

@@ -36,6 +36,11 @@ static inline unsigned __float_as_uint(float f) {
     std::memcpy(&u, &f, 4);
     return u;
 }
+static inline float __uint_as_float(unsigned u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -601,4 +601,20 @@ void doh_cmem_filter_decides(const birp_cmem_params* params, const float* xyz, l
     }
 }
 
+// r / 10 as the CMEM kernel takes it (div10 for an ordinary r, the division otherwise) against the division, for the
+// bit patterns first, first + stride, ... below last: bad[0] = mismatches of the kernel's form, bad[1] = of div10 alone
+void doh_div10_check(unsigned first, unsigned last, unsigned stride, unsigned long long bad[2]) {
+    unsigned long long n0 = 0, n1 = 0;
+    for (unsigned long long u = first; u < last; u += stride) {
+        const float r = __uint_as_float((unsigned)u);
+        const float want = r / 10.f;
+        const float fast = birp::div10(r);
+        const float used = birp::cmem_r_is_ordinary(r) ? fast : want;
+        if (want == want && __float_as_uint(used) != __float_as_uint(want)) ++n0;
+        if (want == want && __float_as_uint(fast) != __float_as_uint(want)) ++n1;
+    }
+    bad[0] = n0;
+    bad[1] = n1;
+}
+
 }  // extern "C"

@@ -36,6 +36,7 @@ def lib():
         L.doh_lerps.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp, _vp]
         L.doh_scale_exhaustive.argtypes = [C.c_int, C.c_uint, C.c_int, _vp]
         L.doh_sample_cmem.argtypes = [_vp, _vp, C.c_long, C.c_int, _vp]
+        L.doh_div10_check.argtypes = [C.c_uint, C.c_uint, C.c_uint, _vp]
         L.doh_cmem_filter_decides.argtypes = [_vp, _vp, C.c_long, _vp]
         L.doh_cmem_table.argtypes = [_vp, _vp]
         L.doh_sample_cmem_table.argtypes = [_vp, _vp, _vp, C.c_long, _vp, _vp]
@@ -162,6 +163,13 @@ def sample_cmem(params, xyz, mode=3):
     params = np.ascontiguousarray(params)
     lib().doh_sample_cmem(_p(params), _p(xyz), len(xyz), int(mode), _p(out))
     return out
+
+
+def div10_check(first_bits: int, last_bits: int, stride: int = 1):
+    """(mismatches of the kernel's r / 10, mismatches of the bare multiply-and-correct form) over a range of fp32 bit patterns"""
+    bad = np.zeros(2, np.uint64)
+    lib().doh_div10_check(first_bits, last_bits, stride, _p(bad))
+    return int(bad[0]), int(bad[1])
 
 
 def cmem_filter_decides(params, xyz):

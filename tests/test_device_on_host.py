@@ -338,6 +338,62 @@ def test_cmem_device_source_reproduces_the_reference_known_answers(kw, answers):
         assert_bit_exact(D.sample_cmem(P, pts, mode), want, f"mode {mode}")
 
 
+def test_cmem_division_by_ten_without_a_division():
+    """r / 10 (src/Cmem.cpp:158,165) as the kernel takes it -- multiply by RN(1/10), exact remainder, one correction;
+    the division itself outside [2^-100, 2^100) -- equals the division: every fp32 from 2^-10 to 2^10 (where radii
+    live), every 251st bit pattern of all the others, and all of the one binade where the bare form is wrong"""
+    f2u = lambda x: int(np.float32(x).view(np.uint32))
+    assert D.div10_check(f2u(2.0 ** -10), f2u(2.0 ** 10)) == (0, 0)
+    kernel_form, bare_form = D.div10_check(0, 0xFFFFFFFF, 251)
+    assert kernel_form == 0 and bare_form > 0  # (the bare form fails on subnormal quotients and on infinities)
+    kernel_form, bare_form = D.div10_check(f2u(2.0 ** -126), f2u(2.0 ** -125))
+    assert (kernel_form, bare_form) == (0, 419431)
+    assert D.div10_check(f2u(2.0 ** -125), f2u(2.0 ** -100), 7)[1] == 0
+
+
+def _equal_or_both_nan(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def test_cmem_radii_that_are_not_ordinary_numbers():
+    """zero, tiny, huge, infinite and NaN radii take the literal b1 / b2 (out of line in the kernel): same values as the
+    oracle, with and without the region filter"""
+    big = np.float32(3e38)
+    pts = np.array([(0, 0, 0), (1e-35, 0, 0), (1e-32, 1e-33, -1e-33), (7e-31, 0, 0), (9e-31, 0, 0), (1e-20, 1e-21, 0),
+                    (1e29, 0, 0), (0, 1e30, 1e29), (2e30, 0, 0), (-3e30, 1e30, 0), (1e19, 1e19, 1e19), (big, 0, 0),
+                    (big, big, 0), (np.inf, 0, 0), (0, -np.inf, 1), (np.nan, 1, 1), (5, np.nan, 0), (12, 3, np.nan),
+                    (1.5e19, 0, 0), (0, 0, 1.9e19)], np.float32)
+    for kw in ({}, O.CMEM_TEST2):
+        P = capi.cmem_init(**kw)
+        with np.errstate(all="ignore"):
+            want = O.orc_cmem_sample(O.orc_cmem_init(**kw), pts)
+        for mode in (2, 3):
+            got = D.sample_cmem(P, pts, mode)
+            assert _equal_or_both_nan(got, want), (mode, got, want)
+
+
+@pytest.mark.parametrize("B", [0.05, 2.4e-9, 2.46e-9, 1e-6])
+def test_cmem_exponential_factor_of_b1(B):
+    """CMEM::Init leaves B = |b| * 1e-9, for which expf(-B (theta/2)^4) is 1.0f for every theta and the kernel skips it
+    (CmemDev::e_one).  A record with another B (poked in: Init cannot produce one) must still go through the
+    exponential: against the oracle on the same record"""
+    P = capi.cmem_init()
+    P["B"] = np.float32(B)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-25, 25, size=(60000, 3)).astype(np.float32)
+    want = O.orc_cmem_sample(P.view(np.float32).copy(), pts)
+    full = D.sample_cmem(P, pts, 2)
+    assert_bit_exact(D.sample_cmem(P, pts, 3), full, "region filter")
+    same = (full.view(np.uint32) == want.view(np.uint32)) | ((full == 0) & (want == 0))
+    assert same.mean() > 0.9
+    scale = np.abs(want).max()
+    err = np.abs(full.astype(np.float64) - want)
+    assert (err <= 1e-5 * np.maximum(np.abs(want), 1e-3 * scale)).mean() >= 0.9995
+    if B >= 1e-6:  # the factor matters: the samples differ from those of the default record
+        assert not np.array_equal(full, D.sample_cmem(capi.cmem_init(), pts, 2))
+
+
 @pytest.mark.parametrize("kw", [{}, O.CMEM_TEST2, dict(dipole=0.2, b=(1, -2, -6), v=(450, 10, -20))])
 def test_cmem_device_source_vs_oracle_and_filter_is_invisible(kw):
     rng = np.random.default_rng(41)

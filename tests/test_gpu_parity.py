@@ -807,6 +807,14 @@ def test_cmem_math_accuracy(gpu):
         assert v < 2.0 ** -44, (name, v)
 
 
+def test_cmem_division_by_ten_is_the_ieee_division_for_every_float(gpu):
+    """r / 10 (src/Cmem.cpp:158,165) is computed without a division where r is an ordinary number: all 2^32 bit patterns
+    on the device"""
+    kernel_form, bare_form = capi.selftest_div10()
+    assert kernel_form == 0
+    assert bare_form == 419431  # the subnormal quotients of r in [2^-126, 2^-125), which the range test excludes
+
+
 CMEM_KW = [{}, O.CMEM_CLI, O.CMEM_TEST2, dict(dipole=0.2, b=(1, -2, -6), v=(450, 10, -20))]
 
 
@@ -889,6 +897,48 @@ def test_cmem_samples_vs_oracle(gpu, kw, fast):
         same = np.mean(got.view(np.uint32) == other.view(np.uint32))
         print(f"own fp64 blocks vs CUDA fp64 library: {same:.6%} of samples bit-identical")
         assert same > 0.9999
+
+
+def test_cmem_radii_that_are_not_ordinary_numbers(gpu):
+    """zero, tiny, huge, infinite and NaN radii take the literal b1 / b2 (out of line in the kernel): same values as the
+    oracle and as the CUDA-library evaluation, with and without the region filter"""
+    big = np.float32(3e38)
+    pts = np.array([(0, 0, 0), (1e-35, 0, 0), (1e-32, 1e-33, -1e-33), (7e-31, 0, 0), (9e-31, 0, 0), (1e-20, 1e-21, 0),
+                    (1e29, 0, 0), (0, 1e30, 1e29), (2e30, 0, 0), (-3e30, 1e30, 0), (1e19, 1e19, 1e19), (big, 0, 0),
+                    (big, big, 0), (np.inf, 0, 0), (0, -np.inf, 1), (np.nan, 1, 1), (5, np.nan, 0), (12, 3, np.nan),
+                    (1.5e19, 0, 0), (0, 0, 1.9e19)], np.float32)
+
+    def same(a, b):
+        return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+    for kw in ({}, O.CMEM_TEST2):
+        P = capi.cmem_init(**kw)
+        with np.errstate(all="ignore"):
+            want = O.orc_cmem_sample(O.orc_cmem_init(**kw), pts)
+        for mode in (False, "nofilter", "notable", "libm64"):
+            got = capi.sample_cmem(P, pts, fast=mode)
+            assert same(got, want), (mode, got, want)
+
+
+@pytest.mark.parametrize("B", [0.05, 2.4e-9, 2.46e-9, 1e-6])
+def test_cmem_exponential_factor_of_b1(gpu, B):
+    """CMEM::Init leaves B = |b| * 1e-9, for which expf(-B (theta/2)^4) is 1.0f for every theta and the kernel skips it.
+    A record with another B (poked in: Init cannot produce one) still goes through the exponential"""
+    P = capi.cmem_init()
+    P["B"] = np.float32(B)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-25, 25, size=(200000, 3)).astype(np.float32)
+    want = O.orc_cmem_sample(P.view(np.float32).copy(), pts)
+    got = capi.sample_cmem(P, pts)
+    assert_bit_exact(got, capi.sample_cmem(P, pts, fast="nofilter"), "region filter")
+    other = capi.sample_cmem(P, pts, fast="libm64")  # the literal evaluation with the CUDA fp64 library
+    assert np.mean(got.view(np.uint32) == other.view(np.uint32)) > 0.9999
+    assert np.mean((got.view(np.uint32) == want.view(np.uint32)) | ((got == 0) & (want == 0))) > 0.9
+    fp, fo = frames_pair(POSES[:2], S.SXI_FOV_W, S.SXI_FOV_H, W, H)
+    img = capi.render_cmem(P, fp, W, H)
+    ref = O.orc_render_cmem(P.view(np.float32).copy(), fo, W, H)
+    for g, w in zip(img, ref):
+        assert assert_image_parity(g, w, f"cmem B={B}") >= 0.99
 
 
 @pytest.mark.parametrize("fast", [False, True, "libm64", "libm32"])
