@@ -425,8 +425,12 @@ __global__ void __launch_bounds__(256) pack_poly_kernel(const float* __restrict_
 // 7.13 / 6.99 / 7.09), one rank's eighth of it 0.924 / 0.918 / 0.940 ms (tolerance mode 0.510 / 0.502 / 0.574); a 512^2
 // image 0.158 / 0.164 / 0.173 ms; the orbit sweep of 64 x 108 frames 27.57 / 27.67 / 27.79 ms.  So: 4 warps for frames of
 // half a million rays and more (a CTA's slot is refilled only when its slowest warp is done), 8 otherwise -- a 1-2 % matter.
-int pick_cta_warps(const RenderGeom& g, int tiles_per_frame) {
+// The CMEM march (`analytic`): its rays differ far more in cost (which regions they cross), and a CTA's slot waits for
+// its slowest warp: 107.1 / 104.5 / 104.0 ms for the 10 000-frame sweep with 8 / 4 / 2 warps (profiles/r2p_ab_cmem_*.json;
+// capping the registers at 48 or 40 for more resident warps instead: 107.1 / 104.0, but the tolerance mode loses 5 %).
+int pick_cta_warps(const RenderGeom& g, int tiles_per_frame, bool analytic) {
     if (g.cta_warps == 2 || g.cta_warps == 4 || g.cta_warps == 8) return g.cta_warps;
+    if (analytic) return 4;
     return tiles_per_frame >= 16384 ? 4 : kWarpsPerBlock;  // >= 2^19 rays of one frame in this launch
 }
 
@@ -452,7 +456,7 @@ int pick_tile_w_log2(const RenderGeom& g) {
 }
 
 bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, const float* d_dist, int flags,
-               float* d_images, unsigned long long* d_valid, int* d_status, unsigned* blocks) {
+               float* d_images, unsigned long long* d_valid, int* d_status, unsigned* blocks, bool analytic = false) {
     a.frames = d_frames;
     a.dist = d_dist;
     a.images = d_images;
@@ -483,7 +487,7 @@ bool fill_args(MarchArgs& a, const birp_frame* d_frames, const RenderGeom& g, co
     a.fast_step = 0.0;
     a.out_offset = g.out_frame_offset;
     a.out_stride = g.out_frame_stride;
-    a.cta_warps = pick_cta_warps(g, a.tiles_per_frame);
+    a.cta_warps = pick_cta_warps(g, a.tiles_per_frame, analytic);
     const long long nb = (a.total_tiles + a.cta_warps - 1) / a.cta_warps;
     *blocks = (unsigned)nb;
     return nb <= 0x7fffffffLL;
@@ -495,7 +499,7 @@ cudaError_t launch_march(const Field& field, const birp_frame* d_frames, const R
                          int* d_status, cudaStream_t stream) {
     MarchArgs a;
     unsigned blocks;
-    if (!fill_args(a, d_frames, g, d_dist, flags, d_images, d_valid, d_status, &blocks))
+    if (!fill_args(a, d_frames, g, d_dist, flags, d_images, d_valid, d_status, &blocks, /*analytic=*/true))
         return cudaErrorInvalidConfiguration;
     if (a.total_tiles <= 0) return cudaSuccess;
     march_kernel<Field><<<blocks, a.cta_warps * 32, 0, stream>>>(a, field);
