@@ -1135,6 +1135,17 @@ __device__ __forceinline__ float cmem_b2(const birp_cmem_params& P, float r) {
     return __double2float_rn(__dmul_rn((double)P.A2, rcp_newton(__dmul_rn(__dmul_rn(sd, sd), sd))));
 }
 
+// ShueModel(theta, phi, bs, ay_bs, az_bs) of src/Cmem.cpp:280-288: the bow-shock radius in the sample's direction
+__device__ __forceinline__ float cmem_radius_bs(const CmemDev& D, float cos_t, float sin_p, float cos_p) {
+    const birp_cmem_params& P = D.P;
+    const float sbase = __fdiv_rn(2.f, __fadd_rn(1.f, cos_t));
+    const float ry = __fmul_rn(P.bs, pow32(sbase, P.ay_bs));
+    const float rz = D.same_flare ? ry : __fmul_rn(P.bs, pow32(sbase, P.az_bs));
+    const float rzc = __fmul_rn(rz, cos_p);
+    const float rys = __fmul_rn(ry, sin_p);
+    return __fdiv_rn(__fmul_rn(ry, rz), __fsqrt_rn(__fadd_rn(__fmul_rn(rzc, rzc), __fmul_rn(rys, rys))));
+}
+
 // magnetopause (LinScaled, :188-222) and bow-shock (ShueModel, :280-288) radii in the sample's direction
 __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float q_p, float& theta, float& sin_t,
                                               float& radius_mp, float& radius_bs) {
@@ -1167,12 +1178,7 @@ __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float
                               __fmul_rn(p2c, (float)cm::exp_d((double)__fmul_rn(D.p3ds, pow32(phi_s, P.a21)))));
     radius_mp = __fadd_rn(__fmul_rn(D.p0r0, f), q);
 
-    const float sbase = __fdiv_rn(2.f, __fadd_rn(1.f, cos_t));
-    const float ry = __fmul_rn(P.bs, pow32(sbase, P.ay_bs));
-    const float rz = D.same_flare ? ry : __fmul_rn(P.bs, pow32(sbase, P.az_bs));
-    const float rzc = __fmul_rn(rz, cos_p);
-    const float rys = __fmul_rn(ry, sin_p);
-    radius_bs = __fdiv_rn(__fmul_rn(ry, rz), __fsqrt_rn(__fadd_rn(__fmul_rn(rzc, rzc), __fmul_rn(rys, rys))));
+    radius_bs = cmem_radius_bs(D, cos_t, sin_p, cos_p);
 }
 
 #define BIRP_CMEM_HALF_THICKNESS 0.025f /* 0.05f / 2, src/Cmem.cpp:133 */
@@ -1211,6 +1217,27 @@ __device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float
     cmem_cosines(x, y, z, r, q_t, q_p);
     cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
     return cmem_regions(D, r, theta, sin_t, radius_mp, radius_bs);
+}
+
+// The same for a sample that lies ABOVE the magnetopause layer for certain (r > mp_hi: the region filter knows, see
+// cmem_try_filter) but next to the bow shock: the Lin radius -- two thirds of the full evaluation -- decides nothing
+// there.  cmem_regions with `r < mp_lo` and `in_mp_layer` false and `r > mp_hi` true, term for term.
+__device__ __forceinline__ float cmem_sample_above_mp(const CmemDev& D, float x, float y, float z) {
+    float r, q_t, q_p;
+    cmem_cosines(x, y, z, r, q_t, q_p);
+    const cm::Angle T = cm::angle_from_cosine(q_t);
+    const cm::Angle F = cm::angle_from_cosine(q_p);
+    const float sin_t = (float)T.s;
+    const float radius_bs = cmem_radius_bs(D, (float)T.c, (float)F.s, (float)F.c);
+    const float bs_lo = __fsub_rn(radius_bs, BIRP_CMEM_HALF_THICKNESS), bs_hi = __fadd_rn(radius_bs, BIRP_CMEM_HALF_THICKNESS);
+    const bool in_sheath = r < bs_lo;
+    const bool in_bs_layer = (r >= bs_lo && r <= bs_hi);
+    float b1 = 0.f;
+    if (in_sheath || in_bs_layer) b1 = cmem_b1(D, r, T.a, sin_t);
+    if (in_sheath) return b1;
+    const float b2 = cmem_b2(D.P, r);
+    if (in_bs_layer) return lerp_ref(b1, b2, __fdiv_rn(__fsub_rn(r, bs_lo), bs_hi));
+    return b2;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1346,61 +1373,74 @@ __device__ __forceinline__ float cmem_sheath_value(const CmemDev& D, float x, fl
     return P.A1 * e * pw;
 }
 
-// The filter: true with the sample in `value` when its region is certain; false when the full evaluation has to decide.
+// The filter: kCmemDecided with the sample in `value` when its region is certain; kCmemUndecided when the full
+// evaluation has to decide; kCmemAboveMp when only the bow shock is left to decide (cmem_sample_above_mp).
+enum { kCmemUndecided = 0, kCmemDecided = 1, kCmemAboveMp = 2 };
 template <bool FASTVAL>
-__device__ __forceinline__ bool cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
+__device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
     float r, q_t, q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
     // Stage 0: the region table.  Most samples lie far from both boundaries of their direction's cell; for those one
     // 16-byte load decides the region, and neither radius is estimated at all.
+    bool above_mp = false;  // r > mp_hi for certain
     if (D.table) {
         const float4 tb = __ldg(D.table + cmem_table_index(q_t, q_p));  // {mp_lo, mp_hi, bs_lo, bs_hi}; never NaN
         if (r < tb.x) {
             value = 0.f;
-            return true;
+            return kCmemDecided;
         }
         if (r > tb.y) {
             if (r > tb.w) {
                 value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-                return true;
+                return kCmemDecided;
             }
             if (r < tb.z) {
                 value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-                return true;
+                return kCmemDecided;
             }
+            above_mp = true;  // between the table's bounds of the bow shock: the (sharper) estimate of its radius is next
         }
     }
     CmemEstimate e = cmem_estimate_stage1(D, q_t, q_p);
     const float ht = BIRP_CMEM_HALF_THICKNESS;
     const float m_bs = BIRP_CMEM_MARGIN(e.bs);
     // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
-    if (D.q_nonpositive && e.trusted && r > e.bs + ht + m_bs && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper)) {
-        // certainly r > bs_hi and r > mp_hi: neither sheath nor a layer
-        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-        return true;
+    // p0 r0 f bounds the magnetopause radius from above when the cusp terms can only lower it
+    above_mp = above_mp || (D.q_nonpositive && e.trusted && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper));
+    if (above_mp) {  // the cusp terms (stage 2) are not needed
+        if (e.trusted && r > e.bs + ht + m_bs) {  // certainly r > bs_hi as well
+            value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+            return kCmemDecided;
+        }
+        if (e.trusted && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
+            value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
+            return kCmemDecided;
+        }
+        return kCmemAboveMp;
     }
     const float mp = cmem_estimate_stage2(D, e);
     const float m_mp = BIRP_CMEM_MARGIN(mp);
     if (e.trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
         value = 0.f;
-        return true;
+        return kCmemDecided;
     }
-    const bool above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
-    if (above_mp && r > e.bs + ht + m_bs) {                 // (parameter sets with q > 0)
+    above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
+    if (above_mp && r > e.bs + ht + m_bs) {      // (parameter sets with q > 0)
         value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-        return true;
+        return kCmemDecided;
     }
     if (above_mp && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
         value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-        return true;
+        return kCmemDecided;
     }
-    return false;
+    return above_mp ? kCmemAboveMp : kCmemUndecided;
 }
 
 __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
     float value;
-    if (cmem_try_filter<false>(D, x, y, z, value)) return value;
-    return cmem_sample_v4(D, x, y, z);
+    const int decided = cmem_try_filter<false>(D, x, y, z, value);
+    if (decided == kCmemDecided) return value;
+    return decided == kCmemAboveMp ? cmem_sample_above_mp(D, x, y, z) : cmem_sample_v4(D, x, y, z);
 }
 
 // BIRP_CMEM_FAST (opt-in, tolerance mode): the same region decisions from the table and the fp32 estimates, values in
@@ -1408,7 +1448,7 @@ __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float
 // agree with the reference's on all but about one sample in 10^4 crossings)
 __device__ __forceinline__ float cmem_sample_fast(const CmemDev& D, float x, float y, float z) {
     float value;
-    if (cmem_try_filter<true>(D, x, y, z, value)) return value;
+    if (cmem_try_filter<true>(D, x, y, z, value) == kCmemDecided) return value;
     return cmem_sample<false>(D, x, y, z);
 }
 

@@ -597,7 +597,7 @@ void doh_cmem_filter_decides(const birp_cmem_params* params, const float* xyz, l
     const birp::CmemDev D = birp::make_cmem_dev(*params);
     for (long p = 0; p < n; ++p) {
         float value;
-        decided[p] = birp::cmem_try_filter<false>(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], value);
+        decided[p] = birp::cmem_try_filter<false>(D, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], value) == birp::kCmemDecided;
     }
 }
 
