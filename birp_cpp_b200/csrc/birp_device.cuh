@@ -1147,8 +1147,12 @@ __device__ __forceinline__ float cmem_radius_bs(const CmemDev& D, float cos_t, f
 }
 
 // magnetopause (LinScaled, :188-222) and bow-shock (ShueModel, :280-288) radii in the sample's direction
+// above_mp: the sample lies ABOVE the magnetopause layer for certain (r > mp_hi: the region filter knows, see
+// cmem_try_filter) -- the Lin radius, two thirds of this function, decides nothing there and is not evaluated: a radius
+// of -inf makes every comparison of cmem_regions come out as it would with the true one (r < mp_lo false, r <= mp_hi
+// false, r > mp_hi true).
 __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float q_p, float& theta, float& sin_t,
-                                              float& radius_mp, float& radius_bs) {
+                                              float& radius_mp, float& radius_bs, bool above_mp = false) {
     const birp_cmem_params& P = D.P;
     const cm::Angle T = cm::angle_from_cosine(q_t);
     const cm::Angle F = cm::angle_from_cosine(q_p);
@@ -1158,6 +1162,11 @@ __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float
     // sinf(2 theta): 2 theta is exact in fp32 and sin 2a = 2 sin a cos a
     const float sin_2t = (float)(2.0 * T.s * T.c);
     const float sin_p = (float)F.s, cos_p = (float)F.c;
+    radius_bs = cmem_radius_bs(D, cos_t, sin_p, cos_p);
+    if (above_mp) {
+        radius_mp = -CUDART_INF_F;
+        return;
+    }
 
     // cos(phi - pi/2) = sin(phi) and cos(phi - 3pi/2) = -sin(phi): the reference evaluates both in fp64
     // (they agree with these to ~1e-16), as well as the outer acos
@@ -1177,8 +1186,6 @@ __device__ __forceinline__ void cmem_radii_v4(const CmemDev& D, float q_t, float
     const float q = __fadd_rn(__fmul_rn(p2c, (float)cm::exp_d((double)__fmul_rn(D.p3dn, pow32(phi_n, P.a21)))),
                               __fmul_rn(p2c, (float)cm::exp_d((double)__fmul_rn(D.p3ds, pow32(phi_s, P.a21)))));
     radius_mp = __fadd_rn(__fmul_rn(D.p0r0, f), q);
-
-    radius_bs = cmem_radius_bs(D, cos_t, sin_p, cos_p);
 }
 
 #define BIRP_CMEM_HALF_THICKNESS 0.025f /* 0.05f / 2, src/Cmem.cpp:133 */
@@ -1212,32 +1219,11 @@ __device__ __forceinline__ float cmem_regions(const CmemDev& D, float r, float t
     return b2;
 }
 
-__device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float y, float z) {
+__device__ __forceinline__ float cmem_sample_v4(const CmemDev& D, float x, float y, float z, bool above_mp = false) {
     float r, q_t, q_p, theta, sin_t, radius_mp, radius_bs;
     cmem_cosines(x, y, z, r, q_t, q_p);
-    cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs);
+    cmem_radii_v4(D, q_t, q_p, theta, sin_t, radius_mp, radius_bs, above_mp);
     return cmem_regions(D, r, theta, sin_t, radius_mp, radius_bs);
-}
-
-// The same for a sample that lies ABOVE the magnetopause layer for certain (r > mp_hi: the region filter knows, see
-// cmem_try_filter) but next to the bow shock: the Lin radius -- two thirds of the full evaluation -- decides nothing
-// there.  cmem_regions with `r < mp_lo` and `in_mp_layer` false and `r > mp_hi` true, term for term.
-__device__ __forceinline__ float cmem_sample_above_mp(const CmemDev& D, float x, float y, float z) {
-    float r, q_t, q_p;
-    cmem_cosines(x, y, z, r, q_t, q_p);
-    const cm::Angle T = cm::angle_from_cosine(q_t);
-    const cm::Angle F = cm::angle_from_cosine(q_p);
-    const float sin_t = (float)T.s;
-    const float radius_bs = cmem_radius_bs(D, (float)T.c, (float)F.s, (float)F.c);
-    const float bs_lo = __fsub_rn(radius_bs, BIRP_CMEM_HALF_THICKNESS), bs_hi = __fadd_rn(radius_bs, BIRP_CMEM_HALF_THICKNESS);
-    const bool in_sheath = r < bs_lo;
-    const bool in_bs_layer = (r >= bs_lo && r <= bs_hi);
-    float b1 = 0.f;
-    if (in_sheath || in_bs_layer) b1 = cmem_b1(D, r, T.a, sin_t);
-    if (in_sheath) return b1;
-    const float b2 = cmem_b2(D.P, r);
-    if (in_bs_layer) return lerp_ref(b1, b2, __fdiv_rn(__fsub_rn(r, bs_lo), bs_hi));
-    return b2;
 }
 
 // ---------------------------------------------------------------------------------
@@ -1265,6 +1251,17 @@ __device__ __forceinline__ float est_sqrt(float x) {
     return sqrtf(x);
 #endif
 }
+// 1 / sqrt(x) from the hardware unit alone (MUFU.RSQ; rsqrtf() wraps it in a rescaling of subnormal arguments, four
+// instructions per call that the filter would pay at every sample)
+__device__ __forceinline__ float est_rsqrt(float x) {
+#ifdef __CUDACC__
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
 // acos(x), |error| < 1e-7: Abramowitz & Stegun 4.4.46, acos(x) = sqrt(1 - x) (a0 + a1 x + ... + a7 x^7) on [0, 1]
 // (|eps| <= 2e-8), mirrored for x < 0
 __device__ __forceinline__ float est_acos(float x) {
@@ -1285,10 +1282,14 @@ __device__ __forceinline__ float est_acos(float x) {
 __device__ __forceinline__ void cmem_cosines_estimate(float x, float y, float z, float& r, float& q_t, float& q_p) {
     const float yz2 = y * y + z * z;
     const float s2 = x * x + yz2;
-    const float rinv = rsqrtf(s2);
+    const float rinv = est_rsqrt(s2);
     r = s2 * rinv;
     q_t = (x != 0.f) ? x * rinv : 1.f;
-    q_p = (y != 0.f) ? y * rsqrtf(yz2) : 1.f;
+    q_p = (y != 0.f) ? y * est_rsqrt(yz2) : 1.f;
+    // The hardware unit flushes a subnormal argument to zero: a sample within 1e-15 RE of the origin (or of the x axis,
+    // where cos(phi) comes from y^2 + z^2) is left to the exact evaluation -- a NaN radius fails every comparison of the
+    // filter, the region table's included.
+    if (!((y != 0.f ? yz2 : s2) >= 1e-30f)) r = __int_as_float(0x7fc00000);
 }
 
 // fp32 estimates for the region filter, in two stages so that a sample beyond the bow shock never pays for the
@@ -1321,7 +1322,7 @@ __device__ __forceinline__ CmemEstimate cmem_estimate_stage1(const CmemDev& D, f
     } else {
         const float rz = P.bs * exp2f(P.az_bs * lb);
         const float rzc = rz * e.cos_p;
-        e.bs = ry * rz * rsqrtf(fmaf(rzc, rzc, ry * ry * e.sin2_p));
+        e.bs = ry * rz * est_rsqrt(fmaf(rzc, rzc, ry * ry * e.sin2_p));
     }
     e.trusted = (1.f + q_t > 0.02f) && (fbase > 0.05f);
     return e;
@@ -1373,31 +1374,22 @@ __device__ __forceinline__ float cmem_sheath_value(const CmemDev& D, float x, fl
     return P.A1 * e * pw;
 }
 
-// The filter: kCmemDecided with the sample in `value` when its region is certain; kCmemUndecided when the full
-// evaluation has to decide; kCmemAboveMp when only the bow shock is left to decide (cmem_sample_above_mp).
-enum { kCmemUndecided = 0, kCmemDecided = 1, kCmemAboveMp = 2 };
-template <bool FASTVAL>
-__device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
-    float r, q_t, q_p;
+// The region filter.  cmem_classify says which region a sample lies in FOR CERTAIN (or that it cannot tell); the value
+// of a classified sample is then computed at ONE place (cmem_try_filter), so that the lanes of a warp that were
+// classified at different stages run the same copy of the value code together.
+enum { kRegInside = 0, kRegSheath = 1, kRegOutside = 2, kRegUndecided = 3, kRegAboveMp = 4 };
+__device__ __forceinline__ int cmem_classify(const CmemDev& D, float x, float y, float z, float& r, float& q_t) {
+    float q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
     // Stage 0: the region table.  Most samples lie far from both boundaries of their direction's cell; for those one
     // 16-byte load decides the region, and neither radius is estimated at all.
     bool above_mp = false;  // r > mp_hi for certain
     if (D.table) {
         const float4 tb = __ldg(D.table + cmem_table_index(q_t, q_p));  // {mp_lo, mp_hi, bs_lo, bs_hi}; never NaN
-        if (r < tb.x) {
-            value = 0.f;
-            return kCmemDecided;
-        }
+        if (r < tb.x) return kRegInside;
         if (r > tb.y) {
-            if (r > tb.w) {
-                value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-                return kCmemDecided;
-            }
-            if (r < tb.z) {
-                value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-                return kCmemDecided;
-            }
+            if (r > tb.w) return kRegOutside;
+            if (r < tb.z) return kRegSheath;
             above_mp = true;  // between the table's bounds of the bow shock: the (sharper) estimate of its radius is next
         }
     }
@@ -1408,39 +1400,38 @@ __device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float 
     // p0 r0 f bounds the magnetopause radius from above when the cusp terms can only lower it
     above_mp = above_mp || (D.q_nonpositive && e.trusted && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper));
     if (above_mp) {  // the cusp terms (stage 2) are not needed
-        if (e.trusted && r > e.bs + ht + m_bs) {  // certainly r > bs_hi as well
-            value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-            return kCmemDecided;
-        }
-        if (e.trusted && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
-            value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-            return kCmemDecided;
-        }
-        return kCmemAboveMp;
+        if (e.trusted && r > e.bs + ht + m_bs) return kRegOutside;  // certainly r > bs_hi as well
+        if (e.trusted && r < e.bs - ht - m_bs) return kRegSheath;   // certainly mp_hi < r < bs_lo
+        return kRegAboveMp;
     }
     const float mp = cmem_estimate_stage2(D, e);
     const float m_mp = BIRP_CMEM_MARGIN(mp);
-    if (e.trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
-        value = 0.f;
-        return kCmemDecided;
-    }
-    above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
-    if (above_mp && r > e.bs + ht + m_bs) {      // (parameter sets with q > 0)
-        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-        return kCmemDecided;
-    }
-    if (above_mp && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
-        value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-        return kCmemDecided;
-    }
-    return above_mp ? kCmemAboveMp : kCmemUndecided;
+    if (e.trusted && r < mp - ht - m_mp) return kRegInside;  // certainly r < mp_lo
+    above_mp = e.trusted && r > mp + ht + m_mp;              // certainly r > mp_hi
+    if (above_mp && r > e.bs + ht + m_bs) return kRegOutside;  // (parameter sets with q > 0)
+    if (above_mp && r < e.bs - ht - m_bs) return kRegSheath;
+    return above_mp ? kRegAboveMp : kRegUndecided;
+}
+
+// kCmemDecided with the sample in `value` when its region is certain; kCmemUndecided when the full evaluation has to
+// decide; kCmemAboveMp when only the bow shock is left to decide (cmem_sample_v4 with above_mp).
+enum { kCmemUndecided = 0, kCmemDecided = 1, kCmemAboveMp = 2 };
+template <bool FASTVAL>
+__device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
+    float r, q_t;
+    const int region = cmem_classify(D, x, y, z, r, q_t);
+    if (region >= kRegUndecided) return region == kRegAboveMp ? kCmemAboveMp : kCmemUndecided;
+    value = 0.f;
+    if (region == kRegSheath) value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
+    if (region == kRegOutside) value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+    return kCmemDecided;
 }
 
 __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {
     float value;
     const int decided = cmem_try_filter<false>(D, x, y, z, value);
     if (decided == kCmemDecided) return value;
-    return decided == kCmemAboveMp ? cmem_sample_above_mp(D, x, y, z) : cmem_sample_v4(D, x, y, z);
+    return cmem_sample_v4(D, x, y, z, decided == kCmemAboveMp);
 }
 
 // BIRP_CMEM_FAST (opt-in, tolerance mode): the same region decisions from the table and the fp32 estimates, values in
