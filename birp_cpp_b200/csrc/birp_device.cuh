@@ -1342,8 +1342,6 @@ __device__ __forceinline__ float cmem_estimate_stage2(const CmemDev& D, CmemEsti
 
 #define BIRP_CMEM_MARGIN(v) (BIRP_CMEM_MARGIN_REL * fabsf(v) + BIRP_CMEM_MARGIN_ABS)
 
-// The filter: true with the sample in `value` when its region is certain; false when the full evaluation
-// (cmem_sample_v4) has to decide.
 // The emissivity of a sample whose REGION is known.  FASTVAL = false: the fp64-then-round evaluation of the default
 // path (bit for bit what the unfiltered evaluation returns).  FASTVAL = true (BIRP_CMEM_FAST, tolerance mode): fp32
 // with the hardware approximations, ~1e-6 relative -- the estimated r and cos(theta) the filter already holds are
@@ -1374,57 +1372,64 @@ __device__ __forceinline__ float cmem_sheath_value(const CmemDev& D, float x, fl
     return P.A1 * e * pw;
 }
 
-// The region filter.  cmem_classify says which region a sample lies in FOR CERTAIN (or that it cannot tell); the value
-// of a classified sample is then computed at ONE place (cmem_try_filter), so that the lanes of a warp that were
-// classified at different stages run the same copy of the value code together.
-enum { kRegInside = 0, kRegSheath = 1, kRegOutside = 2, kRegUndecided = 3, kRegAboveMp = 4 };
-__device__ __forceinline__ int cmem_classify(const CmemDev& D, float x, float y, float z, float& r, float& q_t) {
-    float q_p;
+// The filter: kCmemDecided with the sample in `value` when its region is certain; kCmemUndecided when the full
+// evaluation has to decide; kCmemAboveMp when the sample lies above the magnetopause layer for certain and only the bow
+// shock is left to decide (cmem_sample_v4 with above_mp).  "Above for certain" needs the TRUE radius to be a number: next
+// to a cusp axis rounding can push the argument of the reference's acos beyond 1, the radius is NaN there and the
+// reference then takes NEITHER the sheath nor a layer (every comparison with it is false) -- so only the region table
+// (whose cells next to a cusp axis bound nothing) and stage 2 (whose trust flag excludes those directions) may say
+// so, not the upper bound p0 r0 f of stage 1 on its own.
+enum { kCmemUndecided = 0, kCmemDecided = 1, kCmemAboveMp = 2 };
+template <bool FASTVAL>
+__device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
+    float r, q_t, q_p;
     cmem_cosines_estimate(x, y, z, r, q_t, q_p);
     // Stage 0: the region table.  Most samples lie far from both boundaries of their direction's cell; for those one
     // 16-byte load decides the region, and neither radius is estimated at all.
-    bool above_mp = false;  // r > mp_hi for certain
+    bool table_above_mp = false;
     if (D.table) {
         const float4 tb = __ldg(D.table + cmem_table_index(q_t, q_p));  // {mp_lo, mp_hi, bs_lo, bs_hi}; never NaN
-        if (r < tb.x) return kRegInside;
+        if (r < tb.x) {
+            value = 0.f;
+            return kCmemDecided;
+        }
         if (r > tb.y) {
-            if (r > tb.w) return kRegOutside;
-            if (r < tb.z) return kRegSheath;
-            above_mp = true;  // between the table's bounds of the bow shock: the (sharper) estimate of its radius is next
+            if (r > tb.w) {
+                value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+                return kCmemDecided;
+            }
+            if (r < tb.z) {
+                value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
+                return kCmemDecided;
+            }
+            table_above_mp = true;  // r > mp_hi for certain, between the table's bounds of the bow shock
         }
     }
     CmemEstimate e = cmem_estimate_stage1(D, q_t, q_p);
     const float ht = BIRP_CMEM_HALF_THICKNESS;
     const float m_bs = BIRP_CMEM_MARGIN(e.bs);
     // every comparison is written so that a NaN anywhere makes it false (-> full evaluation)
-    // p0 r0 f bounds the magnetopause radius from above when the cusp terms can only lower it
-    above_mp = above_mp || (D.q_nonpositive && e.trusted && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper));
-    if (above_mp) {  // the cusp terms (stage 2) are not needed
-        if (e.trusted && r > e.bs + ht + m_bs) return kRegOutside;  // certainly r > bs_hi as well
-        if (e.trusted && r < e.bs - ht - m_bs) return kRegSheath;   // certainly mp_hi < r < bs_lo
-        return kRegAboveMp;
+    if (D.q_nonpositive && e.trusted && r > e.bs + ht + m_bs && r > e.mp_upper + ht + BIRP_CMEM_MARGIN(e.mp_upper)) {
+        // certainly r > bs_hi and r > mp_hi: neither sheath nor a layer
+        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+        return kCmemDecided;
     }
     const float mp = cmem_estimate_stage2(D, e);
     const float m_mp = BIRP_CMEM_MARGIN(mp);
-    if (e.trusted && r < mp - ht - m_mp) return kRegInside;  // certainly r < mp_lo
-    above_mp = e.trusted && r > mp + ht + m_mp;              // certainly r > mp_hi
-    if (above_mp && r > e.bs + ht + m_bs) return kRegOutside;  // (parameter sets with q > 0)
-    if (above_mp && r < e.bs - ht - m_bs) return kRegSheath;
-    return above_mp ? kRegAboveMp : kRegUndecided;
-}
-
-// kCmemDecided with the sample in `value` when its region is certain; kCmemUndecided when the full evaluation has to
-// decide; kCmemAboveMp when only the bow shock is left to decide (cmem_sample_v4 with above_mp).
-enum { kCmemUndecided = 0, kCmemDecided = 1, kCmemAboveMp = 2 };
-template <bool FASTVAL>
-__device__ __forceinline__ int cmem_try_filter(const CmemDev& D, float x, float y, float z, float& value) {
-    float r, q_t;
-    const int region = cmem_classify(D, x, y, z, r, q_t);
-    if (region >= kRegUndecided) return region == kRegAboveMp ? kCmemAboveMp : kCmemUndecided;
-    value = 0.f;
-    if (region == kRegSheath) value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
-    if (region == kRegOutside) value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
-    return kCmemDecided;
+    if (e.trusted && r < mp - ht - m_mp) {  // certainly r < mp_lo
+        value = 0.f;
+        return kCmemDecided;
+    }
+    const bool above_mp = e.trusted && r > mp + ht + m_mp;  // certainly r > mp_hi
+    if (above_mp && r > e.bs + ht + m_bs) {                 // (parameter sets with q > 0)
+        value = cmem_outside_value<FASTVAL>(D, x, y, z, r);
+        return kCmemDecided;
+    }
+    if (above_mp && r < e.bs - ht - m_bs) {  // certainly mp_hi < r < bs_lo: open magnetosheath
+        value = cmem_sheath_value<FASTVAL>(D, x, y, z, r, q_t);
+        return kCmemDecided;
+    }
+    return (above_mp || table_above_mp) ? kCmemAboveMp : kCmemUndecided;
 }
 
 __device__ __forceinline__ float cmem_sample_v5(const CmemDev& D, float x, float y, float z) {

@@ -373,6 +373,29 @@ def test_cmem_radii_that_are_not_ordinary_numbers():
             assert _equal_or_both_nan(got, want), (mode, got, want)
 
 
+def test_cmem_nan_magnetopause_radius_next_to_a_cusp_axis():
+    """next to a cusp axis rounding pushes the argument of the reference's acos beyond 1: the Lin radius is NaN there and
+    the reference takes neither the sheath nor a layer (a sample below the bow shock still gets b2).  The filter may not
+    conclude "above the magnetopause" from the upper bound of its first stage there -- a version that did was caught by
+    two pixels of the orbit sweep (frames 19 and 30), which are kept here with their frames"""
+    P = capi.cmem_init()
+    tab = D.cmem_table(P)
+    pts = np.array([(6.8797760e+00, -3.2266974e-03, 1.3621016e+01), (5.6001272e+00, -1.1186600e-03, -1.1084445e+01)], np.float32)
+    want = O.orc_cmem_sample(O.orc_cmem_init(), pts)
+    full = D.sample_cmem(P, pts, 2)
+    assert_bit_exact(full, want)
+    assert_bit_exact(D.sample_cmem(P, pts, 3), full, "region filter")
+    assert_bit_exact(D.sample_cmem_table(P, tab, pts)[0], full, "region table + filter")
+    poses = S.orbit_poses(40)[[19, 30]]
+    fo = O.orc_frames(poses, S.DEFAULT_AIM_X, S.SXI_FOV_W, S.SXI_FOV_H, S.SXI_W, S.SXI_H)
+    for f in fo:
+        allp = O.orc_trace_points(f, S.SXI_W, S.SXI_H, 200, 44).reshape(-1, 3)
+        assert (np.abs(allp - pts[0]).max(axis=1) < 1e-6).any() or (np.abs(allp - pts[1]).max(axis=1) < 1e-6).any()
+        full = D.sample_cmem(P, allp, 2)
+        assert_bit_exact(D.sample_cmem(P, allp, 3), full, "region filter")
+        assert_bit_exact(D.sample_cmem_table(P, tab, allp)[0], full, "region table + filter")
+
+
 @pytest.mark.parametrize("B", [0.05, 2.4e-9, 2.46e-9, 1e-6])
 def test_cmem_exponential_factor_of_b1(B):
     """CMEM::Init leaves B = |b| * 1e-9, for which expf(-B (theta/2)^4) is 1.0f for every theta and the kernel skips it
