@@ -88,14 +88,14 @@ enum {
                                    fewer per sample, measured +1.9 %); this flag keeps the general loop as the cross-check */
     BIRP_CMEM_LIBM32 = 262144,   /* CMEM only, diagnostic: the CUDA fp32 math library for every sample, no table, no filter
                                     (round 1's BIRP_CMEM_FAST; slower than the default) */
-    BIRP_CMEM_NO_TABLE = 131072, /* CMEM only: do not use the region table of the parameter set (per bin of cos(theta), bounds
-                                    of both radii over every phi: a sample far from both boundaries is classified by one
-                                    16-byte load instead of the fp32 radius estimates); identical results, kept as the
-                                    cross-check */
+    BIRP_CMEM_NO_TABLE = 131072, /* CMEM only: do not use the region table of the parameter set (256 x 64 cells over
+                                    cos(theta) x cos(phi), each with bounds of both radii over the cell and its neighbours:
+                                    a sample far from both boundaries is classified by one 16-byte load instead of the
+                                    fp32 radius estimates); identical results, kept as the cross-check */
     BIRP_FAST_MARCH = 32768,    /* DataCube, trilinear, opt-in: tolerance mode.  The default march is bit-identical to the
                                    reference Camera; with this flag the VALUE of an in-bounds sample is computed with fused
                                    arithmetic (one FFMA per coordinate, the cell's interpolant as a polynomial from one
-                                   32-byte record, the scale applied once per ray): 27 instead of 62 instructions per sample.
+                                   32-byte record, the scale applied once per ray): 28 instead of 60 instructions in the loop.
                                    Which steps are in bounds and where a ray ends are still decided with the reference's own
                                    arithmetic, so images agree with the reference to ~1e-6 relative per pixel (north_star's
                                    tolerance: 1e-5 per pixel, 1e-4 integrated flux).  Needs a further copy of the grid (8x,
